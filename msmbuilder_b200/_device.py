@@ -1,0 +1,145 @@
+"""Device-memory plumbing (PyTorch is used for allocation, streams and copies only)."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .utils import is_tensor
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device (or host) address of a tensor / ndarray, or NULL."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if is_tensor(t):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
+def dtype_id(t):
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.float64:
+        return _lib.F64
+    raise TypeError("frames must be float32 or float64 on the device, got %s" % t.dtype)
+
+
+def _float_dtype(dt):
+    """Reference policy (kcenters.py:80-82, tica.py:402 modulo storage width):
+    float32 and float64 are kept, everything else is widened to float64."""
+    if is_tensor(dt):
+        dt = dt.dtype
+    if dt in (torch.float32, np.dtype(np.float32), np.float32):
+        return torch.float32
+    return torch.float64
+
+
+def to_device(X, ndim=2):
+    """One array-like -> contiguous CUDA tensor (float32 or float64)."""
+    _lib.require_gpu()
+    if is_tensor(X):
+        want = _float_dtype(X.dtype)
+        t = X if X.dtype == want else X.to(want)
+        if not t.is_cuda:
+            t = t.cuda(non_blocking=True)
+        t = t.contiguous()
+    else:
+        a = np.asarray(X)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a).cuda()
+    if ndim == 2 and t.ndim == 1:
+        t = t.unsqueeze(0)
+    return t
+
+
+class FrameStore(object):
+    """The concatenation of a list of sequences as ONE (N, ...) device tensor.
+
+    Replaces MultiSequenceClusterMixin._concat's host np.concatenate
+    (msmbuilder/cluster/base.py:55-58): host arrays are copied straight into
+    their slot of the device buffer; device tensors that already sit back to
+    back in one allocation are adopted without a copy.
+    """
+
+    def __init__(self, sequences):
+        _lib.require_gpu()
+        seqs = list(sequences)
+        if len(seqs) == 0:
+            raise ValueError("no sequences")
+        self.lengths = [int(s.shape[0]) for s in seqs]
+        inner = tuple(seqs[0].shape[1:])
+        for s in seqs:
+            if tuple(s.shape[1:]) != inner:
+                raise ValueError("all sequences must have the same trailing shape")
+        dts = {_float_dtype(s.dtype) for s in seqs}
+        dtype = torch.float64 if torch.float64 in dts else torch.float32
+        self.offsets = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
+        n_total = int(self.offsets[-1])
+        row = int(np.prod(inner)) if inner else 1
+
+        adopted = None
+        if all(is_tensor(s) and s.is_cuda and s.dtype == dtype and s.is_contiguous()
+               for s in seqs) and n_total > 0:
+            base = seqs[0].data_ptr()
+            es = seqs[0].element_size()
+            if all(s.data_ptr() == base + int(o) * row * es
+                   for s, o in zip(seqs, self.offsets[:-1])):
+                try:
+                    adopted = seqs[0].as_strided((n_total,) + inner,
+                                                 torch.empty((n_total,) + inner, device="meta").stride())
+                except RuntimeError:
+                    adopted = None
+        if adopted is not None:
+            self.data = adopted
+        else:
+            self.data = torch.empty((n_total,) + inner, dtype=dtype, device="cuda")
+            for s, o, n in zip(seqs, self.offsets[:-1], self.lengths):
+                if n == 0:
+                    continue
+                dst = self.data[int(o):int(o) + n]
+                if is_tensor(s):
+                    dst.copy_(s, non_blocking=True)
+                else:
+                    a = np.asarray(s)
+                    if a.dtype not in (np.float32, np.float64):
+                        a = a.astype(np.float64)
+                    dst.copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=False)
+        self.n = n_total
+        self.inner = inner
+
+    def split(self, concat):
+        """cluster/base.py:76-77 on host arrays or device tensors."""
+        return [concat[int(o): int(o) + n] for o, n in zip(self.offsets[:-1], self.lengths)]
+
+
+class Workspace(object):
+    """Grow-only device scratch buffer keyed by purpose."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes):
+        nbytes = max(int(nbytes), 256)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes or not buf.is_cuda \
+                or buf.device != torch.device("cuda", torch.cuda.current_device()):
+            buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+            self._bufs[key] = buf
+        return buf
+
+
+_WS = None
+
+
+def workspace():
+    global _WS
+    if _WS is None:
+        _WS = Workspace()
+    return _WS

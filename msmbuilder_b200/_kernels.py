@@ -1,0 +1,264 @@
+"""Device-level wrappers: CUDA tensors in, CUDA tensors out, one C-ABI call each.
+
+Everything here launches on torch's current stream and returns without
+synchronising unless a Python scalar is requested.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import _device as dev
+
+_I64 = torch.int64
+
+
+def _rows_tensor(rows):
+    if rows is None:
+        return None
+    if isinstance(rows, torch.Tensor):
+        return rows.to(device="cuda", dtype=_I64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).cuda()
+
+
+# --------------------------------------------------------------------------- K2
+class KCentersState(object):
+    """Per-shard state of a k-centers run on a (n, d) device tensor (vector
+    metrics) or a centred (n, n_atoms, 3) tensor + traces (rmsd)."""
+
+    def __init__(self, data, metric, traces=None, row_offset=0):
+        _lib.require_gpu()
+        self.data = data
+        self.rmsd = (metric == "rmsd")
+        self.metric = None if self.rmsd else _lib.metric_id(metric)
+        self.traces = traces
+        self.n = int(data.shape[0])
+        self.row_offset = int(row_offset)
+        if self.rmsd:
+            self.n_atoms = int(data.shape[1])
+            self.row_elems = self.n_atoms * 3 + 1     # coords + trace
+            self.dtype = _lib.F32
+        else:
+            self.d = int(data.shape[1])
+            self.row_elems = self.d
+            self.dtype = dev.dtype_id(data)
+        lib = _lib.load()
+        self.cand_bytes = int(lib.msmb200_candidate_bytes(self.row_elems, self.dtype))
+        self.distances = torch.full((self.n,), float("inf"), dtype=torch.float64, device="cuda")
+        self.labels = torch.zeros((self.n,), dtype=torch.int32, device="cuda")
+        self.ws = torch.zeros(int(lib.msmb200_kcenters_workspace_bytes(0)), dtype=torch.uint8,
+                              device="cuda")
+        self.local = torch.zeros(self.cand_bytes, dtype=torch.uint8, device="cuda")
+
+    def payload_ptr(self, cand):
+        return ctypes.c_void_p(cand.data_ptr() + 16)
+
+    def seed(self, cand, local_row):
+        """Write the seed centre (kcenters.py:84) into candidate buffer `cand`."""
+        if self.rmsd:
+            flat = self.data.reshape(self.n, -1)
+            view = cand[16:16 + 4 * self.row_elems].view(torch.float32)
+            view[:self.n_atoms * 3].copy_(flat[local_row])
+            view[self.n_atoms * 3:].copy_(self.traces[local_row:local_row + 1])
+            hdr = cand[:16].view(torch.float64)
+            hdr[0] = float("inf")
+            cand[8:16].view(torch.int64)[0] = self.row_offset + int(local_row)
+        else:
+            _lib.call("msmb200_candidate_from_row", dev.ptr(self.data), int(local_row), self.d,
+                      self.d, self.dtype, self.row_offset, dev.ptr(cand), dev.stream_ptr())
+
+    def run_pass(self, center_cand, label, out_cand=None):
+        """One pass against the centre stored in `center_cand`; this shard's
+        farthest frame is written to `out_cand` (default: self.local)."""
+        out = self.local if out_cand is None else out_cand
+        if self.rmsd:
+            _lib.call("msmb200_rmsd_kcenters_pass", dev.ptr(self.data), dev.ptr(self.traces),
+                      self.n, self.n_atoms, self.payload_ptr(center_cand), int(label),
+                      dev.ptr(self.distances), dev.ptr(self.labels), self.row_offset,
+                      dev.ptr(out), dev.ptr(self.ws), self.ws.numel(), dev.stream_ptr())
+        else:
+            _lib.call("msmb200_kcenters_pass", dev.ptr(self.data), self.n, self.d, self.d,
+                      self.dtype, self.metric, self.payload_ptr(center_cand), int(label),
+                      dev.ptr(self.distances), dev.ptr(self.labels), self.row_offset,
+                      dev.ptr(out), dev.ptr(self.ws), self.ws.numel(), dev.stream_ptr())
+        return out
+
+    def select(self, gathered, n_cand, out_cand):
+        _lib.call("msmb200_candidate_select", dev.ptr(gathered), int(n_cand), self.cand_bytes,
+                  self.row_elems, self.dtype, dev.ptr(out_cand), dev.stream_ptr())
+
+
+def kcenters_fit(data, n_clusters, metric, seed_index, traces=None):
+    """Single-GPU Gonzalez k-centers (kcenters.py:79-102): k passes enqueued back
+    to back, the arg-max that names the next centre never leaves the device.
+
+    Returns (cluster_ids int64[k] tensor, distances f64[n], labels i32[n])."""
+    st = KCentersState(data, metric, traces=traces)
+    k = int(n_clusters)
+    # ring of k candidate slots: slot i holds centre i (its index is cluster_ids_[i])
+    ring = torch.zeros((k + 1, st.cand_bytes), dtype=torch.uint8, device="cuda")
+    st.seed(ring[0], int(seed_index))
+    for i in range(k):
+        st.run_pass(ring[i], i, out_cand=ring[i + 1])
+    ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
+    return ids, st.distances, st.labels
+
+
+# --------------------------------------------------------------------------- K3
+def assign_nearest(X, Y, metric, rows=None, want_min_dist=False):
+    """labels (i32), min_dist (f64 or None), inertia (0-d f64 tensor)."""
+    _lib.require_gpu()
+    lib = _lib.load()
+    rows_t = _rows_tensor(rows)
+    n_out = int(X.shape[0]) if rows_t is None else int(rows_t.numel())
+    labels = torch.empty((n_out,), dtype=torch.int32, device="cuda")
+    min_dist = torch.empty((n_out,), dtype=torch.float64, device="cuda") if want_min_dist else None
+    inertia = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    if n_out == 0:
+        return labels, min_dist, inertia[0]
+    if metric == "rmsd":
+        raise TypeError("use rmsd_assign_nearest for metric='rmsd'")
+    m = _lib.metric_id(metric)
+    if X.dtype != Y.dtype:
+        raise TypeError('X and y must be both float32 or float64')
+    d, k = int(X.shape[1]), int(Y.shape[0])
+    ws_bytes = int(lib.msmb200_assign_workspace_bytes(n_out, k, d))
+    ws = dev.workspace().get("assign", ws_bytes)
+    _lib.call("msmb200_assign_nearest", dev.ptr(X), int(X.shape[0]), d, d, dev.dtype_id(X),
+              dev.ptr(Y), k, m, dev.ptr(rows_t), n_out if rows_t is not None else 0,
+              dev.ptr(labels), dev.ptr(min_dist), dev.ptr(inertia), dev.ptr(ws), ws.numel(),
+              dev.stream_ptr())
+    return labels, min_dist, inertia[0]
+
+
+def rmsd_assign_nearest(xyz, traces, Y, Y_traces, rows=None, want_min_dist=False):
+    _lib.require_gpu()
+    rows_t = _rows_tensor(rows)
+    n_out = int(xyz.shape[0]) if rows_t is None else int(rows_t.numel())
+    labels = torch.empty((n_out,), dtype=torch.int32, device="cuda")
+    min_dist = torch.empty((n_out,), dtype=torch.float64, device="cuda") if want_min_dist else None
+    inertia = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    if n_out:
+        _lib.call("msmb200_rmsd_assign_nearest", dev.ptr(xyz), dev.ptr(traces),
+                  int(xyz.shape[0]), int(xyz.shape[1]), dev.ptr(Y), dev.ptr(Y_traces),
+                  int(Y.shape[0]), dev.ptr(rows_t), n_out if rows_t is not None else 0,
+                  dev.ptr(labels), dev.ptr(min_dist), dev.ptr(inertia), dev.stream_ptr())
+    return labels, min_dist, inertia[0]
+
+
+# --------------------------------------------------------------------------- K4
+def dist(X, y, metric, rows=None):
+    _lib.require_gpu()
+    rows_t = _rows_tensor(rows)
+    n_out = int(X.shape[0]) if rows_t is None else int(rows_t.numel())
+    out = torch.empty((n_out,), dtype=torch.float64, device="cuda")
+    if n_out:
+        _lib.call("msmb200_dist", dev.ptr(X), int(X.shape[0]), int(X.shape[1]), int(X.shape[1]),
+                  dev.dtype_id(X), dev.ptr(y), _lib.metric_id(metric), dev.ptr(rows_t),
+                  n_out if rows_t is not None else 0, dev.ptr(out), dev.stream_ptr())
+    return out
+
+
+def cdist(XA, XB, metric):
+    _lib.require_gpu()
+    out = torch.empty((int(XA.shape[0]), int(XB.shape[0])), dtype=torch.float64, device="cuda")
+    if out.numel():
+        _lib.call("msmb200_cdist", dev.ptr(XA), int(XA.shape[0]), dev.ptr(XB), int(XB.shape[0]),
+                  int(XA.shape[1]), dev.dtype_id(XA), _lib.metric_id(metric), dev.ptr(out),
+                  dev.stream_ptr())
+    return out
+
+
+def pdist(X, metric, rows=None):
+    _lib.require_gpu()
+    rows_t = _rows_tensor(rows)
+    m = int(X.shape[0]) if rows_t is None else int(rows_t.numel())
+    out = torch.empty((m * (m - 1) // 2,), dtype=torch.float64, device="cuda")
+    if out.numel():
+        _lib.call("msmb200_pdist", dev.ptr(X), int(X.shape[0]), int(X.shape[1]), int(X.shape[1]),
+                  dev.dtype_id(X), _lib.metric_id(metric), dev.ptr(rows_t),
+                  m if rows_t is not None else 0, dev.ptr(out), dev.stream_ptr())
+    return out
+
+
+def sumdist(X, metric, pairs):
+    _lib.require_gpu()
+    pairs_t = _rows_tensor(np.asarray(pairs).reshape(-1, 2) if not isinstance(pairs, torch.Tensor)
+                           else pairs)
+    out = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    _lib.call("msmb200_sumdist", dev.ptr(X), int(X.shape[0]), int(X.shape[1]), int(X.shape[1]),
+              dev.dtype_id(X), _lib.metric_id(metric), dev.ptr(pairs_t),
+              int(pairs_t.shape[0]), dev.ptr(out), dev.stream_ptr())
+    return out[0]
+
+
+# --------------------------------------------------------------------------- RMSD
+def rmsd_center(xyz):
+    """Centre frames IN PLACE (like Trajectory.center_coordinates, cluster/base.py:68)
+    and return the float32 traces."""
+    _lib.require_gpu()
+    traces = torch.empty((int(xyz.shape[0]),), dtype=torch.float32, device="cuda")
+    _lib.call("msmb200_rmsd_center", dev.ptr(xyz), int(xyz.shape[0]), int(xyz.shape[1]),
+              dev.ptr(traces), dev.stream_ptr())
+    return traces
+
+
+def rmsd_dist(xyz, traces, y, y_trace, rows=None):
+    _lib.require_gpu()
+    rows_t = _rows_tensor(rows)
+    n_out = int(xyz.shape[0]) if rows_t is None else int(rows_t.numel())
+    out = torch.empty((n_out,), dtype=torch.float64, device="cuda")
+    if n_out:
+        _lib.call("msmb200_rmsd_dist", dev.ptr(xyz), dev.ptr(traces), int(xyz.shape[0]),
+                  int(xyz.shape[1]), dev.ptr(y), ctypes.c_float(float(y_trace)), dev.ptr(rows_t),
+                  n_out if rows_t is not None else 0, dev.ptr(out), dev.stream_ptr())
+    return out
+
+
+def rmsd_pdist(xyz, traces, rows=None):
+    _lib.require_gpu()
+    rows_t = _rows_tensor(rows)
+    m = int(xyz.shape[0]) if rows_t is None else int(rows_t.numel())
+    out = torch.empty((m * (m - 1) // 2,), dtype=torch.float64, device="cuda")
+    if out.numel():
+        _lib.call("msmb200_rmsd_pdist", dev.ptr(xyz), dev.ptr(traces), int(xyz.shape[0]),
+                  int(xyz.shape[1]), dev.ptr(rows_t), m if rows_t is not None else 0,
+                  dev.ptr(out), dev.stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------- host k-medoids
+def kmedoids(n_clusters, distmatrix, n_pass, clusterid=None, random_state=None):
+    """_kmedoids.kmedoids (cluster/_kmedoids.pyx:23-107), n_pass == 0 only."""
+    if n_pass != 0:
+        raise NotImplementedError("only n_pass == 0 is on the hot path "
+                                  "(minibatchkmedoids.py:116-118)")
+    dm = np.ascontiguousarray(distmatrix, dtype=np.float64)
+    n_elements = int(1 + np.sqrt(8 * len(dm) + 1) / 2.0)
+    if len(dm) != (n_elements * (n_elements - 1) / 2):
+        raise ValueError('len(distmatrix)=%s is not a valid size of a condensed distance '
+                         'matrix, which should be of size (N*(N-1)/2) for some positive '
+                         'integer, N' % len(dm))
+    if n_clusters > n_elements:
+        raise ValueError('Number of clusters requested (%d) greater than '
+                         'number of elements (%d)' % (n_clusters, n_elements))
+    if clusterid is not None and len(clusterid) != n_elements:
+        raise ValueError('clusterid must be None or an array of length n_elements')
+    cid = np.zeros(n_elements, dtype=np.int64) if clusterid is None else \
+        np.array(clusterid, dtype=np.int64, copy=True)
+    err = ctypes.c_double(0.0)
+    ifound = ctypes.c_int64(0)
+    _lib.call("msmb200_kmedoids", int(n_clusters), n_elements, dev.ptr(dm), dev.ptr(cid),
+              ctypes.byref(err), ctypes.byref(ifound))
+    return cid.astype(np.intp, copy=False), err.value, int(ifound.value)
+
+
+def contigify_ids(ids):
+    """_kmedoids.contigify_ids (cluster/_kmedoids.pyx:110-117)."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    keys = np.zeros(max(len(ids), 1), dtype=np.int64)
+    n_keys = ctypes.c_int64(0)
+    _lib.call("msmb200_contigify_ids", dev.ptr(ids), len(ids), dev.ptr(keys),
+              ctypes.byref(n_keys))
+    return ids.astype(np.intp, copy=False), {int(keys[r]): r for r in range(n_keys.value)}

@@ -1,0 +1,8 @@
+"""Clusterers of the hot path (see msmbuilder/cluster/__init__.py for the full
+reference list; only the libdistance-driven assignment loops live here)."""
+from .base import MultiSequenceClusterMixin
+from .kcenters import KCenters
+from .minibatchkmedoids import MiniBatchKMedoids
+from .minibatchkmeans import MiniBatchKMeans
+
+__all__ = ['KCenters', 'MiniBatchKMedoids', 'MiniBatchKMeans', 'MultiSequenceClusterMixin']

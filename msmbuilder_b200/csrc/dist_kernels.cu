@@ -1,0 +1,562 @@
+// dist_kernels.cu -- vector-metric distance kernels of libmsmb200 (sm_100a).
+//
+//   K2  kcenters_pass      one Gonzalez pass: d(x_i, c), strict running min,
+//                          label update and the arg-max that names the next
+//                          centre, fused in ONE streaming read of X.
+//                          (replaces kcenters.py:92-97 + dist.hpp:44-60)
+//   K3  assign_nearest     arg-min over k centres, lowest index on ties
+//                          (replaces assign.hpp:50-91)
+//   K4  dist/cdist/pdist/sumdist (dist.hpp, cdist.hpp, pdist.hpp, sumdist.hpp)
+//
+// All of these are HBM-bound integer/byte-style streaming work (4*D + 8 bytes
+// per frame per pass): coalesced 16-byte loads, a sub-warp of G lanes per frame,
+// warp-shuffle reductions, grid sized as a multiple of the SM count.  No tensor
+// cores here by design.
+#include "common.cuh"
+
+namespace msmb {
+
+static constexpr int kThreads = 256;
+
+// A sub-warp "group" of G lanes (G = power of two <= 32) owns one frame / pair.
+// The loops below are written so that every lane of a warp executes the same
+// number of iterations (full-mask shuffles inside group_distance).
+#define MSMB_GROUP_SETUP()                                                             \
+    const int lane_in_group = threadIdx.x & (G - 1);                                   \
+    const int groups_per_warp = 32 / G;                                                \
+    const int group_in_warp = (threadIdx.x & 31) / G;                                  \
+    const long long warp_group0 =                                                      \
+        (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * groups_per_warp;   \
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) / G
+
+struct BlockCand {
+    double v;
+    long long i;
+};
+
+// Workspace layout for the pass: [unsigned counter | pad to 16 | BlockCand[grid]]
+static inline int pass_grid() { return sm_count() * 8; }
+
+// ---------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------
+template <typename T, int METRIC, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+kcenters_pass_kernel(const T *__restrict__ X, long long n, int d, long long ld,
+                     const T *__restrict__ center, int label,
+                     double *__restrict__ dist, int *__restrict__ labels,
+                     long long row_offset, BlockCand *__restrict__ block_cands,
+                     unsigned *__restrict__ counter, msmb200_candidate *__restrict__ out,
+                     int G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s_center = reinterpret_cast<T *>(smem_raw);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) s_center[j] = center[j];
+    __syncthreads();
+
+    MSMB_GROUP_SETUP();
+
+    ArgMax best;
+    best.v = -INFINITY;
+    best.i = 0x7fffffffffffffffLL;
+
+    // warp-uniform trip count: every lane joins every shuffle; out-of-range
+    // groups recompute the last row and discard it.
+    for (long long r0 = warp_group0; r0 < n; r0 += n_groups) {
+        const long long r_raw = r0 + group_in_warp;
+        const bool valid = r_raw < n;
+        const long long r = valid ? r_raw : n - 1;
+        double dv = group_distance<METRIC, T, VEC>(X + r * ld, s_center, d, lane_in_group, G);
+        if (valid && lane_in_group == 0) {
+            double cur = dist[r];
+            if (dv < cur) {          // strict: kcenters.py:93
+                cur = dv;
+                dist[r] = dv;
+                labels[r] = label;
+            }
+            if (cur > best.v) {      // rows visited in increasing order per thread
+                best.v = cur;
+                best.i = r;
+            }
+        }
+    }
+
+    // block arg-max (first index wins ties == np.argmax, kcenters.py:97)
+    __shared__ ArgMax s_warp[kThreads / 32];
+    __shared__ bool s_is_last;
+    best = argmax_warp(best);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        ArgMax b = (threadIdx.x < kThreads / 32) ? s_warp[threadIdx.x]
+                                                  : ArgMax{-INFINITY, 0x7fffffffffffffffLL};
+        b = argmax_warp(b);
+        if (threadIdx.x == 0) {
+            block_cands[blockIdx.x].v = b.v;
+            block_cands[blockIdx.x].i = b.i;
+            __threadfence();
+            unsigned ticket = atomicInc(counter, gridDim.x - 1);   // wraps to 0: self-resetting
+            s_is_last = (ticket == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+
+    // last block: reduce the per-block candidates, publish winner + its row
+    __threadfence();
+    ArgMax w{-INFINITY, 0x7fffffffffffffffLL};
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        ArgMax c;
+        c.v = __ldcg(&block_cands[b].v);
+        c.i = __ldcg(&block_cands[b].i);
+        w = argmax_merge(w, c);
+    }
+    w = argmax_warp(w);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        ArgMax b = (threadIdx.x < kThreads / 32) ? s_warp[threadIdx.x]
+                                                  : ArgMax{-INFINITY, 0x7fffffffffffffffLL};
+        b = argmax_warp(b);
+        if (threadIdx.x == 0) s_warp[0] = b;
+    }
+    __syncthreads();
+    w = s_warp[0];
+    if (w.i == 0x7fffffffffffffffLL) w.i = 0;   // n == 0 or all-NaN shard
+    if (threadIdx.x == 0) {
+        out->value = w.v;
+        out->index = row_offset + w.i;
+    }
+    T *payload = reinterpret_cast<T *>(out + 1);
+    if (n > 0)
+        for (int j = threadIdx.x; j < d; j += blockDim.x) payload[j] = X[w.i * ld + j];
+}
+
+template <typename T>
+__global__ void candidate_select_kernel(const unsigned char *__restrict__ cands, int n_cand,
+                                        size_t stride, int row_elems,
+                                        msmb200_candidate *__restrict__ out)
+{
+    __shared__ int s_win;
+    if (threadIdx.x == 0) {
+        int win = 0;
+        const msmb200_candidate *c0 = reinterpret_cast<const msmb200_candidate *>(cands);
+        double bv = c0->value;
+        long long bi = c0->index;
+        for (int r = 1; r < n_cand; ++r) {
+            const msmb200_candidate *c =
+                reinterpret_cast<const msmb200_candidate *>(cands + (size_t)r * stride);
+            if (c->value > bv || (c->value == bv && c->index < bi)) {
+                bv = c->value;
+                bi = c->index;
+                win = r;
+            }
+        }
+        s_win = win;
+        out->value = bv;
+        out->index = bi;
+    }
+    __syncthreads();
+    const T *src = reinterpret_cast<const T *>(cands + (size_t)s_win * stride + sizeof(msmb200_candidate));
+    T *dst = reinterpret_cast<T *>(out + 1);
+    for (int j = threadIdx.x; j < row_elems; j += blockDim.x) dst[j] = src[j];
+}
+
+template <typename T>
+__global__ void candidate_from_row_kernel(const T *__restrict__ X, long long row, int d,
+                                          long long ld, long long row_offset,
+                                          msmb200_candidate *__restrict__ out)
+{
+    if (threadIdx.x == 0) {
+        out->value = INFINITY;
+        out->index = row_offset + row;
+    }
+    T *dst = reinterpret_cast<T *>(out + 1);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) dst[j] = X[row * ld + j];
+}
+
+// ---------------------------------------------------------------------------
+// K3 (exact engine): one sub-warp per frame scans all k centres in float64,
+// exactly the reference arithmetic; strict '<' keeps the lowest centre index.
+// ---------------------------------------------------------------------------
+template <typename T, int METRIC, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+assign_exact_kernel(const T *__restrict__ X, long long n_out, int d, long long ld,
+                    const T *__restrict__ Y, int k, const long long *__restrict__ rows,
+                    int *__restrict__ labels, double *__restrict__ min_dist,
+                    double *__restrict__ block_sums, int G)
+{
+    MSMB_GROUP_SETUP();
+    double local = 0.0;
+    for (long long i0 = warp_group0; i0 < n_out; i0 += n_groups) {
+        const long long i_raw = i0 + group_in_warp;
+        const bool valid = i_raw < n_out;
+        const long long i = valid ? i_raw : n_out - 1;
+        const long long r = rows ? rows[i] : i;
+        const T *u = X + r * ld;
+        double best = 1.7976931348623157e308;   // DBL_MAX, assign.hpp:66
+        int arg = 0;
+        for (int j = 0; j < k; ++j) {
+            double dv = group_distance<METRIC, T, VEC, false>(u, Y + (long long)j * d, d,
+                                                              lane_in_group, G);
+            if (dv < best) {
+                best = dv;
+                arg = j;
+            }
+        }
+        if (valid && lane_in_group == 0) {
+            labels[i] = arg;
+            if (min_dist) min_dist[i] = best;
+            local += best;
+        }
+    }
+    // deterministic inertia: fixed-order block partials, summed by a second kernel
+    __shared__ double s_sum[kThreads / 32];
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) s += s_sum[w];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+__global__ void sum_partials_kernel(const double *__restrict__ partials, int n, double *out)
+{
+    __shared__ double s[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s[w];
+        *out = t;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4: dist (one-to-many), pair kernels (cdist / pdist / sumdist)
+// ---------------------------------------------------------------------------
+template <typename T, int METRIC, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+dist_kernel(const T *__restrict__ X, long long n_out, int d, long long ld,
+            const T *__restrict__ y, const long long *__restrict__ rows,
+            double *__restrict__ out, int G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s_y = reinterpret_cast<T *>(smem_raw);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) s_y[j] = y[j];
+    __syncthreads();
+    MSMB_GROUP_SETUP();
+    for (long long i0 = warp_group0; i0 < n_out; i0 += n_groups) {
+        const long long i_raw = i0 + group_in_warp;
+        const bool valid = i_raw < n_out;
+        const long long i = valid ? i_raw : n_out - 1;
+        const long long r = rows ? rows[i] : i;
+        double dv = group_distance<METRIC, T, VEC>(X + r * ld, s_y, d, lane_in_group, G);
+        if (valid && lane_in_group == 0) out[i] = dv;
+    }
+}
+
+// MODE 0: cdist  (pair p -> (p / nb, p % nb), A rows from XA, B rows from XB)
+// MODE 1: pdist  (pair p -> condensed (i, j), i < j, optional row gather)
+// MODE 2: sumdist (explicit pairs; per-block partial sums)
+template <typename T, int METRIC, bool VEC, int MODE>
+__global__ void __launch_bounds__(kThreads)
+pair_kernel(const T *__restrict__ XA, const T *__restrict__ XB, long long n_pairs,
+            long long na, long long nb, int d, long long ld,
+            const long long *__restrict__ idx, double *__restrict__ out,
+            double *__restrict__ block_sums, int G)
+{
+    MSMB_GROUP_SETUP();
+    double local = 0.0;
+    for (long long p0 = warp_group0; p0 < n_pairs; p0 += n_groups) {
+        const long long p_raw = p0 + group_in_warp;
+        const bool valid = p_raw < n_pairs;
+        const long long p = valid ? p_raw : n_pairs - 1;
+        long long ia, ib;
+        if (MODE == 0) {
+            ia = p / nb;
+            ib = p % nb;
+        } else if (MODE == 1) {
+            // invert p = m*i - i*(i+1)/2 + (j - i - 1), m = na (pdist.hpp:84-95 order)
+            const double m = (double)na;
+            long long i = (long long)floor(((2.0 * m - 1.0) - sqrt((2.0 * m - 1.0) * (2.0 * m - 1.0) - 8.0 * (double)p)) * 0.5);
+            if (i < 0) i = 0;
+            // fix floating-point off-by-one
+            while (i > 0 && na * i - i * (i + 1) / 2 > p) --i;
+            while (na * (i + 1) - (i + 1) * (i + 2) / 2 <= p) ++i;
+            long long j = p - (na * i - i * (i + 1) / 2) + i + 1;
+            ia = idx ? idx[i] : i;
+            ib = idx ? idx[j] : j;
+        } else {
+            ia = idx[2 * p];
+            ib = idx[2 * p + 1];
+        }
+        double dv = group_distance<METRIC, T, VEC, false>(XA + ia * ld, XB + ib * ld, d,
+                                                          lane_in_group, G);
+        if (valid && lane_in_group == 0) {
+            if (MODE == 2) local += dv;
+            else out[p] = dv;
+        }
+    }
+    if (MODE == 2) {
+        __shared__ double s_sum[kThreads / 32];
+        for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+        if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < kThreads / 32; ++w) s += s_sum[w];
+            block_sums[blockIdx.x] = s;
+        }
+    }
+}
+
+template <typename T>
+static bool vec_ok(const void *a, const void *b, int d, long long ld)
+{
+    constexpr int N = Vec<T>::N;
+    return (d % N == 0) && (ld % N == 0) && aligned16(a) && (b == nullptr || aligned16(b));
+}
+
+static inline int grid_for(long long groups_needed, int G)
+{
+    long long per_block = kThreads / G;
+    long long blocks = (groups_needed + per_block - 1) / per_block;
+    long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace msmb
+
+using namespace msmb;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" size_t msmb200_candidate_bytes(int row_elems, int dtype)
+{
+    size_t es = dtype == MSMB200_F64 ? 8 : 4;
+    size_t b = sizeof(msmb200_candidate) + (size_t)row_elems * es;
+    return (b + 15) & ~(size_t)15;
+}
+
+extern "C" size_t msmb200_kcenters_workspace_bytes(int device)
+{
+    (void)device;
+    // counter (16 B) + one BlockCand per block; generous upper bound on the grid
+    return 16 + sizeof(BlockCand) * (size_t)(8 * 256);
+}
+
+extern "C" int msmb200_kcenters_pass(const void *X, int64_t n, int d, int64_t ld, int dtype,
+                                     int metric, const void *center, int32_t center_label,
+                                     double *distances, int32_t *labels, int64_t row_offset,
+                                     msmb200_candidate *out, void *workspace,
+                                     size_t workspace_bytes, void *stream)
+{
+    MSMB_REQUIRE(n >= 0 && d > 0 && ld >= d, "kcenters_pass: bad shape n=%lld d=%d ld=%lld",
+                 (long long)n, d, (long long)ld);
+    MSMB_REQUIRE(X && center && distances && labels && out && workspace,
+                 "kcenters_pass: null pointer");
+    const int grid_cap = pass_grid();
+    MSMB_REQUIRE(workspace_bytes >= 16 + sizeof(BlockCand) * (size_t)grid_cap,
+                 "kcenters_pass: workspace too small (%zu)", workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned *counter = reinterpret_cast<unsigned *>(workspace);
+    BlockCand *cands = reinterpret_cast<BlockCand *>(reinterpret_cast<unsigned char *>(workspace) + 16);
+    return dispatch(dtype, metric, [&](auto t, auto m) -> int {
+        typedef decltype(t) T;
+        constexpr int METRIC = decltype(m)::value;
+        const bool vec = vec_ok<T>(X, nullptr, d, ld);
+        const int G = lanes_per_row(d, Vec<T>::N, vec);
+        int grid = grid_for(n, G);
+        if (grid > grid_cap) grid = grid_cap;
+        // the self-resetting ticket counter needs a stable grid per workspace
+        // only within one launch, so any grid size is fine.
+        size_t smem = (size_t)d * sizeof(T);
+        smem = (smem + 15) & ~(size_t)15;
+        if (vec)
+            kcenters_pass_kernel<T, METRIC, true><<<grid, kThreads, smem, st>>>(
+                (const T *)X, n, d, ld, (const T *)center, center_label, distances, labels,
+                row_offset, cands, counter, out, G);
+        else
+            kcenters_pass_kernel<T, METRIC, false><<<grid, kThreads, smem, st>>>(
+                (const T *)X, n, d, ld, (const T *)center, center_label, distances, labels,
+                row_offset, cands, counter, out, G);
+        MSMB_LAUNCH_CHECK();
+        return MSMB200_OK;
+    });
+}
+
+extern "C" int msmb200_candidate_select(const void *cands, int n_cand, size_t stride_bytes,
+                                        int row_elems, int dtype, msmb200_candidate *out,
+                                        void *stream)
+{
+    MSMB_REQUIRE(cands && out && n_cand > 0 && row_elems >= 0, "candidate_select: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MSMB200_F64)
+        candidate_select_kernel<double><<<1, 128, 0, st>>>((const unsigned char *)cands, n_cand,
+                                                          stride_bytes, row_elems, out);
+    else
+        candidate_select_kernel<float><<<1, 128, 0, st>>>((const unsigned char *)cands, n_cand,
+                                                         stride_bytes, row_elems, out);
+    MSMB_LAUNCH_CHECK();
+    return MSMB200_OK;
+}
+
+extern "C" int msmb200_candidate_from_row(const void *X, int64_t row, int d, int64_t ld,
+                                          int dtype, int64_t row_offset,
+                                          msmb200_candidate *out, void *stream)
+{
+    MSMB_REQUIRE(X && out && row >= 0 && d > 0, "candidate_from_row: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MSMB200_F64)
+        candidate_from_row_kernel<double><<<1, 128, 0, st>>>((const double *)X, row, d, ld,
+                                                            row_offset, out);
+    else
+        candidate_from_row_kernel<float><<<1, 128, 0, st>>>((const float *)X, row, d, ld,
+                                                           row_offset, out);
+    MSMB_LAUNCH_CHECK();
+    return MSMB200_OK;
+}
+
+extern "C" size_t msmb200_assign_workspace_bytes(int64_t n_out, int k, int d)
+{
+    (void)n_out; (void)k; (void)d;
+    return sizeof(double) * (size_t)(8 * 256) + 256;
+}
+
+extern "C" int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t ld, int dtype,
+                                      const void *Y, int k, int metric, const int64_t *rows,
+                                      int64_t n_rows, int32_t *labels, double *min_dist,
+                                      double *inertia, void *workspace, size_t workspace_bytes,
+                                      void *stream)
+{
+    MSMB_REQUIRE(d > 0 && k > 0 && ld >= d && n >= 0, "assign_nearest: bad shape");
+    MSMB_REQUIRE(X && Y && labels && workspace, "assign_nearest: null pointer");
+    const int64_t n_out = rows ? n_rows : n;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partials = reinterpret_cast<double *>(workspace);
+    return dispatch(dtype, metric, [&](auto t, auto m) -> int {
+        typedef decltype(t) T;
+        constexpr int METRIC = decltype(m)::value;
+        const bool vec = vec_ok<T>(X, Y, d, ld);
+        const int G = lanes_per_row(d, Vec<T>::N, vec);
+        const int grid = grid_for(n_out, G);
+        MSMB_REQUIRE(workspace_bytes >= sizeof(double) * (size_t)grid,
+                     "assign_nearest: workspace too small");
+        if (vec)
+            assign_exact_kernel<T, METRIC, true><<<grid, kThreads, 0, st>>>(
+                (const T *)X, n_out, d, ld, (const T *)Y, k, (const long long *)rows, labels,
+                min_dist, partials, G);
+        else
+            assign_exact_kernel<T, METRIC, false><<<grid, kThreads, 0, st>>>(
+                (const T *)X, n_out, d, ld, (const T *)Y, k, (const long long *)rows, labels,
+                min_dist, partials, G);
+        MSMB_LAUNCH_CHECK();
+        if (inertia) {
+            sum_partials_kernel<<<1, 256, 0, st>>>(partials, grid, inertia);
+            MSMB_LAUNCH_CHECK();
+        }
+        return MSMB200_OK;
+    });
+}
+
+extern "C" int msmb200_dist(const void *X, int64_t n, int d, int64_t ld, int dtype,
+                            const void *y, int metric, const int64_t *rows, int64_t n_rows,
+                            double *out, void *stream)
+{
+    MSMB_REQUIRE(d > 0 && ld >= d && n >= 0 && X && y && out, "dist: bad args");
+    const int64_t n_out = rows ? n_rows : n;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dispatch(dtype, metric, [&](auto t, auto m) -> int {
+        typedef decltype(t) T;
+        constexpr int METRIC = decltype(m)::value;
+        const bool vec = vec_ok<T>(X, nullptr, d, ld);
+        const int G = lanes_per_row(d, Vec<T>::N, vec);
+        const int grid = grid_for(n_out, G);
+        size_t smem = ((size_t)d * sizeof(T) + 15) & ~(size_t)15;
+        if (vec)
+            dist_kernel<T, METRIC, true><<<grid, kThreads, smem, st>>>(
+                (const T *)X, n_out, d, ld, (const T *)y, (const long long *)rows, out, G);
+        else
+            dist_kernel<T, METRIC, false><<<grid, kThreads, smem, st>>>(
+                (const T *)X, n_out, d, ld, (const T *)y, (const long long *)rows, out, G);
+        MSMB_LAUNCH_CHECK();
+        return MSMB200_OK;
+    });
+}
+
+template <int MODE>
+static int launch_pairs(const void *XA, const void *XB, long long n_pairs, long long na,
+                        long long nb, int d, long long ld, int dtype, int metric,
+                        const int64_t *idx, double *out, cudaStream_t st)
+{
+    return dispatch(dtype, metric, [&](auto t, auto m) -> int {
+        typedef decltype(t) T;
+        constexpr int METRIC = decltype(m)::value;
+        const bool vec = vec_ok<T>(XA, XB, d, ld);
+        const int G = lanes_per_row(d, Vec<T>::N, vec);
+        const int grid = grid_for(n_pairs, G);
+        double *partials = nullptr;
+        if (MODE == 2) {
+            MSMB_CUDA(cudaMallocAsync(&partials, sizeof(double) * grid, st));
+        }
+        if (vec)
+            pair_kernel<T, METRIC, true, MODE><<<grid, kThreads, 0, st>>>(
+                (const T *)XA, (const T *)XB, n_pairs, na, nb, d, ld, (const long long *)idx,
+                out, partials, G);
+        else
+            pair_kernel<T, METRIC, false, MODE><<<grid, kThreads, 0, st>>>(
+                (const T *)XA, (const T *)XB, n_pairs, na, nb, d, ld, (const long long *)idx,
+                out, partials, G);
+        MSMB_LAUNCH_CHECK();
+        if (MODE == 2) {
+            sum_partials_kernel<<<1, 256, 0, st>>>(partials, grid, out);
+            MSMB_LAUNCH_CHECK();
+            MSMB_CUDA(cudaFreeAsync(partials, st));
+        }
+        return MSMB200_OK;
+    });
+}
+
+extern "C" int msmb200_cdist(const void *XA, int64_t na, const void *XB, int64_t nb, int d,
+                             int dtype, int metric, double *out, void *stream)
+{
+    MSMB_REQUIRE(XA && XB && out && d > 0 && na >= 0 && nb >= 0, "cdist: bad args");
+    if (na == 0 || nb == 0) return MSMB200_OK;
+    return launch_pairs<0>(XA, XB, na * nb, na, nb, d, d, dtype, metric, nullptr, out,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int msmb200_pdist(const void *X, int64_t n, int d, int64_t ld, int dtype,
+                             int metric, const int64_t *rows, int64_t n_rows, double *out,
+                             void *stream)
+{
+    MSMB_REQUIRE(X && out && d > 0 && ld >= d, "pdist: bad args");
+    const long long m = rows ? n_rows : n;
+    if (m < 2) return MSMB200_OK;
+    return launch_pairs<1>(X, X, m * (m - 1) / 2, m, m, d, ld, dtype, metric, rows, out,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int msmb200_sumdist(const void *X, int64_t n, int d, int64_t ld, int dtype,
+                               int metric, const int64_t *pairs, int64_t p, double *out,
+                               void *stream)
+{
+    (void)n;
+    MSMB_REQUIRE(X && out && pairs && d > 0 && ld >= d && p >= 0, "sumdist: bad args");
+    if (p == 0) {
+        MSMB_CUDA(cudaMemsetAsync(out, 0, sizeof(double), (cudaStream_t)stream));
+        return MSMB200_OK;
+    }
+    return launch_pairs<2>(X, X, p, 0, 0, d, ld, dtype, metric, pairs, out,
+                           (cudaStream_t)stream);
+}

@@ -1,0 +1,104 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE.  Writes tests/golden/*.npz.
+
+Runs the reference's OWN code (verbatim tica.py / kcenters.py /
+minibatchkmedoids.py through oracle/ref_loader.py, and its libdistance C++
+through oracle/_ref/libref.so) on seeded inputs and stores inputs' seeds +
+outputs.  Only runnable where /root/reference exists (the build container);
+the fixtures travel, the reference does not.
+
+    python -m oracle.gen_golden
+"""
+import os
+import warnings
+
+import numpy as np
+
+from . import ref_loader
+from . import libdistance_oracle as lo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def tica_inputs(seed, n_seq, length, D, dtype):
+    from msmbuilder_b200.synthetic import ar1_numpy
+    seqs = ar1_numpy(n_seq, length, D, seed=seed, dtype=dtype)
+    return seqs
+
+
+def gen_tica():
+    tICA = ref_loader.load_tica()
+    cases = [
+        dict(name="tica_d6_lag3", seed=11, n_seq=4, length=700, D=6, lag=3, k=3, shrinkage=None,
+             dtype="float32", short=[2]),
+        dict(name="tica_d16_lag10", seed=12, n_seq=3, length=1500, D=16, lag=10, k=4, shrinkage=None,
+             dtype="float32", short=[]),
+        dict(name="tica_d64_lag10_f64", seed=13, n_seq=2, length=2500, D=64, lag=10, k=4,
+             shrinkage=0.0, dtype="float64", short=[]),
+        dict(name="tica_d256_lag10", seed=14, n_seq=2, length=3000, D=256, lag=10, k=4,
+             shrinkage=None, dtype="float32", short=[5]),
+    ]
+    for c in cases:
+        seqs = tica_inputs(c["seed"], c["n_seq"], c["length"], c["D"], np.dtype(c["dtype"]))
+        for n_short in c["short"]:
+            seqs.insert(1, seqs[0][:n_short].copy())    # a too-short sequence: skipped, not counted
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = tICA(n_components=c["k"], lag_time=c["lag"], shrinkage=c["shrinkage"]).fit(seqs)
+            proj = m.transform([seqs[0][:50]])[0]
+        np.savez_compressed(
+            os.path.join(GOLD, c["name"] + ".npz"),
+            seed=c["seed"], n_seq=c["n_seq"], length=c["length"], D=c["D"], lag=c["lag"],
+            k=c["k"], shrinkage=np.nan if c["shrinkage"] is None else c["shrinkage"],
+            dtype=c["dtype"], short=np.array(c["short"], dtype=np.int64),
+            eigenvalues=m.eigenvalues_, eigenvectors=m.eigenvectors_, means=m.means_,
+            timescales=m.timescales_, n_observations=m.n_observations_,
+            n_sequences=m.n_sequences_, shrinkage_=m.shrinkage_,
+            C_tau=m._outer_0_to_T_lagged, C_00=m._outer_0_to_TminusTau,
+            C_tt=m._outer_offset_to_T, S_0=m._sum_0_to_TminusTau, S_tau=m._sum_tau_to_T,
+            S=m._sum_0_to_T, proj50=proj)
+        print("wrote", c["name"], m.eigenvalues_)
+
+
+def cluster_inputs(seed, n_seq, length, D, dtype):
+    rs = np.random.RandomState(seed)
+    centers = rs.randn(7, D) * 3
+    return [(centers[rs.randint(0, 7, size=length)] + rs.randn(length, D)).astype(dtype)
+            for _ in range(n_seq)]
+
+
+def gen_cluster():
+    KCenters, MiniBatchKMedoids, _ = ref_loader.load_cluster()
+    out = {}
+    for metric in lo.VECTOR_METRICS:
+        for dtype in ("float32", "float64"):
+            seqs = cluster_inputs(21, 3, 400, 5, np.dtype(dtype))
+            if metric in ("hamming", "jaccard"):
+                seqs = [np.round(s).astype(dtype) for s in seqs]
+            kc = KCenters(n_clusters=9, metric=metric, random_state=3).fit(seqs)
+            key = "kc_%s_%s_" % (metric, dtype)
+            out[key + "ids"] = np.array(kc.cluster_ids_)
+            out[key + "labels"] = np.concatenate(kc.labels_)
+            out[key + "distances"] = np.concatenate(kc.distances_)
+            out[key + "inertia"] = kc.inertia_
+            out[key + "predict"] = np.concatenate(kc.predict(seqs))
+            mb = MiniBatchKMedoids(n_clusters=6, batch_size=40, max_iter=3, metric=metric,
+                                   random_state=5).fit(seqs)
+            key = "mb_%s_%s_" % (metric, dtype)
+            out[key + "ids"] = np.array(mb.cluster_ids_)
+            out[key + "labels"] = np.concatenate(mb.labels_)
+            out[key + "inertia"] = mb.inertia_
+    np.savez_compressed(os.path.join(GOLD, "cluster_small.npz"), **out)
+    print("wrote cluster_small with", len(out), "arrays")
+
+
+def main():
+    if not ref_loader.available():
+        raise SystemExit("reference tree absent: goldens can only be generated in the build container")
+    os.makedirs(GOLD, exist_ok=True)
+    gen_tica()
+    gen_cluster()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,74 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports every symbol that
+include/msmb200.h declares; the host-only entry points (k-medoids) are checked
+against the oracle here because they need no device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from msmbuilder_b200 import _lib
+from oracle import libdistance_oracle as lo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "msmb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msmb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), "libmsmb200.so does not export %s" % s
+        assert s in _lib.SIGNATURES, "python binding table lacks %s" % s
+    assert set(_lib.SIGNATURES) == set(syms)
+
+
+def test_version_and_sizes():
+    lib = _lib.load()
+    assert lib.msmb200_abi_version() == 1
+    assert lib.msmb200_tica_acc_len(256) == 3 * 256 * 256 + 3 * 256 + 2
+    assert lib.msmb200_candidate_bytes(256, _lib.F32) == 16 + 1024
+    assert lib.msmb200_candidate_bytes(3, _lib.F64) % 16 == 0
+
+
+def test_no_cpu_fallback_is_loud():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from msmbuilder_b200.decomposition import tICA
+    from msmbuilder_b200.cluster import KCenters
+    with pytest.raises(_lib.Msmb200Error):
+        tICA(lag_time=1).fit([np.random.randn(50, 3)])
+    with pytest.raises(_lib.Msmb200Error):
+        KCenters(n_clusters=2).fit([np.random.randn(50, 3)])
+
+
+def test_host_kmedoids_matches_oracle():
+    from msmbuilder_b200 import _kernels as K
+    rs = np.random.RandomState(0)
+    for trial in range(30):
+        n, k = rs.randint(6, 80), rs.randint(2, 8)
+        X = rs.randn(n, 3)
+        if trial % 4 == 0:
+            X = np.round(X)
+        dm = lo.pdist(X, "euclidean")
+        cid = rs.randint(0, k, n)
+        cid[:k] = np.arange(k)
+        a = K.kmedoids(k, dm, 0, cid)
+        b = lo.kmedoids(k, dm, 0, cid)
+        np.testing.assert_array_equal(a[0], b[0])
+        assert a[1] == b[1] and a[2] == b[2]
+        ca, cb = K.contigify_ids(a[0].copy()), lo.contigify_ids(b[0].copy())
+        np.testing.assert_array_equal(ca[0], cb[0])
+        assert ca[1] == cb[1]
+    with pytest.raises(ValueError):
+        K.kmedoids(3, np.zeros(4), 0, None)          # not a triangular number
+    with pytest.raises(ValueError):
+        K.kmedoids(9, np.zeros(3), 0, None)          # more clusters than elements
