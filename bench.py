@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the hot path: tICA fit + KCenters assign.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+
+Workload (BASELINE.json metric "frames/sec tICA fit + KCenters assign, 50M x 256
+f32"): S sequences x 100,000 frames x 256 float32 features, seeded AR(1) data
+generated on the device (msmbuilder_b200/synthetic.py).  One STEP is one pass of
+the hot path over all frames:
+
+  1. tICA(lag_time=10).fit  -> the covariance accumulation K1 over every sequence
+     (tica.py:401-424; the eigensolve is lazy in the reference too and is not part
+     of fit), plus the all-reduce of the packed accumulator when N > 1;
+  2. KCenters(n_clusters=k).fit -> k fused distance/assign passes K2 over every
+     frame (kcenters.py:91-97), labels + distances + centre ids produced.
+
+`value` = total frames / step time with the frames already resident in HBM
+(CUDA events, max over ranks).  `e2e` = the same two estimator calls through the
+public Python API on HOST (pinned) arrays: H2D of the frames and D2H of the
+results inside the timed region, on a bounded number of frames (`e2e.frames`).
+N > 1 shards the same 50M frames across ranks (strong scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=50_000_000)
+    ap.add_argument("--features", type=int, default=256)
+    ap.add_argument("--seq-len", type=int, default=100_000)
+    ap.add_argument("--lag", type=int, default=10)
+    ap.add_argument("--k", type=int, default=8, help="KCenters n_clusters (reference default 8)")
+    ap.add_argument("--engine", default="auto")
+    ap.add_argument("--e2e-frames", type=int, default=4_000_000)
+    ap.add_argument("--cpu-frames", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_burst=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = device_index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            pw = [float(r[3]) for r in rows if len(r) >= 9]
+            out["samples"] = len(sm)
+            if sm:
+                loaded = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+                out["sm_mhz"] = float(np.median(loaded))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(pw)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for j, nm in enumerate(names):
+                if any(len(r) >= 9 and r[5 + j].strip().lower() == "active" for r in rows):
+                    out["reasons"].append(nm)
+        except Exception as e:  # pragma: no cover
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_hot_path(seqs, lag, k, use_ref):
+    """The reference CPU path on host arrays: tICA accumulation in NumPy float64
+    (oracle port of tica.py:401-424, all BLAS threads) + k KCenters passes through
+    the reference's own single-threaded libdistance C++ (oracle/_ref) or its port.
+    Returns (seconds_tica, seconds_kcenters)."""
+    import warnings
+    from oracle.tica_oracle import TicaOracle
+    from oracle import cluster_oracle as co
+    from oracle import libdistance_oracle as lo
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        TicaOracle(n_components=4, lag_time=lag).fit(seqs)
+    t1 = time.perf_counter()
+    X = np.concatenate(seqs)            # cluster/base.py:58 (the reference concatenates on the host)
+    co.kcenters_fit(X, k, "euclidean", random_state=0, impl="reference" if use_ref else "port")
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def host_sample(n_frames, seq_len, D, seed):
+    """Seeded host sample of the same workload (device-generated when a GPU exists)."""
+    n_seq = max(1, n_frames // seq_len)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from msmbuilder_b200.synthetic import ar1_device
+            x = ar1_device(n_seq, seq_len, D, seed=seed).cpu().numpy()
+            torch.cuda.empty_cache()
+            return [x[i * seq_len:(i + 1) * seq_len] for i in range(n_seq)]
+    except Exception:
+        pass
+    from msmbuilder_b200.synthetic import ar1_numpy
+    return ar1_numpy(n_seq, seq_len, D, seed=seed)
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import libdistance_oracle as lo
+    use_ref = lo.have_reference()
+    seqs = host_sample(args.cpu_frames, args.seq_len, args.features, seed=1000)
+    n = sum(len(s) for s in seqs)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_hot_path(seqs[:1], args.lag, 1, use_ref)
+    times = []
+    for _ in range(args.steps):
+        a, b = cpu_hot_path(seqs, args.lag, args.k, use_ref)
+        times.append(a + b)
+    ms = 1e3 * float(np.mean(times))
+    value = n / (ms / 1e3)
+    sample = ("%d frames x %d f32 (%d sequences), tICA NumPy f64 on %d BLAS threads + %d KCenters "
+              "passes on 1 thread (%s)" % (n, args.features, len(seqs), cpu_threads(), args.k,
+                                           "reference C++ via oracle/_ref" if use_ref else "oracle port"))
+    line = {
+        "impl": "reference", "metric": "frames/sec tICA fit + KCenters assign", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count(),
+                         "kind": "reference" if use_ref else "port", "sample": sample,
+                         "blas_threads": cpu_threads()},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, ws):
+    return {"workload": "tICA(lag_time=%d).fit + KCenters(n_clusters=%d, 'euclidean').fit on %d x %d "
+                        "float32 frames (%d sequences x %d)" % (
+                            args.lag, args.k, args.frames, args.features,
+                            args.frames // args.seq_len, args.seq_len),
+            "frames": args.frames, "features": args.features, "lag_time": args.lag,
+            "n_clusters": args.k, "seq_len": args.seq_len, "sharding": "frames/%d" % ws,
+            "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2" % (
+                args.frames / ws * args.features * 4 / 1e9)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from msmbuilder_b200 import _lib, parallel as par
+    from msmbuilder_b200 import _device as dev
+    from msmbuilder_b200.synthetic import ar1_device
+    from msmbuilder_b200.decomposition import tICA
+    from msmbuilder_b200.cluster import KCenters
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.require_gpu()
+    lib = _lib.load()
+    D, L, lag, k = args.features, args.seq_len, args.lag, args.k
+    n_seq_total = args.frames // L
+    seq_ranges = par.shard_rows(n_seq_total, ws)
+    s0, s1 = seq_ranges[rank]
+    n_seq = s1 - s0
+    n_local = n_seq * L
+    n_total = n_seq_total * L
+    row_offset = s0 * L
+
+    X = ar1_device(n_seq, L, D, seed=1000 + rank)
+    torch.cuda.synchronize()
+    seqs = [X[i * L:(i + 1) * L] for i in range(n_seq)]
+    est = tICA(n_components=4, lag_time=lag, engine=args.engine)
+    est._initialize(D)
+    acc = torch.zeros(int(lib.msmb200_tica_acc_len(D)), dtype=torch.float64, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    phase_ms = {"tica": [], "kcenters": []}
+    state = {}
+
+    def step(record):
+        acc.zero_()
+        if record:
+            ev[0].record()
+        est._accumulate_device(seqs, acc=acc)
+        par.allreduce_packed(acc)
+        if record:
+            ev[1].record()
+        ids, distances, labels, ring = par.kcenters_fit_gpu(X, row_offset, k, "euclidean",
+                                                            seed_global=12345 % n_total)
+        if record:
+            ev[2].record()
+        state["ids"], state["labels"], state["distances"] = ids, labels, distances
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.msmb200_launch_count()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        step(True)
+        ev[2].synchronize()
+        phase_ms["tica"].append(ev[0].elapsed_time(ev[1]))
+        phase_ms["kcenters"].append(ev[1].elapsed_time(ev[2]))
+    t_stop.record()
+    barrier()
+    launches = int(lib.msmb200_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([t_start.elapsed_time(t_stop)], dtype=torch.float64, device="cuda")
+    tica_ms = torch.tensor([float(np.mean(phase_ms["tica"]))], dtype=torch.float64, device="cuda")
+    kc_ms = torch.tensor([float(np.mean(phase_ms["kcenters"]))], dtype=torch.float64, device="cuda")
+    if ws > 1:
+        for t in (total_ms, tica_ms, kc_ms):
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = n_total / (ms_per_step / 1e3)
+
+    # sanity on the timed work: eigenvalues from the device accumulator are sane
+    est2 = tICA(n_components=4, lag_time=lag, engine=args.engine)
+    est2._initialize(D)
+    est2._add_packed(acc.cpu().numpy())
+    eig = [float(v) for v in est2.eigenvalues_]
+
+    # ---------------- e2e: public estimator API on pinned host arrays -----------------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_frames // ws, n_local) // L * L
+        ne = max(ne, L)
+        host = [X[i * L:(i + 1) * L].cpu().pin_memory() for i in range(ne // L)]
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            t = tICA(n_components=4, lag_time=lag, engine=args.engine)
+            kc = KCenters(n_clusters=k, random_state=0)
+            if ws == 1:
+                t.fit(host)
+                kc.fit(host)
+            else:
+                par.tica_fit_sharded(t, host)
+                par.kcenters_fit_sharded(kc, host, rank * ne, ne * ws)
+            return t, kc
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            t, kc = e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+        if ws > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = 2 * ne * D * 4                       # each estimator uploads its frames
+        d2h = int(lib.msmb200_tica_acc_len(D)) * 8 + ne * (8 + 4) + k * (8 + D * 4)
+        e2e = {"value": ne * ws / float(dt.item()), "unit": "frames/s", "frames": ne * ws,
+               "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": d2h * ws,
+               "api": "tICA.fit(host arrays) + KCenters.fit(host arrays)"
+                      + ("" if ws == 1 else " via parallel.*_fit_sharded")}
+        del host
+
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    engine_used = "simt_f64"
+    if args.engine in ("auto", "umma_3xtf32", "umma_tf32"):
+        from ctypes import c_int
+        engine_used = args.engine
+    tica_s = float(tica_ms.item()) / 1e3
+    kc_s = float(kc_ms.item()) / 1e3
+    pass_s = kc_s / k
+    bytes_per_pass = (n_total / ws) * (4 * D + 8)          # per GPU: frame + f64 running min
+    hbm_ach = bytes_per_pass / pass_s / 1e9
+    flops_tica = 4.0 * D * D * (n_total / ws)              # algorithmic: two rank-1 DxD updates / frame
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    tica_ach = flops_tica / tica_s / 1e12
+    roof_k2 = {"kernel": "kcenters_pass_kernel", "bound": "hbm", "achieved": hbm_ach,
+               "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+               "traffic": None, "peak_source": peaks["source"],
+               "algorithmic_bytes_per_launch": bytes_per_pass, "ms_per_launch": pass_s * 1e3,
+               "share_of_step": kc_s / (ms_per_step / 1e3)}
+    roof_k1 = {"kernel": "tica_accumulate(%s)" % args.engine, "bound": "tensor", "achieved": tica_ach,
+               "peak": tf32_peak, "unit": "TFLOP/s", "frac": tica_ach / tf32_peak, "traffic": None,
+               "peak_source": peaks["source"] + "; TF32 dense taken as 1/2 of the measured sustained bf16",
+               "algorithmic_flops_per_launch": flops_tica, "ms_per_launch": tica_s * 1e3,
+               "share_of_step": tica_s / (ms_per_step / 1e3)}
+    dominant = roof_k2 if kc_s >= tica_s else roof_k1
+
+    line = {
+        "metric": "frames/sec tICA fit + KCenters assign", "value": value, "unit": "frames/s",
+        "n_gpus": ws, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 in; tf32x3 tensor-core products, f32/f64 accumulation (tICA); f64 distances (KCenters)"
+                 if args.engine != "simt_f64" else "f32 in; f64 arithmetic",
+        "data": "synthetic", "config": workload_config(args, ws),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": dominant, "roofline_all": [roof_k1, roof_k2],
+        "phases_ms": {"tica_fit": tica_s * 1e3, "kcenters_fit": kc_s * 1e3},
+        "tica_engine": args.engine, "check": {"eigenvalues": eig},
+    }
+
+    if ws == 1 and not args.no_cpu_baseline:
+        from oracle import libdistance_oracle as lo
+        use_ref = lo.have_reference()
+        nc = max(L, min(args.cpu_frames, n_local) // L * L)
+        hs = [X[i * L:(i + 1) * L].cpu().numpy() for i in range(nc // L)]
+        a, b = cpu_hot_path(hs, lag, k, use_ref)
+        line["cpu_baseline"] = {
+            "value": nc / (a + b), "unit": "frames/s", "cores": os.cpu_count(),
+            "blas_threads": cpu_threads(), "kind": "reference" if use_ref else "port",
+            "sample": "%d of the same frames (D2H copy): tICA NumPy f64 %.2f s on %d BLAS threads + "
+                      "%d KCenters passes %.2f s on 1 thread (the reference's libdistance is "
+                      "single-threaded)" % (nc, a, cpu_threads(), k, b)}
+    print(json.dumps(line))
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,9 @@ enum { MSMB200_F32 = 0, MSMB200_F64 = 1 };
 /* ---- library ---------------------------------------------------------- */
 int msmb200_abi_version(void);
 const char *msmb200_last_error(void);           /* thread-local, never NULL */
+/* number of CUDA kernels this library has launched in this process (bench.py's
+ * gpu_launches is a difference of two readings) */
+uint64_t msmb200_launch_count(void);
 /* sm count / compute capability of `device`; E_NODEVICE when none. */
 int msmb200_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
                         size_t *total_mem);

@@ -24,6 +24,7 @@ ENGINES = {"auto": TICA_AUTO, "simt_f64": TICA_SIMT_F64,
 SIGNATURES = {
     "msmb200_abi_version": (c_int, []),
     "msmb200_last_error": (ctypes.c_char_p, []),
+    "msmb200_launch_count": (ctypes.c_uint64, []),
     "msmb200_device_info": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                     ctypes.POINTER(c_int), ctypes.POINTER(c_sz)]),
     "msmb200_tica_acc_len": (c_sz, [c_int]),

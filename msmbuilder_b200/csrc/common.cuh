@@ -28,7 +28,13 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         }                                                                      \
     } while (0)
 
-#define MSMB_LAUNCH_CHECK() MSMB_CUDA(cudaGetLastError())
+void count_launch();
+// every kernel launch of the library is followed by this (also feeds msmb200_launch_count)
+#define MSMB_LAUNCH_CHECK()                                                    \
+    do {                                                                       \
+        ::msmb::count_launch();                                                \
+        MSMB_CUDA(cudaGetLastError());                                         \
+    } while (0)
 
 int sm_count();   // of the current device (cached per device)
 

@@ -21,6 +21,9 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return MSMB200_E_CUDA;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
+
 int sm_count()
 {
     static int cached[64] = {0};
@@ -51,6 +54,11 @@ using namespace msmb;
 extern "C" int msmb200_abi_version(void) { return MSMB200_ABI_VERSION; }
 
 extern "C" const char *msmb200_last_error(void) { return g_err; }
+
+extern "C" uint64_t msmb200_launch_count(void)
+{
+    return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+}
 
 extern "C" int msmb200_device_info(int device, int *sm, int *cc_major, int *cc_minor,
                                    size_t *total_mem)

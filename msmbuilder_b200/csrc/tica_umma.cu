@@ -1,12 +1,702 @@
-// tica_umma.cu -- K1 on tcgen05 tensor cores (placeholder until the kernel lands).
+// tica_umma.cu -- K1 on Blackwell tensor cores: TMA-fed tcgen05.mma (kind::tf32,
+// cta_group::2) with TMEM accumulators.  sm_100a only.
+//
+// What it computes (per call, for D = 256 float32 features):
+//   C_tau' = sum_t x'_t x'_{t+lag}^T       C_00' = sum_t x'_t x'_t^T
+//   S_0'   = sum_t x'_t                    S_tau' = sum_t x'_{t+lag}
+// over the pair indices t of every sequence, where x' = fl32(x - shift) is the frame
+// re-centred by a provisional per-feature mean (covariances are shift invariant;
+// the raw moments of tica.py:417-422 are reconstructed exactly in float64 by
+// tica_umma_finalize).  The few pair indices that do not fill a 4-frame block and
+// the 2*lag head/tail frames that distinguish C_00 from C_tautau are handled in
+// float64 by tica_umma_edges.
+//
+// Design:
+//  * A CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns a range of 32-frame tiles.
+//    CTA r holds features [128r, 128r+128): as the M-half of A (unlagged frames)
+//    and as the N-half of B (lagged frames) of one M=256 x N=256 x K=8 UMMA.
+//  * TMEM per CTA: 128 lanes x 512 columns fp32 = C_tau rows (cols 0..255) and
+//    C_00 rows (cols 256..511) of this CTA's 128 features: all of TMEM.
+//  * Operands are K-major, no swizzle: [row-block of 4 frames][feature][4 frames],
+//    i.e. 16-byte chunks = 4 consecutive frames of one feature, core matrix =
+//    8 features x 4 frames (LBO = 2048 B between row-blocks, SBO = 128 B).
+//  * TMA: one 4-D tensor map per sequence and operand, dims (4 feat, 4 frames,
+//    D/4 groups, n/4 row-blocks), box (4,4,32,KT/4) -> smem [rb][g][frame][4 feat]:
+//    every 64-byte block already sits where its K-major transpose belongs, so the
+//    converter warps transpose 4x4 inside a lane quad (4 shuffles) IN PLACE.
+//    The lagged operand has its own map whose base is shifted by lag rows, so any
+//    lag works and no operand needs an unaligned descriptor.
+//  * Precision: x' = hi + lo with hi = tf32_rn(x'), lo = tf32_rn(x' - hi);
+//    products hi*hi + hi*lo + lo*hi (3 MMAs, ~2^-21 relative), fp32 accumulation in
+//    TMEM over a bounded slab of frames, then flushed into float64 partials.
+//  * Warp roles (384 threads): w0 TMA producer, w1 MMA issuer (leader CTA), w2 TMEM
+//    allocator, w4-7 converters (fp32 -> centred tf32 hi/lo, transpose, column sums),
+//    w8-11 epilogue (tcgen05.ld -> float64 read-modify-write of the pair's partials).
 #include "common.cuh"
+#include <cuda.h>
+#include <vector>
+
 namespace msmb {
-bool tica_umma_supported(int D, int64_t ld, int dtype, int lag) { (void)D; (void)ld; (void)dtype; (void)lag; return false; }
-size_t tica_umma_workspace_bytes(int D) { (void)D; return 0; }
-int tica_umma_accumulate(const void *const *, const int64_t *, int, int, int64_t, int, int, double *,
-                         void *, size_t, cudaStream_t)
+
+constexpr int UM_D = 256;                       // features handled by this kernel
+constexpr int UM_F = 128;                       // features per CTA
+constexpr int UM_KT = 32;                       // frames per tile
+constexpr int UM_RB = UM_KT / 4;                // 4-frame row-blocks per tile
+constexpr int UM_STAGES = 3;
+constexpr int UM_TILE_BYTES = UM_KT * UM_F * 4; // 16 KB
+constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
+constexpr int UM_SBO = 128;                     // next 8-feature group
+constexpr int UM_THREADS = 384;
+constexpr int UM_SLAB_TILES_DEFAULT = 128;      // 4096 frames of fp32 accumulation per flush
+
+struct UmmaParams {
+    const CUtensorMap *mapsA;     // [n_seq] unlagged
+    const CUtensorMap *mapsB;     // [n_seq] base shifted by lag rows
+    const int *tile_prefix;       // [n_seq + 1] tiles before sequence s
+    const int *seq_blocks;        // [n_seq] full 4-frame blocks of pair indices
+    int n_seq;
+    int n_tiles;
+    int n_pairs;                  // clusters launched
+    int slab_tiles;
+    int passes;                   // 3 = hi/lo split, 1 = plain tf32
+    const float *shift;           // [D]
+    double *partials;             // [n_pairs][2][D][D]  (C_tau', C_00')
+    double *sums;                 // [2][D]  (S_0', S_tau')  atomically accumulated
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-    set_error("tcgen05 engine not built");
-    return MSMB200_E_UNSUPPORTED;
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the same-named barrier of CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;"
+                 ::: "memory");
+}
+// K-major, no swizzle, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((UM_LBO >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((UM_SBO >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// tf32 x tf32 -> f32, K-major A and B, M = 256 (pair), N = 256
+__device__ __forceinline__ uint32_t umma_idesc()
+{
+    uint32_t d = 0;
+    d |= 1u << 4;                     // D format F32
+    d |= 2u << 7;                     // A format TF32
+    d |= 2u << 10;                    // B format TF32
+    d |= (uint32_t)(256 >> 3) << 17;  // N
+    d |= (uint32_t)(256 >> 4) << 24;  // M
+    return d;
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db,
+                                               uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrive (when all prior MMAs of this thread have completed) on `bar` in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+#define UM_TMEM_LD32(v, taddr) asm volatile( \
+    "tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
+    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+    : "r"(taddr) : "memory")
+
+struct UmmaSmem {
+    uint64_t full[UM_STAGES];      // TMA landed (tx bytes), local
+    uint64_t conv[UM_STAGES];      // operands converted; the LEADER's copy is used (8 arrivals)
+    uint64_t empty[UM_STAGES];     // MMAs done reading the stage (multicast commit), local
+    uint64_t acc_full;             // slab finished (multicast commit), local
+    uint64_t acc_empty;            // accumulators drained; the LEADER's copy is used (8 arrivals)
+    uint32_t tmem_base;
+    int valid_rb[UM_STAGES];
+};
+
+// ---------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
+tica_umma_kernel(const UmmaParams P)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1 KB-aligned operand ring, control block behind it
+    unsigned char *ring = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    UmmaSmem *ctl = reinterpret_cast<UmmaSmem *>(ring + UM_STAGES * UM_STAGE_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t cta_rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int pair = blockIdx.x >> 1;
+
+    // this pair's tile range (identical in every role of both CTAs)
+    const long long t_begin = (long long)P.n_tiles * pair / P.n_pairs;
+    const long long t_end = (long long)P.n_tiles * (pair + 1) / P.n_pairs;
+    const int my_tiles = (int)(t_end - t_begin);
+    const int n_slabs = (my_tiles + P.slab_tiles - 1) / P.slab_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->conv[s], 8);
+            mbar_init(&ctl->empty[s], 1);
+        }
+        mbar_init(&ctl->acc_full, 1);
+        mbar_init(&ctl->acc_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&ctl->tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer (one lane, both CTAs) ============
+        if (lane == 0 && my_tiles > 0) {
+            int s = 0;
+            {   // locate the sequence of the first tile
+                int lo = 0, hi = P.n_seq;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (P.tile_prefix[mid] <= t_begin) lo = mid; else hi = mid;
+                }
+                s = lo;
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = t_begin; t < t_end; ++t) {
+                while (t >= P.tile_prefix[s + 1]) ++s;
+                const int rb0 = (int)(t - P.tile_prefix[s]) * UM_RB;
+                int valid = P.seq_blocks[s] - rb0;
+                if (valid > UM_RB) valid = UM_RB;
+                mbar_wait(&ctl->empty[stage], phase ^ 1);
+                ctl->valid_rb[stage] = valid;
+                mbar_expect_tx(&ctl->full[stage], 2 * UM_TILE_BYTES);
+                unsigned char *st = ring + stage * UM_STAGE_BYTES;
+                tma_load_4d(st, &P.mapsA[s], &ctl->full[stage], 0, 0, 32 * (int)cta_rank, rb0);
+                tma_load_4d(st + 2 * UM_TILE_BYTES, &P.mapsB[s], &ctl->full[stage], 0, 0,
+                            32 * (int)cta_rank, rb0);
+                if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA, one lane) =============
+        if (cta_rank == 0 && lane == 0 && my_tiles > 0) {
+            const uint32_t idesc = umma_idesc();
+            const uint32_t ring_addr = smem_u32(ring);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const bool slab_first = (t % P.slab_tiles) == 0;
+                const bool slab_last = ((t + 1) % P.slab_tiles) == 0 || t + 1 == my_tiles;
+                mbar_wait(&ctl->conv[stage], phase);
+                if (slab_first && t > 0) {
+                    mbar_wait(&ctl->acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t a_hi = ring_addr + stage * UM_STAGE_BYTES;
+                const uint32_t a_lo = a_hi + UM_TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * UM_TILE_BYTES;
+                const uint32_t b_lo = a_hi + 3 * UM_TILE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < UM_KT / 8; ++ks) {
+                    const uint32_t off = ks * 2 * UM_LBO;
+                    const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
+                    const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
+                    const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
+                    umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
+                    if (P.passes == 3) {
+                        umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
+                        umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                    }
+                    umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                    if (P.passes == 3) {
+                        umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
+                        umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                    }
+                }
+                umma_commit_pair(&ctl->empty[stage]);     // stage may be refilled (both CTAs)
+                if (slab_last) umma_commit_pair(&ctl->acc_full);
+                if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================ converters (128 threads, both CTAs) ==========
+        const int ct = tid - 128;
+        const int g = ct >> 2, q = ct & 3;             // quad g owns feature group g, lane q a frame / feature
+        const float4 sh = *reinterpret_cast<const float4 *>(P.shift + UM_F * cta_rank + 4 * g);
+        const bool split = P.passes == 3;
+        double sumA = 0.0, sumB = 0.0;                 // column sums of feature 128*rank + 4g + q
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            mbar_wait(&ctl->full[stage], phase);
+            const int valid = ctl->valid_rb[stage];
+            unsigned char *st = ring + stage * UM_STAGE_BYTES;
+            float tsA = 0.f, tsB = 0.f;
+#pragma unroll
+            for (int op = 0; op < 2; ++op) {
+                unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES;
+                unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
+#pragma unroll 2
+                for (int rb = 0; rb < UM_RB; ++rb) {
+                    const int off = (rb * 32 + g) * 64 + q * 16;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    if (rb < valid) {
+                        const float4 v = *reinterpret_cast<const float4 *>(hi_buf + off);
+                        a0 = v.x - sh.x; a1 = v.y - sh.y; a2 = v.z - sh.z; a3 = v.w - sh.w;
+                    }
+                    // 4x4 transpose inside the quad: lane q holds frame q (4 features) ->
+                    // lane q holds feature q (4 frames)
+                    {
+                        const bool o1 = q & 1;
+                        float t0 = o1 ? a0 : a1, t1 = o1 ? a2 : a3;
+                        float r0 = __shfl_xor_sync(0xffffffffu, t0, 1);
+                        float r1 = __shfl_xor_sync(0xffffffffu, t1, 1);
+                        if (o1) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
+                        const bool o2 = q & 2;
+                        t0 = o2 ? a0 : a2; t1 = o2 ? a1 : a3;
+                        r0 = __shfl_xor_sync(0xffffffffu, t0, 2);
+                        r1 = __shfl_xor_sync(0xffffffffu, t1, 2);
+                        if (o2) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
+                    }
+                    const float s4 = (a0 + a1) + (a2 + a3);
+                    if (op == 0) tsA += s4; else tsB += s4;
+                    float4 h;
+                    h.x = tf32_rn(a0); h.y = tf32_rn(a1); h.z = tf32_rn(a2); h.w = tf32_rn(a3);
+                    *reinterpret_cast<float4 *>(hi_buf + off) = h;
+                    if (split) {
+                        float4 l;
+                        l.x = tf32_rn(a0 - h.x); l.y = tf32_rn(a1 - h.y);
+                        l.z = tf32_rn(a2 - h.z); l.w = tf32_rn(a3 - h.w);
+                        *reinterpret_cast<float4 *>(lo_buf + off) = l;
+                    }
+                }
+            }
+            sumA += (double)tsA;
+            sumB += (double)tsB;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&ctl->conv[stage], 0);
+            if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (my_tiles > 0) {
+            const int f = UM_F * cta_rank + 4 * g + q;
+            atomicAdd(&P.sums[f], sumA);
+            atomicAdd(&P.sums[UM_D + f], sumB);
+        }
+    } else if (warp >= 8) {
+        // ================================ epilogue (128 threads, both CTAs) =============
+        const int ew = warp - 8;                       // == warp % 4: TMEM lane quarter
+        const int row = UM_F * cta_rank + ew * 32 + lane;
+        double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + (size_t)row * UM_D;
+        uint32_t acc_phase = 0;
+        for (int slab = 0; slab < n_slabs; ++slab) {
+            mbar_wait(&ctl->acc_full, acc_phase);
+            acc_phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll 1
+            for (int c0 = 0; c0 < 512; c0 += 32) {
+                uint32_t v[32];
+                UM_TMEM_LD32(v, tmem + ((uint32_t)(ew * 32) << 16) + c0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                double *dst = pc + (c0 < 256 ? c0 : (size_t)UM_D * UM_D + (c0 - 256));
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    double2 cur = *reinterpret_cast<double2 *>(dst + j);
+                    cur.x += (double)__uint_as_float(v[j]);
+                    cur.y += (double)__uint_as_float(v[j + 1]);
+                    *reinterpret_cast<double2 *>(dst + j) = cur;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0 && slab + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
+        }
+    }
+
+    // teardown: nobody may still be using the peer's barriers / TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
+// ---------------------------------------------------------------------------------------
+// provisional per-feature mean of the first rows of the first sequence -> float32 shift
+__global__ void tica_shift_kernel(const float *__restrict__ X, long long n, long long ld, int D,
+                                  float *__restrict__ shift)
+{
+    const long long rows = n < 512 ? n : 512;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (long long r = 0; r < rows; ++r) s += (double)X[r * ld + c];
+        shift[c] = (float)(s / (double)rows);
+    }
+}
+
+struct EdgeSeq {
+    const float *base;
+    long long n;
+};
+
+// float64 edge terms, in the SAME centred coordinates x' = fl32(x - shift):
+//   E[0] += sum over the remainder pair indices t in [4*floor(P/4), P) of x'_t x'_{t+lag}^T
+//   E[1] += the same t of x'_t x'_t^T
+//   E[2] += sum_{t < lag} x'_t x'_t^T            (head: in C_00, not in C_tautau)
+//   E[3] += sum_{t >= n-lag} x'_t x'_t^T         (tail: in C_tautau, not in C_00)
+//   es[0..2] (D each): remainder sums of x'_t, of x'_{t+lag}, and the tail-row sum
+// grid (n_blocks, D/16): block (b, it) accumulates rows 16*it..16*it+15 of the outputs
+// over sequences b, b + n_blocks, ...
+__global__ void __launch_bounds__(256)
+tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld, int lag,
+                       const float *__restrict__ shift, double *__restrict__ E,
+                       double *__restrict__ es)
+{
+    constexpr int D = UM_D;
+    __shared__ double sx[D], sy[D];
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.y * 16;
+    double acc[4][16];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[m][u] = 0.0;
+    double s0 = 0.0, st = 0.0, stail = 0.0;    // column `tid` sums (only blockIdx.y == 0 publishes)
+
+    for (int s = blockIdx.x; s < n_seq; s += gridDim.x) {
+        const float *X = seqs[s].base;
+        const long long n = seqs[s].n;
+        const long long Pn = n - lag;
+        const long long R = (Pn / 4) * 4;
+        // row list: remainder pairs, head rows, tail rows
+        const int n_rem = (int)(Pn - R);
+        const long long total = n_rem + 2LL * lag;
+        for (long long e = 0; e < total; ++e) {
+            int kind;
+            long long t;
+            if (e < n_rem) { kind = 0; t = R + e; }
+            else if (e < n_rem + lag) { kind = 2; t = e - n_rem; }
+            else { kind = 3; t = n - lag + (e - n_rem - lag); }
+            __syncthreads();
+            sx[tid] = (double)(X[t * ld + tid] - shift[tid]);
+            if (kind == 0) sy[tid] = (double)(X[(t + lag) * ld + tid] - shift[tid]);
+            __syncthreads();
+            const double xj = sx[tid];
+            if (kind == 0) {
+                const double yj = sy[tid];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const double xi = sx[i0 + u];
+                    acc[0][u] = fma(xi, yj, acc[0][u]);
+                    acc[1][u] = fma(xi, xj, acc[1][u]);
+                }
+                s0 += xj;
+                st += yj;
+            } else if (kind == 2) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc[2][u] = fma(sx[i0 + u], xj, acc[2][u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc[3][u] = fma(sx[i0 + u], xj, acc[3][u]);
+                stail += xj;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            atomicAdd(&E[(size_t)m * D * D + (size_t)(i0 + u) * D + tid], acc[m][u]);
+    if (blockIdx.y == 0) {
+        atomicAdd(&es[tid], s0);
+        atomicAdd(&es[D + tid], st);
+        atomicAdd(&es[2 * D + tid], stail);
+    }
+}
+
+// reduce the pair partials, add the float64 edge terms, undo the shift, add into `acc`
+__global__ void __launch_bounds__(256)
+tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
+                          const double *__restrict__ sums, const double *__restrict__ E,
+                          const double *__restrict__ es, const float *__restrict__ shift,
+                          double n_pairs_total /* sum_s (n_s - lag) */, double n_obs, double n_seq,
+                          double *__restrict__ acc)
+{
+    constexpr int D = UM_D;
+    const size_t DD = (size_t)D * D;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // element of a D x D matrix
+    if (idx >= (int)DD) return;
+    const int i = idx / D, j = idx % D;
+    double ctau = 0.0, c00 = 0.0;
+    for (int p = 0; p < n_pairs; ++p) {
+        ctau += partials[(size_t)p * 2 * DD + idx];
+        c00 += partials[(size_t)p * 2 * DD + DD + idx];
+    }
+    ctau += E[idx];
+    c00 += E[DD + idx];
+    const double ctt = c00 - E[2 * DD + idx] + E[3 * DD + idx];
+    const double si = (double)shift[i], sj = (double)shift[j];
+    const double S0i = sums[i] + es[i], S0j = sums[j] + es[j];
+    const double Sti = sums[D + i] + es[D + i], Stj = sums[D + j] + es[D + j];
+    const double Np = n_pairs_total;
+    acc[idx] += ctau + S0i * sj + si * Stj + Np * si * sj;
+    acc[DD + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
+    acc[2 * DD + idx] += ctt + Sti * sj + si * Stj + Np * si * sj;
+    if (i == 0) {
+        // vectors and counters (one thread per column j)
+        const double S0 = S0j, St = Stj;
+        const double Sall = S0 + es[2 * D + j];       // all rows = pair rows + last `lag` rows
+        acc[3 * DD + j] += S0 + Np * sj;
+        acc[3 * DD + D + j] += St + Np * sj;
+        acc[3 * DD + 2 * D + j] += Sall + n_obs * sj;
+        if (j == 0) {
+            acc[3 * DD + 3 * D] += n_obs;
+            acc[3 * DD + 3 * D + 1] += n_seq;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool tica_umma_supported(int D, int64_t ld, int dtype, int lag)
+{
+    return D == UM_D && dtype == MSMB200_F32 && (ld % 4) == 0 && lag >= 1;
+}
+
+size_t tica_umma_workspace_bytes(int D)
+{
+    (void)D;
+    return 0;   // scratch is stream-ordered (cudaMallocAsync) inside the call
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, int n_seq_in,
+                         int D, int64_t ld, int lag, int passes, double *acc, void *workspace,
+                         size_t workspace_bytes, cudaStream_t st)
+{
+    (void)workspace; (void)workspace_bytes;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return MSMB200_E_CUDA;
+    }
+    // usable sequences (tica.py:410-412: n <= lag is skipped and not counted)
+    std::vector<EdgeSeq> seqs;
+    double n_obs = 0.0, n_pairs_total = 0.0;
+    for (int s = 0; s < n_seq_in; ++s) {
+        if (!(seq_rows[s] > lag)) continue;
+        if ((reinterpret_cast<uintptr_t>(seq_ptrs[s]) & 15u) != 0) {
+            set_error("tcgen05 engine needs 16-byte aligned sequences");
+            return MSMB200_E_UNSUPPORTED;
+        }
+        EdgeSeq e;
+        e.base = reinterpret_cast<const float *>(seq_ptrs[s]);
+        e.n = seq_rows[s];
+        seqs.push_back(e);
+        n_obs += (double)e.n;
+        n_pairs_total += (double)(e.n - lag);
+    }
+    const int n_seq = (int)seqs.size();
+    if (n_seq == 0) return MSMB200_OK;
+
+    std::vector<CUtensorMap> maps(2 * (size_t)n_seq);
+    std::vector<int> tile_prefix(n_seq + 1, 0), seq_blocks(n_seq, 0);
+    long long tiles = 0;
+    for (int s = 0; s < n_seq; ++s) {
+        const long long Q = (seqs[s].n - lag) / 4;      // full 4-frame blocks of pair indices
+        seq_blocks[s] = (int)Q;
+        tile_prefix[s] = (int)tiles;
+        tiles += (Q + UM_RB - 1) / UM_RB;
+        if (tiles > 0x7fffffffLL) {
+            set_error("too many tiles");
+            return MSMB200_E_UNSUPPORTED;
+        }
+        for (int which = 0; which < 2; ++which) {
+            // Q == 0: the map is never used (no tiles); encode a 1-block dummy
+            cuuint64_t dims[4] = {4, 4, (cuuint64_t)(D / 4), (cuuint64_t)(Q > 0 ? Q : 1)};
+            cuuint64_t strides[3] = {(cuuint64_t)ld * 4, 16, (cuuint64_t)ld * 16};
+            cuuint32_t box[4] = {4, 4, 32, UM_RB};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            void *base = (void *)(seqs[s].base + (which ? (size_t)lag * ld : 0));
+            CUresult r = enc(&maps[2 * (size_t)s + which], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
+                             dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled failed (%d) for sequence %d", (int)r, s);
+                return MSMB200_E_CUDA;
+            }
+        }
+    }
+    tile_prefix[n_seq] = (int)tiles;
+
+    int n_pairs = sm_count() / 2;
+    n_pairs = env_int("MSMB200_UMMA_PAIRS", n_pairs);
+    if (tiles < n_pairs) n_pairs = (int)(tiles > 0 ? tiles : 1);
+    const size_t DD = (size_t)D * D;
+
+    // one stream-ordered scratch block:
+    // [mapsA | mapsB | tile_prefix | seq_blocks | edge seqs | shift | sums | E | es | partials]
+    auto align_up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    size_t off = 0;
+    const size_t o_mapsA = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
+    const size_t o_mapsB = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
+    const size_t o_prefix = off; off = align_up(off + sizeof(int) * (n_seq + 1), 128);
+    const size_t o_blocks = off; off = align_up(off + sizeof(int) * n_seq, 128);
+    const size_t o_eseq = off; off = align_up(off + sizeof(EdgeSeq) * n_seq, 128);
+    const size_t o_shift = off; off = align_up(off + sizeof(float) * D, 128);
+    const size_t o_zero = off;       // everything from here on is zero-initialised
+    const size_t o_sums = off; off = align_up(off + sizeof(double) * 2 * D, 128);
+    const size_t o_E = off; off = align_up(off + sizeof(double) * 4 * DD, 128);
+    const size_t o_es = off; off = align_up(off + sizeof(double) * 3 * D, 128);
+    const size_t o_part = off; off = align_up(off + sizeof(double) * 2 * DD * n_pairs, 128);
+    unsigned char *scratch = nullptr;
+    MSMB_CUDA(cudaMallocAsync(&scratch, off, st));
+    MSMB_CUDA(cudaMemsetAsync(scratch + o_zero, 0, off - o_zero, st));
+
+    std::vector<CUtensorMap> mA(n_seq), mB(n_seq);
+    for (int s = 0; s < n_seq; ++s) { mA[s] = maps[2 * (size_t)s]; mB[s] = maps[2 * (size_t)s + 1]; }
+    MSMB_CUDA(cudaMemcpyAsync(scratch + o_mapsA, mA.data(), sizeof(CUtensorMap) * n_seq, cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaMemcpyAsync(scratch + o_mapsB, mB.data(), sizeof(CUtensorMap) * n_seq, cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaMemcpyAsync(scratch + o_prefix, tile_prefix.data(), sizeof(int) * (n_seq + 1), cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaMemcpyAsync(scratch + o_blocks, seq_blocks.data(), sizeof(int) * n_seq, cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaMemcpyAsync(scratch + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq, cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaStreamSynchronize(st));    // host vectors are pageable: keep them alive until copied
+
+    float *d_shift = reinterpret_cast<float *>(scratch + o_shift);
+    tica_shift_kernel<<<1, 256, 0, st>>>(seqs[0].base, seqs[0].n, ld, D, d_shift);
+    MSMB_LAUNCH_CHECK();
+
+    UmmaParams P;
+    P.mapsA = reinterpret_cast<const CUtensorMap *>(scratch + o_mapsA);
+    P.mapsB = reinterpret_cast<const CUtensorMap *>(scratch + o_mapsB);
+    P.tile_prefix = reinterpret_cast<const int *>(scratch + o_prefix);
+    P.seq_blocks = reinterpret_cast<const int *>(scratch + o_blocks);
+    P.n_seq = n_seq;
+    P.n_tiles = (int)tiles;
+    P.n_pairs = n_pairs;
+    P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", UM_SLAB_TILES_DEFAULT);
+    if (P.slab_tiles < 1) P.slab_tiles = 1;
+    P.passes = passes;
+    P.shift = d_shift;
+    P.partials = reinterpret_cast<double *>(scratch + o_part);
+    P.sums = reinterpret_cast<double *>(scratch + o_sums);
+
+    if (tiles > 0) {
+        const size_t smem = (size_t)UM_STAGES * UM_STAGE_BYTES + sizeof(UmmaSmem) + 1024;
+        static bool attr_set = false;
+        if (!attr_set) {
+            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        tica_umma_kernel<<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+        MSMB_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(n_seq < 64 ? n_seq : 64, D / 16);
+        tica_umma_edges_kernel<<<grid, 256, 0, st>>>(
+            reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq, ld, lag, d_shift,
+            reinterpret_cast<double *>(scratch + o_E), reinterpret_cast<double *>(scratch + o_es));
+        MSMB_LAUNCH_CHECK();
+    }
+    tica_umma_finalize_kernel<<<(unsigned)((DD + 255) / 256), 256, 0, st>>>(
+        P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(scratch + o_E),
+        reinterpret_cast<const double *>(scratch + o_es), d_shift, n_pairs_total, n_obs,
+        (double)n_seq, acc);
+    MSMB_LAUNCH_CHECK();
+    MSMB_CUDA(cudaFreeAsync(scratch, st));
+    return MSMB200_OK;
+}
+
 }  // namespace msmb

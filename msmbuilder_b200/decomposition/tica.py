@@ -290,6 +290,13 @@ class tICA(BaseEstimator, TransformerMixin):
         flush()
 
     def _accumulate_batch(self, seqs):
+        packed = self._accumulate_device(seqs).cpu().numpy()   # synchronises
+        self._add_packed(packed)
+
+    def _accumulate_device(self, seqs, acc=None):
+        """Run K1 over `seqs` (host arrays are uploaded, device tensors used in
+        place); returns the packed float64 accumulator as a CUDA tensor (layout:
+        include/msmb200.h).  Asynchronous on torch's current stream."""
         import torch
         from .. import _device as dev
         _lib.require_gpu()
@@ -315,15 +322,15 @@ class tICA(BaseEstimator, TransformerMixin):
         rows = (ctypes.c_int64 * n_seq)(*[int(t.shape[0]) for t in dev_seqs])
         lib = _lib.load()
         acc_len = lib.msmb200_tica_acc_len(D)
-        acc = torch.zeros(acc_len, dtype=torch.float64, device="cuda")
+        if acc is None:
+            acc = torch.zeros(acc_len, dtype=torch.float64, device="cuda")
         engine = _lib.ENGINES[self.engine]
         ws_bytes = lib.msmb200_tica_workspace_bytes(D, engine)
         ws = dev.workspace().get(("tica", D), ws_bytes)
         _lib.call("msmb200_tica_accumulate", ptrs, rows, n_seq, D, D, dev.dtype_id(dev_seqs[0]),
                   int(self.lag_time), engine, dev.ptr(acc), dev.ptr(ws), ws.numel(),
                   dev.stream_ptr())
-        packed = acc.cpu().numpy()   # synchronises
-        self._add_packed(packed)
+        return acc
 
     def _add_packed(self, packed):
         """Fold one packed device accumulator (layout: include/msmb200.h) into the

@@ -1,0 +1,215 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink).
+
+The hot path shards by frames:
+
+* tICA: whole sequences are dealt to ranks (longest-processing-time first); each
+  rank accumulates its packed float64 statistics on its GPU and ONE
+  ``all_reduce(SUM)`` of 3*D*D + 3*D + 2 doubles (1.58 MB at D = 256) merges them.
+  The sufficient statistics are additive (tica.py:414-422 are all ``+=``), and
+  n_observations / n_sequences ride in the same buffer.
+* KCenters: the concatenated frames are sharded contiguously; every pass each
+  rank writes its farthest frame {value, global index, row} into a candidate
+  slot, ONE ``all_gather`` of those slots (16 B + one row per rank) follows, and
+  every rank deterministically selects (max value, then lowest global index ==
+  np.argmax's first maximum, kcenters.py:97), so the next centre is known
+  everywhere without a broadcast.
+* assign_nearest: centres are broadcast once; labels stay with their shard.
+
+The collectives are tiny and latency-bound, so they are plain NCCL calls on
+device buffers.  The same code runs under the ``gloo`` backend with CPU tensors
+when the compute callbacks are swapped for host ones (that is how the
+world_size-2 CPU tests exercise the protocol).
+"""
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+CAND_HEADER = 16   # sizeof(msmb200_candidate): double value, int64 index
+
+
+def world():
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_sequences(lengths, world_size):
+    """Longest-processing-time assignment of whole sequences to ranks.
+    Returns a list (per rank) of sequence indices, each in ascending order."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    loads = [0] * world_size
+    owned = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda q: (loads[q], q))
+        owned[r].append(i)
+        loads[r] += int(lengths[i])
+    return [sorted(o) for o in owned]
+
+
+def shard_rows(n_total, world_size):
+    """Contiguous, near-equal row ranges [(start, stop)] per rank."""
+    base, extra = divmod(int(n_total), world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        stop = start + base + (1 if r < extra else 0)
+        out.append((start, stop))
+        start = stop
+    return out
+
+
+def allreduce_packed(packed, group=None):
+    """In-place SUM all-reduce of a packed float64 tICA accumulator (device tensor
+    under NCCL, CPU tensor under gloo)."""
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+def select_candidate_host(gathered, n_cand, cand_bytes):
+    """Host mirror of msmb200_candidate_select for CPU (gloo) runs: gathered is a
+    uint8 tensor of n_cand slots; returns the winning slot index."""
+    buf = gathered.numpy().reshape(n_cand, cand_bytes)
+    values = buf[:, :8].copy().view(np.float64).reshape(-1)
+    idx = buf[:, 8:16].copy().view(np.int64).reshape(-1)
+    win = 0
+    for r in range(1, n_cand):
+        if values[r] > values[win] or (values[r] == values[win] and idx[r] < idx[win]):
+            win = r
+    return win
+
+
+def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn, alloc_fn,
+                             group=None):
+    """Rank-collective Gonzalez loop.
+
+    seed_fn(cand)                      fill `cand` with the seed centre on the rank
+                                       that owns it (value must be +inf there) and
+                                       with value = -inf elsewhere
+    pass_fn(center_cand, label, out)   one local pass; writes the local farthest
+                                       frame into `out`
+    select_fn(gathered, n, out)        choose the winner among n gathered slots
+    alloc_fn(n_bytes)                  zeroed uint8 buffer on the compute device
+
+    Returns the (k, cand_bytes) ring of chosen centres (slot i = centre i).
+    """
+    rank, ws = world()
+    k = int(n_clusters)
+    ring = alloc_fn((k + 1) * cand_bytes).reshape(k + 1, cand_bytes)
+    local = alloc_fn(cand_bytes)
+    gathered = alloc_fn(ws * cand_bytes)
+
+    def exchange(dst):
+        if ws == 1:
+            dst.copy_(local)
+            return
+        dist.all_gather_into_tensor(gathered, local, group=group)
+        select_fn(gathered, ws, dst)
+
+    seed_fn(local)
+    exchange(ring[0])
+    for i in range(k):
+        pass_fn(ring[i], i, local)
+        exchange(ring[i + 1])
+    return ring
+
+
+def broadcast_centers(centers, src=0, group=None):
+    _, ws = world()
+    if ws > 1:
+        dist.broadcast(centers, src=src, group=group)
+    return centers
+
+
+def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, traces=None,
+                     group=None):
+    """KCenters over frame shards: `data_local` is this rank's contiguous slice of
+    the concatenated frames, starting at global row `row_offset`.
+
+    Returns (cluster_ids int64[k] (global indices, device), distances f64[n_local],
+    labels i32[n_local], centres ring (k+1, cand_bytes) uint8)."""
+    from . import _kernels as K
+    st = K.KCentersState(data_local, metric, traces=traces, row_offset=row_offset)
+
+    def alloc(nbytes):
+        return torch.zeros(int(nbytes), dtype=torch.uint8, device="cuda")
+
+    def seed_fn(cand):
+        local = int(seed_global) - int(row_offset)
+        if 0 <= local < st.n:
+            st.seed(cand, local)
+        else:
+            cand.zero_()
+            cand[:8].view(torch.float64)[0] = float("-inf")
+
+    def pass_fn(center_cand, label, out):
+        st.run_pass(center_cand, label, out_cand=out)
+
+    ring = kcenters_fit_distributed(n_clusters, st.cand_bytes, seed_fn, pass_fn, st.select,
+                                    alloc, group=group)
+    k = int(n_clusters)
+    ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
+    return ids, st.distances, st.labels, ring
+
+
+# ----------------------------------------------------------------- estimator level
+def tica_fit_sharded(est, local_sequences, group=None):
+    """``tICA.fit`` under torchrun: every rank passes ITS sequences; after one
+    all-reduce every rank holds the same fitted estimator (tica.py:261-290)."""
+    import warnings
+    est._initialized = False
+    seqs = []
+    for X in local_sequences:
+        est._initialize(int(X.shape[1]))
+        if not int(X.shape[0]) > est.lag_time:
+            warnings.warn("length of data (%d) is too short for the lag time (%d)"
+                          % (int(X.shape[0]), est.lag_time))
+            continue
+        seqs.append(X)
+    lib_len = 3 * est.n_features ** 2 + 3 * est.n_features + 2
+    if seqs:
+        acc = est._accumulate_device(seqs)
+    else:
+        acc = torch.zeros(lib_len, dtype=torch.float64, device="cuda")
+    allreduce_packed(acc, group=group)
+    est._add_packed(acc.cpu().numpy())
+    if est.n_sequences_ == 0:
+        raise ValueError('All sequences were shorter than the lag time, %d' % est.lag_time)
+    return est
+
+
+def kcenters_fit_sharded(est, local_sequences, row_offset, n_total, group=None):
+    """``KCenters.fit`` under torchrun: `local_sequences` are this rank's slice of
+    the global frame order starting at global row `row_offset`.  Sets the usual
+    fitted attributes; labels_/distances_ cover the local sequences only."""
+    from sklearn.utils import check_random_state
+    from ._device import FrameStore
+    store = FrameStore(list(local_sequences))
+    seed = check_random_state(est.random_state).randint(0, int(n_total))   # same draw on every rank
+    traces = None
+    data = store.data
+    if est.metric == 'rmsd':
+        from . import _kernels as K
+        data = data.clone()
+        traces = K.rmsd_center(data)
+    ids, distances, labels, ring = kcenters_fit_gpu(data, row_offset, est.n_clusters, est.metric,
+                                                    seed, traces=traces, group=group)
+    k = int(est.n_clusters)
+    est.cluster_ids_ = [int(c) for c in ids.cpu().numpy()]
+    row_elems = data[0].numel()
+    es = data.element_size()
+    cent = ring[:k, CAND_HEADER:CAND_HEADER + row_elems * es].contiguous().view(data.dtype)
+    est.cluster_centers_ = cent.reshape((k,) + tuple(data.shape[1:])).cpu().numpy()
+    est.labels_ = store.split(labels.cpu().numpy().astype(int))
+    est.distances_ = store.split(distances.cpu().numpy())
+    local_sum = distances.sum().reshape(1)
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(local_sum, op=dist.ReduceOp.SUM, group=group)
+    est.inertia_ = float(local_sum.item())
+    return est
