@@ -37,51 +37,17 @@ struct BlockCand {
 // Workspace layout for the pass: [unsigned counter | pad to 16 | BlockCand[grid]]
 static inline int pass_grid() { return sm_count() * 8; }
 
-// ---------------------------------------------------------------------------
-// K2
-// ---------------------------------------------------------------------------
-template <typename T, int METRIC, bool VEC>
-__global__ void __launch_bounds__(kThreads)
-kcenters_pass_kernel(const T *__restrict__ X, long long n, int d, long long ld,
-                     const T *__restrict__ center, int label,
-                     double *__restrict__ dist, int *__restrict__ labels,
-                     long long row_offset, BlockCand *__restrict__ block_cands,
-                     unsigned *__restrict__ counter, msmb200_candidate *__restrict__ out,
-                     int G)
+
+// Block arg-max, per-block candidate, last-block-done reduction; the winner (value,
+// global index, frame) is published in `out`.  First index wins ties == np.argmax
+// (kcenters.py:97).  Must be reached by every thread of the block.
+template <typename T>
+__device__ __forceinline__ void pass_publish(ArgMax best, const T *__restrict__ X, long long n,
+                                             int d, long long ld, long long row_offset,
+                                             BlockCand *__restrict__ block_cands,
+                                             unsigned *__restrict__ counter,
+                                             msmb200_candidate *__restrict__ out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *s_center = reinterpret_cast<T *>(smem_raw);
-    for (int j = threadIdx.x; j < d; j += blockDim.x) s_center[j] = center[j];
-    __syncthreads();
-
-    MSMB_GROUP_SETUP();
-
-    ArgMax best;
-    best.v = -INFINITY;
-    best.i = 0x7fffffffffffffffLL;
-
-    // warp-uniform trip count: every lane joins every shuffle; out-of-range
-    // groups recompute the last row and discard it.
-    for (long long r0 = warp_group0; r0 < n; r0 += n_groups) {
-        const long long r_raw = r0 + group_in_warp;
-        const bool valid = r_raw < n;
-        const long long r = valid ? r_raw : n - 1;
-        double dv = group_distance<METRIC, T, VEC>(X + r * ld, s_center, d, lane_in_group, G);
-        if (valid && lane_in_group == 0) {
-            double cur = dist[r];
-            if (dv < cur) {          // strict: kcenters.py:93
-                cur = dv;
-                dist[r] = dv;
-                labels[r] = label;
-            }
-            if (cur > best.v) {      // rows visited in increasing order per thread
-                best.v = cur;
-                best.i = r;
-            }
-        }
-    }
-
-    // block arg-max (first index wins ties == np.argmax, kcenters.py:97)
     __shared__ ArgMax s_warp[kThreads / 32];
     __shared__ bool s_is_last;
     best = argmax_warp(best);
@@ -131,6 +97,138 @@ kcenters_pass_kernel(const T *__restrict__ X, long long n, int d, long long ld,
     T *payload = reinterpret_cast<T *>(out + 1);
     if (n > 0)
         for (int j = threadIdx.x; j < d; j += blockDim.x) payload[j] = X[w.i * ld + j];
+}
+
+
+// ---------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------
+template <typename T, int METRIC, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+kcenters_pass_kernel(const T *__restrict__ X, long long n, int d, long long ld,
+                     const T *__restrict__ center, int label,
+                     double *__restrict__ dist, int *__restrict__ labels,
+                     long long row_offset, BlockCand *__restrict__ block_cands,
+                     unsigned *__restrict__ counter, msmb200_candidate *__restrict__ out,
+                     int G)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s_center = reinterpret_cast<T *>(smem_raw);
+    for (int j = threadIdx.x; j < d; j += blockDim.x) s_center[j] = center[j];
+    __syncthreads();
+
+    MSMB_GROUP_SETUP();
+
+    ArgMax best;
+    best.v = -INFINITY;
+    best.i = 0x7fffffffffffffffLL;
+
+    // warp-uniform trip count: every lane joins every shuffle; out-of-range
+    // groups recompute the last row and discard it.
+    for (long long r0 = warp_group0; r0 < n; r0 += n_groups) {
+        const long long r_raw = r0 + group_in_warp;
+        const bool valid = r_raw < n;
+        const long long r = valid ? r_raw : n - 1;
+        double dv = group_distance<METRIC, T, VEC>(X + r * ld, s_center, d, lane_in_group, G);
+        if (valid && lane_in_group == 0) {
+            double cur = dist[r];
+            if (dv < cur) {          // strict: kcenters.py:93
+                cur = dv;
+                dist[r] = dv;
+                labels[r] = label;
+            }
+            if (cur > best.v) {      // rows visited in increasing order per thread
+                best.v = cur;
+                best.i = r;
+            }
+        }
+    }
+
+    pass_publish<T>(best, X, n, d, ld, row_offset, block_cands, counter, out);
+}
+
+// ---------------------------------------------------------------------------
+// K2 fast path (float32 frames, 16-byte vector loads, d/4 == ITERS * G):
+// each sub-warp group streams R frames per iteration with all R*ITERS 16-byte
+// loads issued before the first use (bytes in flight per warp: R * 4 * d), the
+// centre lives in registers, the R float64 reductions are interleaved, and lane
+// j of a group owns the running-minimum update of frame j (its distances[] value
+// is prefetched before the arithmetic).  Same arithmetic as the generic kernel.
+// ---------------------------------------------------------------------------
+template <int METRIC, int ITERS, int R>
+__global__ void __launch_bounds__(kThreads)
+kcenters_pass_fast_kernel(const float *__restrict__ X, long long n, int d, long long ld,
+                          const float *__restrict__ center, int label,
+                          double *__restrict__ dist, int *__restrict__ labels,
+                          long long row_offset, BlockCand *__restrict__ block_cands,
+                          unsigned *__restrict__ counter, msmb200_candidate *__restrict__ out,
+                          int G)
+{
+    typedef Metric<METRIC, float> M;
+    const int lane_in_group = threadIdx.x & (G - 1);
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long NG = ((long long)gridDim.x * blockDim.x) / G;
+    const long long warp_gid0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / G);
+    const long long ld4 = ld >> 2;
+    const float4 *X4 = reinterpret_cast<const float4 *>(X);
+
+    float4 c[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+        c[i] = reinterpret_cast<const float4 *>(center)[lane_in_group + i * G];
+
+    ArgMax best{-INFINITY, 0x7fffffffffffffffLL};
+
+    for (long long it = 0; (it * R) * NG + warp_gid0 < n; ++it) {
+        long long rr[R];
+        float4 x[R][ITERS];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            rr[j] = (it * R + j) * NG + gid;
+            const long long rc = rr[j] < n ? rr[j] : n - 1;
+            const float4 *p = X4 + rc * ld4 + lane_in_group;
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) x[j][i] = ldg_stream(p + i * G);
+        }
+        long long myrow = -1;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (lane_in_group == j && rr[j] < n) myrow = rr[j];
+        double cur = INFINITY;
+        if (myrow >= 0) cur = __ldcg(dist + myrow);
+
+        double dv[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i) {
+                M::acc(a, b, x[j][i].x, c[i].x);
+                M::acc(a, b, x[j][i].y, c[i].y);
+                M::acc(a, b, x[j][i].z, c[i].z);
+                M::acc(a, b, x[j][i].w, c[i].w);
+            }
+            a = group_combine<M::kIsMax>(a, G);
+            if (M::kTwoAcc) b = group_combine<false>(b, G);
+            dv[j] = M::fin(a, b, d);
+        }
+        double mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (lane_in_group == j) mine = dv[j];
+        if (myrow >= 0) {
+            if (mine < cur) {            // strict: kcenters.py:93
+                cur = mine;
+                dist[myrow] = mine;
+                labels[myrow] = label;
+            }
+            if (cur > best.v) {          // a lane's rows increase with `it`
+                best.v = cur;
+                best.i = myrow;
+            }
+        }
+    }
+    pass_publish<float>(best, X, n, d, ld, row_offset, block_cands, counter, out);
 }
 
 template <typename T>
@@ -382,6 +480,24 @@ extern "C" int msmb200_kcenters_pass(const void *X, int64_t n, int d, int64_t ld
         // only within one launch, so any grid size is fine.
         size_t smem = (size_t)d * sizeof(T);
         smem = (smem + 15) & ~(size_t)15;
+        if (std::is_same<T, float>::value && vec && G >= 4 && (d / 4) % G == 0 &&
+            aligned16(center)) {
+            const int iters = (d / 4) / G;
+            bool done = true;
+#define MSMB_FAST(I, RR)                                                                       \
+            kcenters_pass_fast_kernel<METRIC, I, RR><<<grid, kThreads, 0, st>>>(              \
+                (const float *)X, n, d, ld, (const float *)center, center_label, distances,    \
+                labels, row_offset, cands, counter, out, G)
+            if (iters == 1) MSMB_FAST(1, 4);
+            else if (iters == 2) MSMB_FAST(2, 4);
+            else if (iters == 4) MSMB_FAST(4, 2);
+            else done = false;
+#undef MSMB_FAST
+            if (done) {
+                MSMB_LAUNCH_CHECK();
+                return MSMB200_OK;
+            }
+        }
         if (vec)
             kcenters_pass_kernel<T, METRIC, true><<<grid, kThreads, smem, st>>>(
                 (const T *)X, n, d, ld, (const T *)center, center_label, distances, labels,

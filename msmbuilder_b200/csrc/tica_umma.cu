@@ -48,7 +48,7 @@ constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
 constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
 constexpr int UM_SBO = 128;                     // next 8-feature group
 constexpr int UM_THREADS = 384;
-constexpr int UM_SLAB_TILES_DEFAULT = 128;      // 4096 frames of fp32 accumulation per flush
+constexpr int UM_SLAB_TILES_DEFAULT = 32;       // 1024 frames of fp32 TMEM accumulation per flush
 
 struct UmmaParams {
     const CUtensorMap *mapsA;     // [n_seq] unlagged
@@ -61,7 +61,8 @@ struct UmmaParams {
     int slab_tiles;
     int passes;                   // 3 = hi/lo split, 1 = plain tf32
     const float *shift;           // [D]
-    double *partials;             // [n_pairs][2][D][D]  (C_tau', C_00')
+    double *partials;             // [n_pairs][2][col][row]  (C_tau', C_00'), column-major so a
+                                  // warp (32 rows) touches 256 contiguous bytes per column
     double *sums;                 // [2][D]  (S_0', S_tau')  atomically accumulated
 };
 
@@ -355,7 +356,7 @@ tica_umma_kernel(const UmmaParams P)
         // ================================ epilogue (128 threads, both CTAs) =============
         const int ew = warp - 8;                       // == warp % 4: TMEM lane quarter
         const int row = UM_F * cta_rank + ew * 32 + lane;
-        double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + (size_t)row * UM_D;
+        double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
         uint32_t acc_phase = 0;
         for (int slab = 0; slab < n_slabs; ++slab) {
             mbar_wait(&ctl->acc_full, acc_phase);
@@ -365,14 +366,19 @@ tica_umma_kernel(const UmmaParams P)
             for (int c0 = 0; c0 < 512; c0 += 32) {
                 uint32_t v[32];
                 UM_TMEM_LD32(v, tmem + ((uint32_t)(ew * 32) << 16) + c0);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                double *dst = pc + (c0 < 256 ? c0 : (size_t)UM_D * UM_D + (c0 - 256));
+                // element (row, col) of matrix m lives at ((m*256 + col) * 256 + row):
+                // c0 runs over [C_tau cols 0..255 | C_00 cols 0..255] = m*256 + col directly
+                double *dst = pc + (size_t)c0 * UM_D;
+                double cur[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    double2 cur = *reinterpret_cast<double2 *>(dst + j);
-                    cur.x += (double)__uint_as_float(v[j]);
-                    cur.y += (double)__uint_as_float(v[j + 1]);
-                    *reinterpret_cast<double2 *>(dst + j) = cur;
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cur[j] = __ldcg(dst + (size_t)(half * 16 + j) * UM_D);
+                    if (half == 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        __stcg(dst + (size_t)(half * 16 + j) * UM_D,
+                               cur[j] + (double)__uint_as_float(v[half * 16 + j]));
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -496,9 +502,10 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
     if (idx >= (int)DD) return;
     const int i = idx / D, j = idx % D;
     double ctau = 0.0, c00 = 0.0;
+    const size_t tidx = (size_t)j * D + i;               // partials are column-major
     for (int p = 0; p < n_pairs; ++p) {
-        ctau += partials[(size_t)p * 2 * DD + idx];
-        c00 += partials[(size_t)p * 2 * DD + DD + idx];
+        ctau += partials[(size_t)p * 2 * DD + tidx];
+        c00 += partials[(size_t)p * 2 * DD + DD + tidx];
     }
     ctau += E[idx];
     c00 += E[DD + idx];
@@ -548,10 +555,18 @@ bool tica_umma_supported(int D, int64_t ld, int dtype, int lag)
     return D == UM_D && dtype == MSMB200_F32 && (ld % 4) == 0 && lag >= 1;
 }
 
+static constexpr int UM_MAX_PAIRS = 96;
+
+// caller-provided scratch: [shift | sums | E | es | partials for up to UM_MAX_PAIRS pairs]
+static size_t ws_fixed_bytes(int D)
+{
+    const size_t DD = (size_t)D * D;
+    return 4096 + sizeof(double) * (2 * D + 4 * DD + 3 * D) + 1024;
+}
 size_t tica_umma_workspace_bytes(int D)
 {
-    (void)D;
-    return 0;   // scratch is stream-ordered (cudaMallocAsync) inside the call
+    if (D != UM_D) return 0;
+    return ws_fixed_bytes(D) + sizeof(double) * 2 * (size_t)D * D * UM_MAX_PAIRS;
 }
 
 static int env_int(const char *name, int dflt)
@@ -564,7 +579,6 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                          int D, int64_t ld, int lag, int passes, double *acc, void *workspace,
                          size_t workspace_bytes, cudaStream_t st)
 {
-    (void)workspace; (void)workspace_bytes;
     EncodeTiledFn enc = encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -622,11 +636,27 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
 
     int n_pairs = sm_count() / 2;
     n_pairs = env_int("MSMB200_UMMA_PAIRS", n_pairs);
+    if (n_pairs > UM_MAX_PAIRS) n_pairs = UM_MAX_PAIRS;
     if (tiles < n_pairs) n_pairs = (int)(tiles > 0 ? tiles : 1);
     const size_t DD = (size_t)D * D;
+    const size_t need = ws_fixed_bytes(D) + sizeof(double) * 2 * DD * n_pairs;
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
+        set_error("tica_accumulate: workspace too small or misaligned (%zu < %zu); size it with "
+                  "msmb200_tica_workspace_bytes", workspace_bytes, need);
+        return MSMB200_E_INVALID;
+    }
+    static bool pool_tuned = false;
+    if (!pool_tuned) {   // keep the small stream-ordered table allocations cached
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_tuned = true;
+    }
 
-    // one stream-ordered scratch block:
-    // [mapsA | mapsB | tile_prefix | seq_blocks | edge seqs | shift | sums | E | es | partials]
+    // small per-call tables: stream-ordered allocation  [mapsA | mapsB | tile_prefix | seq_blocks | edge seqs]
     auto align_up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 0;
     const size_t o_mapsA = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
@@ -634,15 +664,17 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const size_t o_prefix = off; off = align_up(off + sizeof(int) * (n_seq + 1), 128);
     const size_t o_blocks = off; off = align_up(off + sizeof(int) * n_seq, 128);
     const size_t o_eseq = off; off = align_up(off + sizeof(EdgeSeq) * n_seq, 128);
-    const size_t o_shift = off; off = align_up(off + sizeof(float) * D, 128);
-    const size_t o_zero = off;       // everything from here on is zero-initialised
-    const size_t o_sums = off; off = align_up(off + sizeof(double) * 2 * D, 128);
-    const size_t o_E = off; off = align_up(off + sizeof(double) * 4 * DD, 128);
-    const size_t o_es = off; off = align_up(off + sizeof(double) * 3 * D, 128);
-    const size_t o_part = off; off = align_up(off + sizeof(double) * 2 * DD * n_pairs, 128);
     unsigned char *scratch = nullptr;
     MSMB_CUDA(cudaMallocAsync(&scratch, off, st));
-    MSMB_CUDA(cudaMemsetAsync(scratch + o_zero, 0, off - o_zero, st));
+    // big zero-initialised part: caller's workspace  [shift | sums | E | es | partials]
+    unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
+    size_t woff = 0;
+    const size_t w_shift = woff; woff = align_up(woff + sizeof(float) * D, 256);
+    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * 2 * D, 256);
+    const size_t w_E = woff; woff = align_up(woff + sizeof(double) * 4 * DD, 256);
+    const size_t w_es = woff; woff = align_up(woff + sizeof(double) * 3 * D, 256);
+    const size_t w_part = woff; woff += sizeof(double) * 2 * DD * n_pairs;
+    MSMB_CUDA(cudaMemsetAsync(wsb + w_sums, 0, woff - w_sums, st));
 
     std::vector<CUtensorMap> mA(n_seq), mB(n_seq);
     for (int s = 0; s < n_seq; ++s) { mA[s] = maps[2 * (size_t)s]; mB[s] = maps[2 * (size_t)s + 1]; }
@@ -653,7 +685,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     MSMB_CUDA(cudaMemcpyAsync(scratch + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq, cudaMemcpyHostToDevice, st));
     MSMB_CUDA(cudaStreamSynchronize(st));    // host vectors are pageable: keep them alive until copied
 
-    float *d_shift = reinterpret_cast<float *>(scratch + o_shift);
+    float *d_shift = reinterpret_cast<float *>(wsb + w_shift);
     tica_shift_kernel<<<1, 256, 0, st>>>(seqs[0].base, seqs[0].n, ld, D, d_shift);
     MSMB_LAUNCH_CHECK();
 
@@ -669,8 +701,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (P.slab_tiles < 1) P.slab_tiles = 1;
     P.passes = passes;
     P.shift = d_shift;
-    P.partials = reinterpret_cast<double *>(scratch + o_part);
-    P.sums = reinterpret_cast<double *>(scratch + o_sums);
+    P.partials = reinterpret_cast<double *>(wsb + w_part);
+    P.sums = reinterpret_cast<double *>(wsb + w_sums);
 
     if (tiles > 0) {
         const size_t smem = (size_t)UM_STAGES * UM_STAGE_BYTES + sizeof(UmmaSmem) + 1024;
@@ -687,12 +719,12 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         dim3 grid(n_seq < 64 ? n_seq : 64, D / 16);
         tica_umma_edges_kernel<<<grid, 256, 0, st>>>(
             reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq, ld, lag, d_shift,
-            reinterpret_cast<double *>(scratch + o_E), reinterpret_cast<double *>(scratch + o_es));
+            reinterpret_cast<double *>(wsb + w_E), reinterpret_cast<double *>(wsb + w_es));
         MSMB_LAUNCH_CHECK();
     }
     tica_umma_finalize_kernel<<<(unsigned)((DD + 255) / 256), 256, 0, st>>>(
-        P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(scratch + o_E),
-        reinterpret_cast<const double *>(scratch + o_es), d_shift, n_pairs_total, n_obs,
+        P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(wsb + w_E),
+        reinterpret_cast<const double *>(wsb + w_es), d_shift, n_pairs_total, n_obs,
         (double)n_seq, acc);
     MSMB_LAUNCH_CHECK();
     MSMB_CUDA(cudaFreeAsync(scratch, st));

@@ -28,7 +28,7 @@ def main():
     print("simt_f64: %.1f ms for %d frames; eig %s" % (1e3 * (time.time() - t0), n_seq * L, ref.eigenvalues_[:4]))
     pr = packed(ref)
     for engine in ("umma_3xtf32", "umma_tf32"):
-        for slab in (16, 128, 1024, 100000):
+        for slab in (8, 16, 32, 64, 100000):
             os.environ["MSMB200_UMMA_SLAB_TILES"] = str(slab)
             m = tICA(n_components=8, lag_time=10, engine=engine)
             m.fit(seqs)
