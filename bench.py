@@ -276,6 +276,9 @@ def run_ours(args):
     launches0 = lib.msmb200_launch_count()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    profiling = os.environ.get("MSMB_PROFILE") == "1"     # ncu --profile-from-start off
+    if profiling:
+        torch.cuda.profiler.start()
     t_start.record()
     for _ in range(args.steps):
         step(True)
@@ -284,6 +287,8 @@ def run_ours(args):
         phase_ms["kcenters"].append(ev[1].elapsed_time(ev[2]))
     t_stop.record()
     barrier()
+    if profiling:
+        torch.cuda.profiler.stop()
     launches = int(lib.msmb200_launch_count() - launches0)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = torch.tensor([t_start.elapsed_time(t_stop)], dtype=torch.float64, device="cuda")

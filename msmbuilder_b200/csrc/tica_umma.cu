@@ -20,12 +20,15 @@
 //  * Operands are K-major, no swizzle: [row-block of 4 frames][feature][4 frames],
 //    i.e. 16-byte chunks = 4 consecutive frames of one feature, core matrix =
 //    8 features x 4 frames (LBO = 2048 B between row-blocks, SBO = 128 B).
-//  * TMA: one 4-D tensor map per sequence and operand, dims (4 feat, 4 frames,
-//    D/4 groups, n/4 row-blocks), box (4,4,32,KT/4) -> smem [rb][g][frame][4 feat]:
-//    every 64-byte block already sits where its K-major transpose belongs, so the
-//    converter warps transpose 4x4 inside a lane quad (4 shuffles) IN PLACE.
-//    The lagged operand has its own map whose base is shifted by lag rows, so any
-//    lag works and no operand needs an unaligned descriptor.
+//  * TMA: one 3-D tensor map per sequence and operand, dims (32 feat, rows, D/32
+//    blocks), box (32, KT, 4), SWIZZLE_128B -> smem [block][frame][128 B]: full
+//    128-byte rows, so every 32-byte sector fetched is used (a first version with
+//    16-byte boxes was TMA-bound at ~4 useful B/cycle/SM, profiles/r1).  The converter
+//    warps read a 4-frame x 4-feature block per lane quad (the swizzle makes that
+//    bank-conflict free), transpose it with 4 shuffles and write the K-major hi/lo
+//    operand tiles.  The lagged operand has its own map whose base is shifted by lag
+//    rows, so any lag works and no operand needs an unaligned descriptor; rows past
+//    the last pair index are zero-filled by TMA.
 //  * Precision: x' = hi + lo with hi = tf32_rn(x'), lo = tf32_rn(x' - hi);
 //    products hi*hi + hi*lo + lo*hi (3 MMAs, ~2^-21 relative), fp32 accumulation in
 //    TMEM over a bounded slab of frames, then flushed into float64 partials.
@@ -42,9 +45,10 @@ constexpr int UM_D = 256;                       // features handled by this kern
 constexpr int UM_F = 128;                       // features per CTA
 constexpr int UM_KT = 32;                       // frames per tile
 constexpr int UM_RB = UM_KT / 4;                // 4-frame row-blocks per tile
-constexpr int UM_STAGES = 3;
+constexpr int UM_STAGES = 2;                    // raw ring and operand ring depth
 constexpr int UM_TILE_BYTES = UM_KT * UM_F * 4; // 16 KB
-constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+constexpr int UM_RAW_BYTES = 2 * UM_TILE_BYTES;     // raw A, raw B (TMA destinations)
+constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo (UMMA operands)
 constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
 constexpr int UM_SBO = 128;                     // next 8-feature group
 constexpr int UM_THREADS = 384;
@@ -54,7 +58,7 @@ struct UmmaParams {
     const CUtensorMap *mapsA;     // [n_seq] unlagged
     const CUtensorMap *mapsB;     // [n_seq] base shifted by lag rows
     const int *tile_prefix;       // [n_seq + 1] tiles before sequence s
-    const int *seq_blocks;        // [n_seq] full 4-frame blocks of pair indices
+    const int *seq_pairs;         // [n_seq] pair indices of sequence s (n_s - lag)
     int n_seq;
     int n_tiles;
     int n_pairs;                  // clusters launched
@@ -97,13 +101,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar,
-                                            int c0, int c1, int c2, int c3)
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// frames are read once: mark them evict-first so the float64 partials stay L2 resident
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2, uint64_t policy)
 {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
-        :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5}], [%2], %6;"
+        :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all()
@@ -165,13 +176,14 @@ __device__ __forceinline__ float tf32_rn(float x)
     : "r"(taddr) : "memory")
 
 struct UmmaSmem {
-    uint64_t full[UM_STAGES];      // TMA landed (tx bytes), local
+    uint64_t raw_full[UM_STAGES];  // TMA landed (tx bytes), local
+    uint64_t raw_empty[UM_STAGES]; // converters done reading the raw stage (4 warp arrivals), local
     uint64_t conv[UM_STAGES];      // operands converted; the LEADER's copy is used (8 arrivals)
-    uint64_t empty[UM_STAGES];     // MMAs done reading the stage (multicast commit), local
+    uint64_t empty[UM_STAGES];     // MMAs done reading the operand stage (multicast commit), local
     uint64_t acc_full;             // slab finished (multicast commit), local
     uint64_t acc_empty;            // accumulators drained; the LEADER's copy is used (8 arrivals)
     uint32_t tmem_base;
-    int valid_rb[UM_STAGES];
+    int valid_rows[UM_STAGES];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -182,7 +194,9 @@ tica_umma_kernel(const UmmaParams P)
     // 1 KB-aligned operand ring, control block behind it
     unsigned char *ring = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    UmmaSmem *ctl = reinterpret_cast<UmmaSmem *>(ring + UM_STAGES * UM_STAGE_BYTES);
+    unsigned char *raw_ring = ring;                                   // [UM_STAGES][A raw | B raw]
+    unsigned char *op_ring = ring + UM_STAGES * UM_RAW_BYTES;         // [UM_STAGES][A_hi|A_lo|B_hi|B_lo]
+    UmmaSmem *ctl = reinterpret_cast<UmmaSmem *>(op_ring + UM_STAGES * UM_STAGE_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t cta_rank;
@@ -197,7 +211,8 @@ tica_umma_kernel(const UmmaParams P)
 
     if (tid == 0) {
         for (int s = 0; s < UM_STAGES; ++s) {
-            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->raw_full[s], 1);
+            mbar_init(&ctl->raw_empty[s], 4);
             mbar_init(&ctl->conv[s], 8);
             mbar_init(&ctl->empty[s], 1);
         }
@@ -230,18 +245,19 @@ tica_umma_kernel(const UmmaParams P)
             }
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t policy = l2_evict_first_policy();
             for (long long t = t_begin; t < t_end; ++t) {
                 while (t >= P.tile_prefix[s + 1]) ++s;
-                const int rb0 = (int)(t - P.tile_prefix[s]) * UM_RB;
-                int valid = P.seq_blocks[s] - rb0;
-                if (valid > UM_RB) valid = UM_RB;
-                mbar_wait(&ctl->empty[stage], phase ^ 1);
-                ctl->valid_rb[stage] = valid;
-                mbar_expect_tx(&ctl->full[stage], 2 * UM_TILE_BYTES);
-                unsigned char *st = ring + stage * UM_STAGE_BYTES;
-                tma_load_4d(st, &P.mapsA[s], &ctl->full[stage], 0, 0, 32 * (int)cta_rank, rb0);
-                tma_load_4d(st + 2 * UM_TILE_BYTES, &P.mapsB[s], &ctl->full[stage], 0, 0,
-                            32 * (int)cta_rank, rb0);
+                const int row0 = (int)(t - P.tile_prefix[s]) * UM_KT;
+                int valid = P.seq_pairs[s] - row0;
+                if (valid > UM_KT) valid = UM_KT;
+                mbar_wait(&ctl->raw_empty[stage], phase ^ 1);
+                ctl->valid_rows[stage] = valid;
+                mbar_expect_tx(&ctl->raw_full[stage], 2 * UM_TILE_BYTES);
+                unsigned char *st = raw_ring + stage * UM_RAW_BYTES;
+                tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
+                tma_load_3d(st + UM_TILE_BYTES, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
+                            4 * (int)cta_rank, policy);
                 if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -249,7 +265,7 @@ tica_umma_kernel(const UmmaParams P)
         // ================================ MMA issuer (leader CTA, one lane) =============
         if (cta_rank == 0 && lane == 0 && my_tiles > 0) {
             const uint32_t idesc = umma_idesc();
-            const uint32_t ring_addr = smem_u32(ring);
+            const uint32_t ring_addr = smem_u32(op_ring);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int t = 0; t < my_tiles; ++t) {
@@ -289,28 +305,41 @@ tica_umma_kernel(const UmmaParams P)
         }
     } else if (warp >= 4 && warp < 8) {
         // ================================ converters (128 threads, both CTAs) ==========
-        const int ct = tid - 128;
-        const int g = ct >> 2, q = ct & 3;             // quad g owns feature group g, lane q a frame / feature
+        // Lane map (one 4-frame row-block of the tile per iteration, all 128 threads):
+        //   warp w  -> 32-feature block w of this CTA (one 128-byte swizzled row segment)
+        //   lane    -> q = lane & 3 frame inside the row-block, and feature group
+        //              g8 = (lane >> 3) ^ ((lane & 4) ? 5 : 0) inside the block.
+        // A quad (4 adjacent lanes) owns one 4x4 block; the pairing g8 / g8^5 inside an
+        // 8-lane phase makes both the swizzled 16-byte reads and the K-major 16-byte
+        // writes hit 8 distinct bank groups.
+        const int cw = warp - 4;
+        const int q = lane & 3;
+        const int g8 = (lane >> 3) ^ ((lane & 4) ? 5 : 0);
+        const int g = 8 * cw + g8;                       // feature group inside the CTA (0..31)
         const float4 sh = *reinterpret_cast<const float4 *>(P.shift + UM_F * cta_rank + 4 * g);
         const bool split = P.passes == 3;
         double sumA = 0.0, sumB = 0.0;                 // column sums of feature 128*rank + 4g + q
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < my_tiles; ++t) {
-            mbar_wait(&ctl->full[stage], phase);
-            const int valid = ctl->valid_rb[stage];
-            unsigned char *st = ring + stage * UM_STAGE_BYTES;
+            mbar_wait(&ctl->raw_full[stage], phase);
+            mbar_wait(&ctl->empty[stage], phase ^ 1);      // UMMA finished with this operand stage
+            const int valid = ctl->valid_rows[stage];
+            const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
+            unsigned char *st = op_ring + stage * UM_STAGE_BYTES;
             float tsA = 0.f, tsB = 0.f;
 #pragma unroll
             for (int op = 0; op < 2; ++op) {
+                const unsigned char *raw = rawst + op * UM_TILE_BYTES + cw * (UM_KT * 128);
                 unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES;
                 unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
-#pragma unroll 2
+#pragma unroll 4
                 for (int rb = 0; rb < UM_RB; ++rb) {
-                    const int off = (rb * 32 + g) * 64 + q * 16;
+                    const int r = 4 * rb + q;              // frame inside the tile
                     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    if (rb < valid) {
-                        const float4 v = *reinterpret_cast<const float4 *>(hi_buf + off);
+                    if (r < valid) {
+                        const float4 v = *reinterpret_cast<const float4 *>(
+                            raw + r * 128 + ((g8 ^ (r & 7)) << 4));
                         a0 = v.x - sh.x; a1 = v.y - sh.y; a2 = v.z - sh.z; a3 = v.w - sh.w;
                     }
                     // 4x4 transpose inside the quad: lane q holds frame q (4 features) ->
@@ -329,6 +358,7 @@ tica_umma_kernel(const UmmaParams P)
                     }
                     const float s4 = (a0 + a1) + (a2 + a3);
                     if (op == 0) tsA += s4; else tsB += s4;
+                    const int off = rb * UM_LBO + (4 * g + q) * 16;
                     float4 h;
                     h.x = tf32_rn(a0); h.y = tf32_rn(a1); h.z = tf32_rn(a2); h.w = tf32_rn(a3);
                     *reinterpret_cast<float4 *>(hi_buf + off) = h;
@@ -344,7 +374,11 @@ tica_umma_kernel(const UmmaParams P)
             sumB += (double)tsB;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&ctl->conv[stage], 0);
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                             :: "r"(smem_u32(&ctl->raw_empty[stage])) : "memory");
+                mbar_arrive_cluster(&ctl->conv[stage], 0);
+            }
             if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
         }
         if (my_tiles > 0) {
@@ -441,7 +475,7 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
         const float *X = seqs[s].base;
         const long long n = seqs[s].n;
         const long long Pn = n - lag;
-        const long long R = (Pn / 4) * 4;
+        const long long R = Pn;       // every pair index goes through the tensor cores (TMA zero-fills the tail)
         // row list: remainder pairs, head rows, tail rows
         const int n_rem = (int)(Pn - R);
         const long long total = n_rem + 2LL * lag;
@@ -552,7 +586,7 @@ static EncodeTiledFn encode_fn()
 
 bool tica_umma_supported(int D, int64_t ld, int dtype, int lag)
 {
-    return D == UM_D && dtype == MSMB200_F32 && (ld % 4) == 0 && lag >= 1;
+    return D == UM_D && dtype == MSMB200_F32 && (ld % 4) == 0 && lag >= 1;   // 16-byte row pitch for TMA
 }
 
 static constexpr int UM_MAX_PAIRS = 96;
@@ -604,27 +638,31 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (n_seq == 0) return MSMB200_OK;
 
     std::vector<CUtensorMap> maps(2 * (size_t)n_seq);
-    std::vector<int> tile_prefix(n_seq + 1, 0), seq_blocks(n_seq, 0);
+    std::vector<int> tile_prefix(n_seq + 1, 0), seq_pairs(n_seq, 0);
     long long tiles = 0;
     for (int s = 0; s < n_seq; ++s) {
-        const long long Q = (seqs[s].n - lag) / 4;      // full 4-frame blocks of pair indices
-        seq_blocks[s] = (int)Q;
+        const long long Pn = seqs[s].n - lag;           // pair indices (>= 1)
+        if (Pn > 0x7fffffffLL) {
+            set_error("sequence too long for the tcgen05 engine");
+            return MSMB200_E_UNSUPPORTED;
+        }
+        seq_pairs[s] = (int)Pn;
         tile_prefix[s] = (int)tiles;
-        tiles += (Q + UM_RB - 1) / UM_RB;
+        tiles += (Pn + UM_KT - 1) / UM_KT;
         if (tiles > 0x7fffffffLL) {
             set_error("too many tiles");
             return MSMB200_E_UNSUPPORTED;
         }
         for (int which = 0; which < 2; ++which) {
-            // Q == 0: the map is never used (no tiles); encode a 1-block dummy
-            cuuint64_t dims[4] = {4, 4, (cuuint64_t)(D / 4), (cuuint64_t)(Q > 0 ? Q : 1)};
-            cuuint64_t strides[3] = {(cuuint64_t)ld * 4, 16, (cuuint64_t)ld * 16};
-            cuuint32_t box[4] = {4, 4, 32, UM_RB};
-            cuuint32_t es[4] = {1, 1, 1, 1};
+            // (32 features, Pn rows, D/32 blocks); rows >= Pn read as zeros
+            cuuint64_t dims[3] = {32, (cuuint64_t)Pn, (cuuint64_t)(D / 32)};
+            cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+            cuuint32_t box[3] = {32, UM_KT, 4};
+            cuuint32_t es[3] = {1, 1, 1};
             void *base = (void *)(seqs[s].base + (which ? (size_t)lag * ld : 0));
-            CUresult r = enc(&maps[2 * (size_t)s + which], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
+            CUresult r = enc(&maps[2 * (size_t)s + which], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                              dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 set_error("cuTensorMapEncodeTiled failed (%d) for sequence %d", (int)r, s);
@@ -656,7 +694,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         pool_tuned = true;
     }
 
-    // small per-call tables: stream-ordered allocation  [mapsA | mapsB | tile_prefix | seq_blocks | edge seqs]
+    // small per-call tables: stream-ordered allocation  [mapsA | mapsB | tile_prefix | seq_pairs | edge seqs]
     auto align_up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
     size_t off = 0;
     const size_t o_mapsA = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
@@ -681,7 +719,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     MSMB_CUDA(cudaMemcpyAsync(scratch + o_mapsA, mA.data(), sizeof(CUtensorMap) * n_seq, cudaMemcpyHostToDevice, st));
     MSMB_CUDA(cudaMemcpyAsync(scratch + o_mapsB, mB.data(), sizeof(CUtensorMap) * n_seq, cudaMemcpyHostToDevice, st));
     MSMB_CUDA(cudaMemcpyAsync(scratch + o_prefix, tile_prefix.data(), sizeof(int) * (n_seq + 1), cudaMemcpyHostToDevice, st));
-    MSMB_CUDA(cudaMemcpyAsync(scratch + o_blocks, seq_blocks.data(), sizeof(int) * n_seq, cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaMemcpyAsync(scratch + o_blocks, seq_pairs.data(), sizeof(int) * n_seq, cudaMemcpyHostToDevice, st));
     MSMB_CUDA(cudaMemcpyAsync(scratch + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq, cudaMemcpyHostToDevice, st));
     MSMB_CUDA(cudaStreamSynchronize(st));    // host vectors are pageable: keep them alive until copied
 
@@ -693,7 +731,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.mapsA = reinterpret_cast<const CUtensorMap *>(scratch + o_mapsA);
     P.mapsB = reinterpret_cast<const CUtensorMap *>(scratch + o_mapsB);
     P.tile_prefix = reinterpret_cast<const int *>(scratch + o_prefix);
-    P.seq_blocks = reinterpret_cast<const int *>(scratch + o_blocks);
+    P.seq_pairs = reinterpret_cast<const int *>(scratch + o_blocks);
     P.n_seq = n_seq;
     P.n_tiles = (int)tiles;
     P.n_pairs = n_pairs;
@@ -705,7 +743,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.sums = reinterpret_cast<double *>(wsb + w_sums);
 
     if (tiles > 0) {
-        const size_t smem = (size_t)UM_STAGES * UM_STAGE_BYTES + sizeof(UmmaSmem) + 1024;
+        const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + sizeof(UmmaSmem) + 1024;
         static bool attr_set = false;
         if (!attr_set) {
             MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel,
