@@ -32,9 +32,9 @@
 //  * Precision: x' = hi + lo with hi = tf32_rn(x'), lo = tf32_rn(x' - hi);
 //    products hi*hi + hi*lo + lo*hi (3 MMAs, ~2^-21 relative), fp32 accumulation in
 //    TMEM over a bounded slab of frames, then flushed into float64 partials.
-//  * Warp roles (384 threads): w0 TMA producer, w1 MMA issuer (leader CTA), w2 TMEM
-//    allocator, w4-7 converters (fp32 -> centred tf32 hi/lo, transpose, column sums),
-//    w8-11 epilogue (tcgen05.ld -> float64 read-modify-write of the pair's partials).
+//  * Warp roles (512 threads): w0 TMA producer, w1 MMA issuer (leader CTA), w2 TMEM
+//    allocator, w4-11 converters (fp32 -> centred tf32 hi/lo, transpose, column sums),
+//    w12-15 epilogue (tcgen05.ld -> float64 read-modify-write of the pair's partials).
 #include "common.cuh"
 #include <cuda.h>
 #include <vector>
@@ -51,7 +51,8 @@ constexpr int UM_RAW_BYTES = 2 * UM_TILE_BYTES;     // raw A, raw B (TMA destina
 constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo (UMMA operands)
 constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
 constexpr int UM_SBO = 128;                     // next 8-feature group
-constexpr int UM_THREADS = 384;
+constexpr int UM_THREADS = 512;
+constexpr int UM_CONV_WARPS = 8;                // converter warps per CTA
 constexpr int UM_SLAB_TILES_DEFAULT = 32;       // 1024 frames of fp32 TMEM accumulation per flush
 
 struct UmmaParams {
@@ -177,8 +178,8 @@ __device__ __forceinline__ float tf32_rn(float x)
 
 struct UmmaSmem {
     uint64_t raw_full[UM_STAGES];  // TMA landed (tx bytes), local
-    uint64_t raw_empty[UM_STAGES]; // converters done reading the raw stage (4 warp arrivals), local
-    uint64_t conv[UM_STAGES];      // operands converted; the LEADER's copy is used (8 arrivals)
+    uint64_t raw_empty[UM_STAGES]; // converters done reading the raw stage (8 warp arrivals), local
+    uint64_t conv[UM_STAGES];      // operands converted; the LEADER's copy is used (16 arrivals)
     uint64_t empty[UM_STAGES];     // MMAs done reading the operand stage (multicast commit), local
     uint64_t acc_full;             // slab finished (multicast commit), local
     uint64_t acc_empty;            // accumulators drained; the LEADER's copy is used (8 arrivals)
@@ -212,8 +213,8 @@ tica_umma_kernel(const UmmaParams P)
     if (tid == 0) {
         for (int s = 0; s < UM_STAGES; ++s) {
             mbar_init(&ctl->raw_full[s], 1);
-            mbar_init(&ctl->raw_empty[s], 4);
-            mbar_init(&ctl->conv[s], 8);
+            mbar_init(&ctl->raw_empty[s], UM_CONV_WARPS);
+            mbar_init(&ctl->conv[s], 2 * UM_CONV_WARPS);
             mbar_init(&ctl->empty[s], 1);
         }
         mbar_init(&ctl->acc_full, 1);
@@ -303,22 +304,22 @@ tica_umma_kernel(const UmmaParams P)
                 if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ================================ converters (128 threads, both CTAs) ==========
-        // Lane map (one 4-frame row-block of the tile per iteration, all 128 threads):
-        //   warp w  -> 32-feature block w of this CTA (one 128-byte swizzled row segment)
-        //   lane    -> q = lane & 3 frame inside the row-block, and feature group
-        //              g8 = (lane >> 3) ^ ((lane & 4) ? 5 : 0) inside the block.
-        // A quad (4 adjacent lanes) owns one 4x4 block; the pairing g8 / g8^5 inside an
-        // 8-lane phase makes both the swizzled 16-byte reads and the K-major 16-byte
-        // writes hit 8 distinct bank groups.
+    } else if (warp >= 4 && warp < 4 + UM_CONV_WARPS) {
+        // ================================ converters (256 threads, both CTAs) ==========
+        // Thread map: warp cw & 3 -> 32-feature block of this CTA, lane -> feature inside
+        // the block; warps 0-3 take the even 4-frame row-blocks of a tile, warps 4-7 the
+        // odd ones.  A thread gathers the 4 frames of ITS feature with four 4-byte
+        // shared loads (a warp reads one 128-byte swizzled row segment per load: all 32
+        // banks, conflict free) and stores one 16-byte K-major chunk (a warp writes 512
+        // contiguous bytes): the fp32 -> tf32 hi/lo conversion transposes for free.
         const int cw = warp - 4;
-        const int q = lane & 3;
-        const int g8 = (lane >> 3) ^ ((lane & 4) ? 5 : 0);
-        const int g = 8 * cw + g8;                       // feature group inside the CTA (0..31)
-        const float4 sh = *reinterpret_cast<const float4 *>(P.shift + UM_F * cta_rank + 4 * g);
+        const int fb = cw & 3;                           // feature block (32 features)
+        const int rb_par = cw >> 2;                      // row-block parity handled by this warp
+        const int f_local = 32 * fb + lane;              // feature inside the CTA (0..127)
+        const int chunk = lane >> 2, within = (lane & 3) * 4;
+        const float sh = P.shift[UM_F * cta_rank + f_local];
         const bool split = P.passes == 3;
-        double sumA = 0.0, sumB = 0.0;                 // column sums of feature 128*rank + 4g + q
+        double sumA = 0.0, sumB = 0.0;                   // column sums of feature 128*rank + f_local
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < my_tiles; ++t) {
@@ -330,43 +331,30 @@ tica_umma_kernel(const UmmaParams P)
             float tsA = 0.f, tsB = 0.f;
 #pragma unroll
             for (int op = 0; op < 2; ++op) {
-                const unsigned char *raw = rawst + op * UM_TILE_BYTES + cw * (UM_KT * 128);
-                unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES;
+                const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
+                unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
                 unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
-#pragma unroll 4
-                for (int rb = 0; rb < UM_RB; ++rb) {
-                    const int r = 4 * rb + q;              // frame inside the tile
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    if (r < valid) {
-                        const float4 v = *reinterpret_cast<const float4 *>(
-                            raw + r * 128 + ((g8 ^ (r & 7)) << 4));
-                        a0 = v.x - sh.x; a1 = v.y - sh.y; a2 = v.z - sh.z; a3 = v.w - sh.w;
+#pragma unroll
+                for (int k = 0; k < UM_RB / 2; ++k) {
+                    const int rb = 2 * k + rb_par;
+                    float a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 4 * rb + i;          // frame inside the tile
+                        const float v = *reinterpret_cast<const float *>(
+                            raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                        a[i] = (r < valid) ? v - sh : 0.f;
                     }
-                    // 4x4 transpose inside the quad: lane q holds frame q (4 features) ->
-                    // lane q holds feature q (4 frames)
-                    {
-                        const bool o1 = q & 1;
-                        float t0 = o1 ? a0 : a1, t1 = o1 ? a2 : a3;
-                        float r0 = __shfl_xor_sync(0xffffffffu, t0, 1);
-                        float r1 = __shfl_xor_sync(0xffffffffu, t1, 1);
-                        if (o1) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
-                        const bool o2 = q & 2;
-                        t0 = o2 ? a0 : a2; t1 = o2 ? a1 : a3;
-                        r0 = __shfl_xor_sync(0xffffffffu, t0, 2);
-                        r1 = __shfl_xor_sync(0xffffffffu, t1, 2);
-                        if (o2) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
-                    }
-                    const float s4 = (a0 + a1) + (a2 + a3);
+                    const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
                     if (op == 0) tsA += s4; else tsB += s4;
-                    const int off = rb * UM_LBO + (4 * g + q) * 16;
                     float4 h;
-                    h.x = tf32_rn(a0); h.y = tf32_rn(a1); h.z = tf32_rn(a2); h.w = tf32_rn(a3);
-                    *reinterpret_cast<float4 *>(hi_buf + off) = h;
+                    h.x = tf32_rn(a[0]); h.y = tf32_rn(a[1]); h.z = tf32_rn(a[2]); h.w = tf32_rn(a[3]);
+                    *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = h;
                     if (split) {
                         float4 l;
-                        l.x = tf32_rn(a0 - h.x); l.y = tf32_rn(a1 - h.y);
-                        l.z = tf32_rn(a2 - h.z); l.w = tf32_rn(a3 - h.w);
-                        *reinterpret_cast<float4 *>(lo_buf + off) = l;
+                        l.x = tf32_rn(a[0] - h.x); l.y = tf32_rn(a[1] - h.y);
+                        l.z = tf32_rn(a[2] - h.z); l.w = tf32_rn(a[3] - h.w);
+                        *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
                     }
                 }
             }
@@ -382,13 +370,13 @@ tica_umma_kernel(const UmmaParams P)
             if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
         }
         if (my_tiles > 0) {
-            const int f = UM_F * cta_rank + 4 * g + q;
+            const int f = UM_F * cta_rank + f_local;
             atomicAdd(&P.sums[f], sumA);
             atomicAdd(&P.sums[UM_D + f], sumB);
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4 + UM_CONV_WARPS) {
         // ================================ epilogue (128 threads, both CTAs) =============
-        const int ew = warp - 8;                       // == warp % 4: TMEM lane quarter
+        const int ew = warp - (4 + UM_CONV_WARPS);                       // == warp % 4: TMEM lane quarter
         const int row = UM_F * cta_rank + ew * 32 + lane;
         double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
         uint32_t acc_phase = 0;
