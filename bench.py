@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, ws):
@@ -398,13 +398,31 @@ def run_ours(args):
             "sample": "%d of the same frames (D2H copy): tICA NumPy f64 %.2f s on %d BLAS threads + "
                       "%d KCenters passes %.2f s on 1 thread (the reference's libdistance is "
                       "single-threaded)" % (nc, a, cpu_threads(), k, b)}
-    print(json.dumps(line))
+    emit(line)
     if ws > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints
+    (e.g. NCCL's version banner) was diverted to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # stray prints -> stderr
     if args.impl == "reference":
         run_reference(args)
     else:
