@@ -159,11 +159,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
         :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+// round-to-nearest (ties away) to tf32's 10-bit mantissa with two full-rate integer ops
+// (cvt.rna.tf32.f32 goes through the slow conversion pipe: 16k conversions per tile)
 __device__ __forceinline__ float tf32_rn(float x)
 {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 #define UM_TMEM_LD32(v, taddr) asm volatile( \
@@ -178,9 +178,9 @@ __device__ __forceinline__ float tf32_rn(float x)
 
 struct UmmaSmem {
     uint64_t raw_full[UM_STAGES];  // TMA landed (tx bytes), local
-    uint64_t raw_empty[UM_STAGES]; // converters done reading the raw stage (8 warp arrivals), local
-    uint64_t conv[UM_STAGES];      // operands converted; the LEADER's copy is used (16 arrivals)
-    uint64_t empty[UM_STAGES];     // MMAs done reading the operand stage (multicast commit), local
+    uint64_t raw_empty[UM_STAGES]; // converters done reading the raw stage (1 arrival), local
+    uint64_t conv[UM_STAGES][2];   // half a tile (16 frames) converted; LEADER's copy, 2 arrivals (1/CTA)
+    uint64_t empty[UM_STAGES][2];  // MMAs done reading that half (multicast commit), local
     uint64_t acc_full;             // slab finished (multicast commit), local
     uint64_t acc_empty;            // accumulators drained; the LEADER's copy is used (8 arrivals)
     uint32_t tmem_base;
@@ -213,9 +213,11 @@ tica_umma_kernel(const UmmaParams P)
     if (tid == 0) {
         for (int s = 0; s < UM_STAGES; ++s) {
             mbar_init(&ctl->raw_full[s], 1);
-            mbar_init(&ctl->raw_empty[s], UM_CONV_WARPS);
-            mbar_init(&ctl->conv[s], 2 * UM_CONV_WARPS);
-            mbar_init(&ctl->empty[s], 1);
+            mbar_init(&ctl->raw_empty[s], 1);
+            for (int h = 0; h < 2; ++h) {
+                mbar_init(&ctl->conv[s][h], 2);
+                mbar_init(&ctl->empty[s][h], 1);
+            }
         }
         mbar_init(&ctl->acc_full, 1);
         mbar_init(&ctl->acc_empty, 8);
@@ -272,34 +274,38 @@ tica_umma_kernel(const UmmaParams P)
             for (int t = 0; t < my_tiles; ++t) {
                 const bool slab_first = (t % P.slab_tiles) == 0;
                 const bool slab_last = ((t + 1) % P.slab_tiles) == 0 || t + 1 == my_tiles;
-                mbar_wait(&ctl->conv[stage], phase);
-                if (slab_first && t > 0) {
-                    mbar_wait(&ctl->acc_empty, acc_phase);
-                    acc_phase ^= 1;
-                }
-                asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t a_hi = ring_addr + stage * UM_STAGE_BYTES;
                 const uint32_t a_lo = a_hi + UM_TILE_BYTES;
                 const uint32_t b_hi = a_hi + 2 * UM_TILE_BYTES;
                 const uint32_t b_lo = a_hi + 3 * UM_TILE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < UM_KT / 8; ++ks) {
-                    const uint32_t off = ks * 2 * UM_LBO;
-                    const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
-                    const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
-                    const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
-                    umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
-                    if (P.passes == 3) {
-                        umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
-                        umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                for (int h = 0; h < 2; ++h) {              // half tiles: 16 frames = 2 K-steps
+                    mbar_wait(&ctl->conv[stage][h], phase);
+                    if (slab_first && h == 0 && t > 0) {
+                        mbar_wait(&ctl->acc_empty, acc_phase);
+                        acc_phase ^= 1;
                     }
-                    umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
-                    if (P.passes == 3) {
-                        umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
-                        umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        const int ks = 2 * h + k2;
+                        const uint32_t off = ks * 2 * UM_LBO;
+                        const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
+                        const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
+                        const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
+                        umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
+                        if (P.passes == 3) {
+                            umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
+                            umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                        }
+                        umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                        if (P.passes == 3) {
+                            umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
+                            umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                        }
                     }
+                    umma_commit_pair(&ctl->empty[stage][h]);   // this half may be rewritten (both CTAs)
                 }
-                umma_commit_pair(&ctl->empty[stage]);     // stage may be refilled (both CTAs)
                 if (slab_last) umma_commit_pair(&ctl->acc_full);
                 if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -324,49 +330,53 @@ tica_umma_kernel(const UmmaParams P)
         uint32_t phase = 0;
         for (int t = 0; t < my_tiles; ++t) {
             mbar_wait(&ctl->raw_full[stage], phase);
-            mbar_wait(&ctl->empty[stage], phase ^ 1);      // UMMA finished with this operand stage
             const int valid = ctl->valid_rows[stage];
             const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
             unsigned char *st = op_ring + stage * UM_STAGE_BYTES;
             float tsA = 0.f, tsB = 0.f;
 #pragma unroll
-            for (int op = 0; op < 2; ++op) {
-                const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
-                unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
-                unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
+            for (int h = 0; h < 2; ++h) {                  // half tiles: row-blocks 4h .. 4h+3
+                mbar_wait(&ctl->empty[stage][h], phase ^ 1);   // UMMA finished with this half
 #pragma unroll
-                for (int k = 0; k < UM_RB / 2; ++k) {
-                    const int rb = 2 * k + rb_par;
-                    float a[4];
+                for (int op = 0; op < 2; ++op) {
+                    const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
+                    unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
+                    unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = 4 * rb + i;          // frame inside the tile
-                        const float v = *reinterpret_cast<const float *>(
-                            raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                        a[i] = (r < valid) ? v - sh : 0.f;
+                    for (int k = 0; k < 2; ++k) {
+                        const int rb = 4 * h + 2 * k + rb_par;
+                        float a[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = 4 * rb + i;          // frame inside the tile
+                            const float v = *reinterpret_cast<const float *>(
+                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            a[i] = (r < valid) ? v - sh : 0.f;
+                        }
+                        const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
+                        if (op == 0) tsA += s4; else tsB += s4;
+                        float4 hv;
+                        hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
+                        *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
+                        if (split) {
+                            float4 l;
+                            l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
+                            l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
+                            *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
+                        }
                     }
-                    const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
-                    if (op == 0) tsA += s4; else tsB += s4;
-                    float4 h;
-                    h.x = tf32_rn(a[0]); h.y = tf32_rn(a[1]); h.z = tf32_rn(a[2]); h.w = tf32_rn(a[3]);
-                    *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = h;
-                    if (split) {
-                        float4 l;
-                        l.x = tf32_rn(a[0] - h.x); l.y = tf32_rn(a[1] - h.y);
-                        l.z = tf32_rn(a[2] - h.z); l.w = tf32_rn(a[3] - h.w);
-                        *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
-                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
+                asm volatile("bar.sync 1, 256;" ::: "memory");                 // all 8 converter warps of this CTA
+                if (tid == 128) {
+                    if (h == 1)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                                     :: "r"(smem_u32(&ctl->raw_empty[stage])) : "memory");
+                    mbar_arrive_cluster(&ctl->conv[stage][h], 0);
                 }
             }
             sumA += (double)tsA;
             sumB += (double)tsB;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
-                             :: "r"(smem_u32(&ctl->raw_empty[stage])) : "memory");
-                mbar_arrive_cluster(&ctl->conv[stage], 0);
-            }
             if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
         }
         if (my_tiles > 0) {
