@@ -53,6 +53,7 @@ constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
 constexpr int UM_SBO = 128;                     // next 8-feature group
 constexpr int UM_THREADS = 512;
 constexpr int UM_CONV_WARPS = 8;                // converter warps per CTA
+constexpr int UM_FLUSH_WARPS = 12;              // warps per CTA that drain TMEM (4 epilogue + 8 converter)
 constexpr int UM_SLAB_TILES_DEFAULT = 32;       // 1024 frames of fp32 TMEM accumulation per flush
 
 struct UmmaParams {
@@ -69,6 +70,7 @@ struct UmmaParams {
     double *partials;             // [n_pairs][2][col][row]  (C_tau', C_00'), column-major so a
                                   // warp (32 rows) touches 256 contiguous bytes per column
     double *sums;                 // [2][D]  (S_0', S_tau')  atomically accumulated
+    long long *dbg;               // optional cycle counters of pair 0 (MSMB200_UMMA_DEBUG=1), else NULL
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -100,7 +102,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
 {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+    // same form as CUTLASS ClusterBarrier::arrive(cta_id): default .release at CTA scope --
+    // the smem writes it publishes were already made visible by fence.proxy.async + bar.sync,
+    // and .release.cluster would cost a MEMBAR.ALL.GPU + ERRBAR (~500 cycles) per arrival
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
@@ -179,13 +184,44 @@ __device__ __forceinline__ float tf32_rn(float x)
 struct UmmaSmem {
     uint64_t raw_full[UM_STAGES];  // TMA landed (tx bytes), local
     uint64_t raw_empty[UM_STAGES]; // converters done reading the raw stage (1 arrival), local
-    uint64_t conv[UM_STAGES][2];   // half a tile (16 frames) converted; LEADER's copy, 2 arrivals (1/CTA)
-    uint64_t empty[UM_STAGES][2];  // MMAs done reading that half (multicast commit), local
+    uint64_t conv[UM_STAGES];      // tile converted; the LEADER's copy is used, 2 arrivals (1 per CTA)
+    uint64_t empty[UM_STAGES];     // MMAs done reading the operand stage (multicast commit), local
     uint64_t acc_full;             // slab finished (multicast commit), local
-    uint64_t acc_empty;            // accumulators drained; the LEADER's copy is used (8 arrivals)
+    uint64_t acc_empty;            // accumulators drained; the LEADER's copy is used (24 arrivals)
     uint32_t tmem_base;
     int valid_rows[UM_STAGES];
 };
+
+
+// Drain this warp's share of the TMEM accumulators into the pair's float64 partials.
+// quarter = warp % 4 (the TMEM lanes a warp may touch); the 16 column chunks of 32 are
+// dealt round-robin to the `nparts` warps that share a quarter.
+__device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, int pair,
+                                            uint32_t cta_rank, int quarter, int part, int nparts,
+                                            int lane)
+{
+    const int row = UM_F * cta_rank + quarter * 32 + lane;
+    double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
+#pragma unroll 1
+    for (int c0 = 32 * part; c0 < 512; c0 += 32 * nparts) {
+        uint32_t v[32];
+        UM_TMEM_LD32(v, tmem + ((uint32_t)(quarter * 32) << 16) + c0);
+        // element (row, col) of matrix m lives at ((m*256 + col) * 256 + row); c0 runs over
+        // [C_tau cols 0..255 | C_00 cols 0..255] = m*256 + col directly
+        double *dst = pc + (size_t)c0 * UM_D;
+        double cur[16];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cur[j] = __ldcg(dst + (size_t)(half * 16 + j) * UM_D);
+            if (half == 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                __stcg(dst + (size_t)(half * 16 + j) * UM_D,
+                       cur[j] + (double)__uint_as_float(v[half * 16 + j]));
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
@@ -214,13 +250,11 @@ tica_umma_kernel(const UmmaParams P)
         for (int s = 0; s < UM_STAGES; ++s) {
             mbar_init(&ctl->raw_full[s], 1);
             mbar_init(&ctl->raw_empty[s], 1);
-            for (int h = 0; h < 2; ++h) {
-                mbar_init(&ctl->conv[s][h], 2);
-                mbar_init(&ctl->empty[s][h], 1);
-            }
+            mbar_init(&ctl->conv[s], 2);
+            mbar_init(&ctl->empty[s], 1);
         }
         mbar_init(&ctl->acc_full, 1);
-        mbar_init(&ctl->acc_empty, 8);
+        mbar_init(&ctl->acc_empty, 2 * UM_FLUSH_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -269,6 +303,9 @@ tica_umma_kernel(const UmmaParams P)
         if (cta_rank == 0 && lane == 0 && my_tiles > 0) {
             const uint32_t idesc = umma_idesc();
             const uint32_t ring_addr = smem_u32(op_ring);
+            const bool dbg_on = P.dbg != nullptr && pair == 0;
+            long long d_wait_conv = 0, d_wait_acc = 0;
+            const long long d_start = clock64();
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int t = 0; t < my_tiles; ++t) {
@@ -278,36 +315,41 @@ tica_umma_kernel(const UmmaParams P)
                 const uint32_t a_lo = a_hi + UM_TILE_BYTES;
                 const uint32_t b_hi = a_hi + 2 * UM_TILE_BYTES;
                 const uint32_t b_lo = a_hi + 3 * UM_TILE_BYTES;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {              // half tiles: 16 frames = 2 K-steps
-                    mbar_wait(&ctl->conv[stage][h], phase);
-                    if (slab_first && h == 0 && t > 0) {
-                        mbar_wait(&ctl->acc_empty, acc_phase);
-                        acc_phase ^= 1;
-                    }
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-                    for (int k2 = 0; k2 < 2; ++k2) {
-                        const int ks = 2 * h + k2;
-                        const uint32_t off = ks * 2 * UM_LBO;
-                        const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
-                        const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
-                        const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
-                        umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
-                        if (P.passes == 3) {
-                            umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
-                            umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
-                        }
-                        umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
-                        if (P.passes == 3) {
-                            umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
-                            umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
-                        }
-                    }
-                    umma_commit_pair(&ctl->empty[stage][h]);   // this half may be rewritten (both CTAs)
+                long long c0 = dbg_on ? clock64() : 0;
+                mbar_wait(&ctl->conv[stage], phase);
+                long long c1 = dbg_on ? clock64() : 0;
+                if (slab_first && t > 0) {
+                    mbar_wait(&ctl->acc_empty, acc_phase);
+                    acc_phase ^= 1;
                 }
+                if (dbg_on) { long long c2 = clock64(); d_wait_conv += c1 - c0; d_wait_acc += c2 - c1; }
+                asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                for (int ks = 0; ks < UM_KT / 8; ++ks) {
+                    const uint32_t off = ks * 2 * UM_LBO;
+                    const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
+                    const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
+                    const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
+                    umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
+                    if (P.passes == 3) {
+                        umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
+                        umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                    }
+                    umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                    if (P.passes == 3) {
+                        umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
+                        umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                    }
+                }
+                umma_commit_pair(&ctl->empty[stage]);      // stage may be rewritten (both CTAs)
                 if (slab_last) umma_commit_pair(&ctl->acc_full);
                 if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (dbg_on) {
+                P.dbg[0] = clock64() - d_start;      // MMA thread: total issue-loop cycles
+                P.dbg[1] = d_wait_conv;              //   of which waiting for converted operands
+                P.dbg[2] = d_wait_acc;               //   of which waiting for the TMEM flush
+                P.dbg[3] = my_tiles;
             }
         }
     } else if (warp >= 4 && warp < 4 + UM_CONV_WARPS) {
@@ -328,57 +370,84 @@ tica_umma_kernel(const UmmaParams P)
         double sumA = 0.0, sumB = 0.0;                   // column sums of feature 128*rank + f_local
         int stage = 0;
         uint32_t phase = 0;
+        const bool dbg_on = P.dbg != nullptr && pair == 0 && tid == 128 && cta_rank == 0;
+        long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0;
+        // the converters are idle whenever the accumulators are being drained (the UMMA pipe
+        // stalls, so no operand stage is released): they help, 2 of the 3 warps per TMEM quarter
+        int next_flush = 0;
+        uint32_t acc_phase = 0;
+        auto help_flush = [&]() {
+            mbar_wait(&ctl->acc_full, acc_phase);
+            acc_phase ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            flush_share(P, tmem, pair, cta_rank, cw & 3, 1 + (cw >> 2), 3, lane);
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0 && next_flush + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
+            ++next_flush;
+        };
         for (int t = 0; t < my_tiles; ++t) {
+            // slab j ends with tile min((j+1)*slab_tiles, my_tiles) - 1; by the time this warp is
+            // about to convert tile t >= end + 2 both operand stages are full, so it may as well drain
+            while (next_flush < n_slabs) {
+                int end = (next_flush + 1) * P.slab_tiles;
+                if (end > my_tiles) end = my_tiles;
+                if (end - 1 + 2 > t) break;
+                help_flush();
+            }
+            long long q0 = dbg_on ? clock64() : 0;
             mbar_wait(&ctl->raw_full[stage], phase);
+            long long q1 = dbg_on ? clock64() : 0;
+            mbar_wait(&ctl->empty[stage], phase ^ 1);      // UMMA finished with this operand stage
+            long long q2 = dbg_on ? clock64() : 0;
             const int valid = ctl->valid_rows[stage];
             const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
             unsigned char *st = op_ring + stage * UM_STAGE_BYTES;
             float tsA = 0.f, tsB = 0.f;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                  // half tiles: row-blocks 4h .. 4h+3
-                mbar_wait(&ctl->empty[stage][h], phase ^ 1);   // UMMA finished with this half
+            for (int op = 0; op < 2; ++op) {
+                const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
+                unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
+                unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
 #pragma unroll
-                for (int op = 0; op < 2; ++op) {
-                    const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
-                    unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
-                    unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
+                for (int k = 0; k < UM_RB / 2; ++k) {
+                    const int rb = 2 * k + rb_par;
+                    float a[4];
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int rb = 4 * h + 2 * k + rb_par;
-                        float a[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = 4 * rb + i;          // frame inside the tile
-                            const float v = *reinterpret_cast<const float *>(
-                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            a[i] = (r < valid) ? v - sh : 0.f;
-                        }
-                        const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
-                        if (op == 0) tsA += s4; else tsB += s4;
-                        float4 hv;
-                        hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
-                        *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
-                        if (split) {
-                            float4 l;
-                            l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
-                            l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
-                            *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 4 * rb + i;          // frame inside the tile
+                        const float v = *reinterpret_cast<const float *>(
+                            raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                        a[i] = (r < valid) ? v - sh : 0.f;
                     }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
-                asm volatile("bar.sync 1, 256;" ::: "memory");                 // all 8 converter warps of this CTA
-                if (tid == 128) {
-                    if (h == 1)
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
-                                     :: "r"(smem_u32(&ctl->raw_empty[stage])) : "memory");
-                    mbar_arrive_cluster(&ctl->conv[stage][h], 0);
+                    const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
+                    if (op == 0) tsA += s4; else tsB += s4;
+                    float4 hv;
+                    hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
+                    *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
+                    if (split) {
+                        float4 l;
+                        l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
+                        l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
+                        *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
+                    }
                 }
             }
             sumA += (double)tsA;
             sumB += (double)tsB;
+            long long q3 = dbg_on ? clock64() : 0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
+            asm volatile("bar.sync 1, 256;" ::: "memory");                 // all 8 converter warps of this CTA
+            if (tid == 128) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                             :: "r"(smem_u32(&ctl->raw_empty[stage])) : "memory");
+                mbar_arrive_cluster(&ctl->conv[stage], 0);
+            }
+            if (dbg_on) { long long q4 = clock64(); d_raw += q1 - q0; d_empty += q2 - q1; d_comp += q3 - q2; d_sync += q4 - q3; }
             if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
         }
+        while (next_flush < n_slabs) help_flush();
+        if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync; }
         if (my_tiles > 0) {
             const int f = UM_F * cta_rank + f_local;
             atomicAdd(&P.sums[f], sumA);
@@ -387,36 +456,21 @@ tica_umma_kernel(const UmmaParams P)
     } else if (warp >= 4 + UM_CONV_WARPS) {
         // ================================ epilogue (128 threads, both CTAs) =============
         const int ew = warp - (4 + UM_CONV_WARPS);                       // == warp % 4: TMEM lane quarter
-        const int row = UM_F * cta_rank + ew * 32 + lane;
-        double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
         uint32_t acc_phase = 0;
+        const bool dbg_on = P.dbg != nullptr && pair == 0 && cta_rank == 0 && ew == 0 && lane == 0;
+        long long d_flush = 0;
         for (int slab = 0; slab < n_slabs; ++slab) {
             mbar_wait(&ctl->acc_full, acc_phase);
+            const long long f0 = dbg_on ? clock64() : 0;
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll 1
-            for (int c0 = 0; c0 < 512; c0 += 32) {
-                uint32_t v[32];
-                UM_TMEM_LD32(v, tmem + ((uint32_t)(ew * 32) << 16) + c0);
-                // element (row, col) of matrix m lives at ((m*256 + col) * 256 + row):
-                // c0 runs over [C_tau cols 0..255 | C_00 cols 0..255] = m*256 + col directly
-                double *dst = pc + (size_t)c0 * UM_D;
-                double cur[16];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) cur[j] = __ldcg(dst + (size_t)(half * 16 + j) * UM_D);
-                    if (half == 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        __stcg(dst + (size_t)(half * 16 + j) * UM_D,
-                               cur[j] + (double)__uint_as_float(v[half * 16 + j]));
-                }
-            }
+            flush_share(P, tmem, pair, cta_rank, ew, 0, 3, lane);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0 && slab + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
+            if (dbg_on) d_flush += clock64() - f0;
         }
+        if (dbg_on) { P.dbg[8] = d_flush; P.dbg[9] = n_slabs; }
     }
 
     // teardown: nobody may still be using the peer's barriers / TMEM
@@ -739,6 +793,13 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.shift = d_shift;
     P.partials = reinterpret_cast<double *>(wsb + w_part);
     P.sums = reinterpret_cast<double *>(wsb + w_sums);
+    P.dbg = nullptr;
+    long long *d_dbg = nullptr;
+    if (env_int("MSMB200_UMMA_DEBUG", 0)) {
+        MSMB_CUDA(cudaMallocAsync(&d_dbg, sizeof(long long) * 16, st));
+        MSMB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16, st));
+        P.dbg = d_dbg;
+    }
 
     if (tiles > 0) {
         const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + sizeof(UmmaSmem) + 1024;
@@ -763,6 +824,18 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         reinterpret_cast<const double *>(wsb + w_es), d_shift, n_pairs_total, n_obs,
         (double)n_seq, acc);
     MSMB_LAUNCH_CHECK();
+    if (d_dbg) {
+        long long h[16];
+        MSMB_CUDA(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+        MSMB_CUDA(cudaStreamSynchronize(st));
+        fprintf(stderr, "[umma dbg pair0] tiles=%lld mma_loop=%lld cyc (%.0f/tile) wait_conv=%.1f%% wait_flush=%.1f%% | "
+                "conv thread: wait_raw=%.0f wait_empty=%.0f compute=%.0f fence+sync+arrive=%.0f cyc/tile | "
+                "flush=%.0f cyc/slab (%lld slabs)\n", h[3], h[0], (double)h[0] / (h[3] ? h[3] : 1),
+                100.0 * h[1] / (h[0] ? h[0] : 1), 100.0 * h[2] / (h[0] ? h[0] : 1),
+                (double)h[4] / (h[3] ? h[3] : 1), (double)h[5] / (h[3] ? h[3] : 1), (double)h[6] / (h[3] ? h[3] : 1),
+                (double)h[7] / (h[3] ? h[3] : 1), (double)h[8] / (h[9] ? h[9] : 1), h[9]);
+        MSMB_CUDA(cudaFreeAsync(d_dbg, st));
+    }
     MSMB_CUDA(cudaFreeAsync(scratch, st));
     return MSMB200_OK;
 }
