@@ -321,6 +321,178 @@ assign_exact_kernel(const T *__restrict__ X, long long n_out, int d, long long l
     }
 }
 
+// ---------------------------------------------------------------------------
+// K3 fast engine (float32 frames, euclidean / sqeuclidean): filter + refine.
+//   1. assign_filter_kernel: register-tiled (8 frames x 4 centres per thread) squared
+//      distances with the REFERENCE's float32 difference but float32 accumulation;
+//      tracks best and second-best.  |float32 sum - exact sum| <= ~(d+2) 2^-24 relative,
+//      so whenever second > best * (1 + margin) the float32 arg-min IS the exact arg-min.
+//   2. the (rare) frames inside the margin -- including exact ties -- are re-scanned by
+//      assign_exact_kernel's float64 arithmetic (lowest index wins, assign.hpp:69).
+//   3. assign_mindist_kernel recomputes the winning distance in float64 exactly like
+//      distance_kernels.h:54-65 for min_dist / inertia.
+// Labels are therefore identical to the exact engine; FP32-pipe bound (3 k d flop/frame).
+// ---------------------------------------------------------------------------
+constexpr int AF_TR = 128, AF_TC = 64, AF_DK = 16;
+
+__global__ void __launch_bounds__(256)
+assign_filter_kernel(const float *__restrict__ X, long long n_out, int d, long long ld,
+                     const float *__restrict__ Y, int k, const long long *__restrict__ rows,
+                     float margin, int *__restrict__ labels, int *__restrict__ amb_list,
+                     int *__restrict__ amb_count)
+{
+    __shared__ __align__(16) float Xs[AF_DK][AF_TR + 4];
+    __shared__ __align__(16) float Cs[AF_DK][AF_TC + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long row0 = (long long)blockIdx.x * AF_TR;
+
+    float best[8], second[8];
+    int arg[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { best[u] = INFINITY; second[u] = INFINITY; arg[u] = 0; }
+
+    for (int c0 = 0; c0 < k; c0 += AF_TC) {
+        float acc[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+        for (int d0 = 0; d0 < d; d0 += AF_DK) {
+            __syncthreads();
+            // stage X tile (AF_TR rows x AF_DK cols) and C tile (AF_TC x AF_DK), transposed
+            for (int e = tid; e < AF_TR * AF_DK; e += 256) {
+                const int r = e / AF_DK, c = e % AF_DK;
+                const long long i = row0 + r;
+                float v = 0.f;
+                if (i < n_out && d0 + c < d) {
+                    const long long src = rows ? rows[i] : i;
+                    v = X[src * ld + d0 + c];
+                }
+                Xs[c][r] = v;
+            }
+            for (int e = tid; e < AF_TC * AF_DK; e += 256) {
+                const int r = e / AF_DK, c = e % AF_DK;
+                float v = 0.f;
+                if (c0 + r < k && d0 + c < d) v = Y[(long long)(c0 + r) * d + d0 + c];
+                Cs[c][r] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < AF_DK; ++kk) {
+                const float4 xa = *reinterpret_cast<const float4 *>(&Xs[kk][ty * 8]);
+                const float4 xb = *reinterpret_cast<const float4 *>(&Xs[kk][ty * 8 + 4]);
+                const float4 cc = *reinterpret_cast<const float4 *>(&Cs[kk][tx * 4]);
+                const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float df = xv[u] - cv[v];
+                        acc[u][v] = fmaf(df, df, acc[u][v]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int j = c0 + tx * 4 + v;
+            if (j < k) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float a = acc[u][v];
+                    if (a < best[u]) { second[u] = best[u]; best[u] = a; arg[u] = j; }
+                    else if (a < second[u]) second[u] = a;
+                }
+            }
+        }
+    }
+    // merge the 16 tx lanes that share a frame (lanes of a half-warp)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best[u], off);
+            const float os = __shfl_xor_sync(0xffffffffu, second[u], off);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg[u], off);
+            // second = smallest of {larger of the two bests, both seconds}
+            const float hi = fmaxf(best[u], ob);
+            float ns = fminf(fminf(second[u], os), hi);
+            if (ob < best[u] || (ob == best[u] && oa < arg[u])) { best[u] = ob; arg[u] = oa; }
+            second[u] = ns;
+        }
+        const long long i = row0 + ty * 8 + u;
+        if (tx == 0 && i < n_out) {
+            labels[i] = arg[u];
+            // inside the rounding margin (or an exact tie, or NaN): exact re-scan needed
+            if (!(second[u] > best[u] * (1.f + margin) + 1e-37f)) {
+                const int slot = atomicAdd(amb_count, 1);
+                amb_list[slot] = (int)i;
+            }
+        }
+    }
+}
+
+// exact float64 re-scan of the frames listed in amb_list (one sub-warp group per frame)
+__global__ void __launch_bounds__(kThreads)
+assign_refine_kernel(const float *__restrict__ X, int d, long long ld, const float *__restrict__ Y,
+                     int k, const long long *__restrict__ rows, const int *__restrict__ amb_list,
+                     const int *__restrict__ amb_count, int *__restrict__ labels, int G, int sq)
+{
+    const int n_amb = *amb_count;
+    MSMB_GROUP_SETUP();
+    for (long long a0 = warp_group0; a0 < n_amb; a0 += n_groups) {
+        const long long a_raw = a0 + group_in_warp;
+        const bool valid = a_raw < n_amb;
+        const long long a = valid ? a_raw : n_amb - 1;
+        const long long i = amb_list[a];
+        const long long r = rows ? rows[i] : i;
+        const float *u = X + r * ld;
+        double bestd = 1.7976931348623157e308;
+        int arg = 0;
+        for (int j = 0; j < k; ++j) {
+            const double dv = sq
+                ? group_distance<MSMB200_SQEUCLIDEAN, float, false, false>(u, Y + (long long)j * d, d, lane_in_group, G)
+                : group_distance<MSMB200_EUCLIDEAN, float, false, false>(u, Y + (long long)j * d, d, lane_in_group, G);
+            if (dv < bestd) { bestd = dv; arg = j; }
+        }
+        if (valid && lane_in_group == 0) labels[i] = arg;
+    }
+}
+
+// exact float64 distance of every frame to its assigned centre (+ block partial sums)
+__global__ void __launch_bounds__(kThreads)
+assign_mindist_kernel(const float *__restrict__ X, long long n_out, int d, long long ld,
+                      const float *__restrict__ Y, const long long *__restrict__ rows,
+                      const int *__restrict__ labels, double *__restrict__ min_dist,
+                      double *__restrict__ block_sums, int G, int sq)
+{
+    MSMB_GROUP_SETUP();
+    double local = 0.0;
+    for (long long i0 = warp_group0; i0 < n_out; i0 += n_groups) {
+        const long long i_raw = i0 + group_in_warp;
+        const bool valid = i_raw < n_out;
+        const long long i = valid ? i_raw : n_out - 1;
+        const long long r = rows ? rows[i] : i;
+        const float *c = Y + (long long)labels[i] * d;
+        const double dv = sq
+            ? group_distance<MSMB200_SQEUCLIDEAN, float, false, true>(X + r * ld, c, d, lane_in_group, G)
+            : group_distance<MSMB200_EUCLIDEAN, float, false, true>(X + r * ld, c, d, lane_in_group, G);
+        if (valid && lane_in_group == 0) {
+            if (min_dist) min_dist[i] = dv;
+            local += dv;
+        }
+    }
+    __shared__ double s_sum[kThreads / 32];
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sacc = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) sacc += s_sum[w];
+        block_sums[blockIdx.x] = sacc;
+    }
+}
+
 __global__ void sum_partials_kernel(const double *__restrict__ partials, int n, double *out)
 {
     __shared__ double s[32];
@@ -543,10 +715,11 @@ extern "C" int msmb200_candidate_from_row(const void *X, int64_t row, int d, int
     return MSMB200_OK;
 }
 
+// workspace: [block partial sums (8*256 doubles) | amb_count (int, 256 B) | amb_list (n_out ints)]
 extern "C" size_t msmb200_assign_workspace_bytes(int64_t n_out, int k, int d)
 {
-    (void)n_out; (void)k; (void)d;
-    return sizeof(double) * (size_t)(8 * 256) + 256;
+    (void)k; (void)d;
+    return sizeof(double) * (size_t)(8 * 256) + 256 + sizeof(int) * (size_t)(n_out > 0 ? n_out : 0) + 256;
 }
 
 extern "C" int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t ld, int dtype,
@@ -560,6 +733,43 @@ extern "C" int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t l
     const int64_t n_out = rows ? n_rows : n;
     cudaStream_t st = (cudaStream_t)stream;
     double *partials = reinterpret_cast<double *>(workspace);
+    if (n_out == 0) {
+        if (inertia) MSMB_CUDA(cudaMemsetAsync(inertia, 0, sizeof(double), st));
+        return MSMB200_OK;
+    }
+    // fast engine: float32 euclidean family, at least 2 centres, index fits int32
+    const size_t fast_ws = sizeof(double) * (size_t)(8 * 256) + 256 + sizeof(int) * (size_t)n_out;
+    if (dtype == MSMB200_F32 && (metric == MSMB200_EUCLIDEAN || metric == MSMB200_SQEUCLIDEAN) &&
+        k >= 2 && n_out < 0x7fffffffLL && workspace_bytes >= fast_ws && !getenv("MSMB200_ASSIGN_EXACT")) {
+        unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
+        int *amb_count = reinterpret_cast<int *>(wsb + sizeof(double) * (size_t)(8 * 256));
+        int *amb_list = reinterpret_cast<int *>(wsb + sizeof(double) * (size_t)(8 * 256) + 256);
+        const int sq = metric == MSMB200_SQEUCLIDEAN;
+        const float margin = 4.0f * (float)(d + 4) * 5.9604645e-8f;     // 4 (d+4) 2^-24
+        MSMB_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), st));
+        const long long blocks = (n_out + AF_TR - 1) / AF_TR;
+        assign_filter_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+            (const float *)X, n_out, d, ld, (const float *)Y, k, (const long long *)rows, margin,
+            labels, amb_list, amb_count);
+        MSMB_LAUNCH_CHECK();
+        const int G = lanes_per_row(d, 1, false);
+        assign_refine_kernel<<<sm_count() * 4, kThreads, 0, st>>>(
+            (const float *)X, d, ld, (const float *)Y, k, (const long long *)rows, amb_list,
+            amb_count, labels, G, sq);
+        MSMB_LAUNCH_CHECK();
+        if (min_dist || inertia) {
+            const int grid = grid_for(n_out, G);
+            assign_mindist_kernel<<<grid, kThreads, 0, st>>>(
+                (const float *)X, n_out, d, ld, (const float *)Y, (const long long *)rows, labels,
+                min_dist, partials, G, sq);
+            MSMB_LAUNCH_CHECK();
+            if (inertia) {
+                sum_partials_kernel<<<1, 256, 0, st>>>(partials, grid, inertia);
+                MSMB_LAUNCH_CHECK();
+            }
+        }
+        return MSMB200_OK;
+    }
     return dispatch(dtype, metric, [&](auto t, auto m) -> int {
         typedef decltype(t) T;
         constexpr int METRIC = decltype(m)::value;

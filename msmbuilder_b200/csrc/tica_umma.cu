@@ -66,6 +66,7 @@ struct UmmaParams {
     int n_pairs;                  // clusters launched
     int slab_tiles;
     int passes;                   // 3 = hi/lo split, 1 = plain tf32
+    int collector;                // reuse the A operand through the collector buffer
     const float *shift;           // [D]
     double *partials;             // [n_pairs][2][col][row]  (C_tau', C_00'), column-major so a
                                   // warp (32 rows) touches 256 contiguous bytes per column
@@ -149,13 +150,14 @@ __device__ __forceinline__ uint32_t umma_idesc()
     d |= (uint32_t)(256 >> 4) << 24;  // M
     return d;
 }
+#define UMMA_TF32_PAIR(QUAL, tmem_d, da, db, idesc, accumulate) asm volatile( \
+    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" \
+    "tcgen05.mma.cta_group::2.kind::tf32" QUAL " [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" \
+    :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory")
 __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db,
                                                uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+    UMMA_TF32_PAIR("", tmem_d, da, db, idesc, accumulate);
 }
 // arrive (when all prior MMAs of this thread have completed) on `bar` in BOTH CTAs
 __device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
@@ -244,7 +246,12 @@ tica_umma_kernel(const UmmaParams P)
     const long long t_begin = (long long)P.n_tiles * pair / P.n_pairs;
     const long long t_end = (long long)P.n_tiles * (pair + 1) / P.n_pairs;
     const int my_tiles = (int)(t_end - t_begin);
-    const int n_slabs = (my_tiles + P.slab_tiles - 1) / P.slab_tiles;
+    // Slab boundaries are staggered across pairs (pair p's first slab is shorter) so the
+    // float64 flushes of the 74 pairs do not hit L2/HBM in the same microsecond.
+    const int slab_off = (int)(((long long)pair * P.slab_tiles) / P.n_pairs);   // in [0, slab_tiles)
+    const int first_len = P.slab_tiles - slab_off;                              // tiles in slab 0
+    const int n_slabs = (my_tiles <= first_len) ? 1
+                        : 1 + (my_tiles - first_len + P.slab_tiles - 1) / P.slab_tiles;
 
     if (tid == 0) {
         for (int s = 0; s < UM_STAGES; ++s) {
@@ -309,8 +316,8 @@ tica_umma_kernel(const UmmaParams P)
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int t = 0; t < my_tiles; ++t) {
-                const bool slab_first = (t % P.slab_tiles) == 0;
-                const bool slab_last = ((t + 1) % P.slab_tiles) == 0 || t + 1 == my_tiles;
+                const bool slab_first = t == 0 || ((t + slab_off) % P.slab_tiles) == 0;
+                const bool slab_last = ((t + slab_off + 1) % P.slab_tiles) == 0 || t + 1 == my_tiles;
                 const uint32_t a_hi = ring_addr + stage * UM_STAGE_BYTES;
                 const uint32_t a_lo = a_hi + UM_TILE_BYTES;
                 const uint32_t b_hi = a_hi + 2 * UM_TILE_BYTES;
@@ -330,15 +337,26 @@ tica_umma_kernel(const UmmaParams P)
                     const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
                     const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
                     const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
-                    umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
-                    if (P.passes == 3) {
-                        umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
-                        umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
-                    }
-                    umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
-                    if (P.passes == 3) {
-                        umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
-                        umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                    if (P.passes == 3 && P.collector) {
+                        // the four MMAs that share A = hi, then the two that share A = lo, keep A
+                        // in the collector buffer: 2 instead of 6 A-tile fetches from shared memory
+                        UMMA_TF32_PAIR(".collector::a::fill", tmem, dAh, dBh, idesc, acc);           // C_tau
+                        UMMA_TF32_PAIR(".collector::a::use", tmem, dAh, dBl, idesc, 1u);
+                        UMMA_TF32_PAIR(".collector::a::use", tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                        UMMA_TF32_PAIR(".collector::a::lastuse", tmem + 256, dAh, dAl, idesc, 1u);
+                        UMMA_TF32_PAIR(".collector::a::fill", tmem, dAl, dBh, idesc, 1u);
+                        UMMA_TF32_PAIR(".collector::a::lastuse", tmem + 256, dAl, dAh, idesc, 1u);
+                    } else {
+                        umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
+                        if (P.passes == 3) {
+                            umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
+                            umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                        }
+                        umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                        if (P.passes == 3) {
+                            umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
+                            umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit_pair(&ctl->empty[stage]);      // stage may be rewritten (both CTAs)
@@ -387,10 +405,10 @@ tica_umma_kernel(const UmmaParams P)
             ++next_flush;
         };
         for (int t = 0; t < my_tiles; ++t) {
-            // slab j ends with tile min((j+1)*slab_tiles, my_tiles) - 1; by the time this warp is
+            // slab j ends with tile min(first_len + j*slab_tiles, my_tiles) - 1; by the time this warp is
             // about to convert tile t >= end + 2 both operand stages are full, so it may as well drain
             while (next_flush < n_slabs) {
-                int end = (next_flush + 1) * P.slab_tiles;
+                int end = first_len + next_flush * P.slab_tiles;     // one past the slab's last tile
                 if (end > my_tiles) end = my_tiles;
                 if (end - 1 + 2 > t) break;
                 help_flush();
@@ -790,6 +808,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", UM_SLAB_TILES_DEFAULT);
     if (P.slab_tiles < 1) P.slab_tiles = 1;
     P.passes = passes;
+    P.collector = env_int("MSMB200_UMMA_COLLECTOR", 0);
     P.shift = d_shift;
     P.partials = reinterpret_cast<double *>(wsb + w_part);
     P.sums = reinterpret_cast<double *>(wsb + w_sums);
