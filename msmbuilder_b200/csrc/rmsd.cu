@@ -46,6 +46,51 @@ __device__ __forceinline__ Mat3 inner_products(const float *__restrict__ x,
     return r;
 }
 
+// G-lane cooperative M = sum_a x_a (x) y_a for the one-centre pass: y lives in shared memory
+// already widened to double; when n_atoms % 4 == 0 each lane streams whole 4-atom groups
+// (three 16-byte loads = 48 contiguous bytes), otherwise one atom at a time.
+template <int G>
+__device__ __forceinline__ Mat3 inner_products_group(const float *__restrict__ x,
+                                                     const double *__restrict__ sy, int n_atoms,
+                                                     int lane_in_group)
+{
+    Mat3 r;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) r.m[q] = 0.0;
+    if ((n_atoms & 3) == 0) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(x);
+        const int n_quads = n_atoms >> 2;
+        for (int qd = lane_in_group; qd < n_quads; qd += G) {
+            const float4 v0 = ldg_stream(x4 + 3 * qd), v1 = ldg_stream(x4 + 3 * qd + 1),
+                         v2 = ldg_stream(x4 + 3 * qd + 2);
+            const double xs[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+            const double *y = sy + 12 * qd;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double x0 = xs[3 * a], x1 = xs[3 * a + 1], x2 = xs[3 * a + 2];
+                const double y0 = y[3 * a], y1 = y[3 * a + 1], y2 = y[3 * a + 2];
+                r.m[0] = fma(x0, y0, r.m[0]); r.m[1] = fma(x0, y1, r.m[1]); r.m[2] = fma(x0, y2, r.m[2]);
+                r.m[3] = fma(x1, y0, r.m[3]); r.m[4] = fma(x1, y1, r.m[4]); r.m[5] = fma(x1, y2, r.m[5]);
+                r.m[6] = fma(x2, y0, r.m[6]); r.m[7] = fma(x2, y1, r.m[7]); r.m[8] = fma(x2, y2, r.m[8]);
+            }
+        }
+    } else {
+        for (int a = lane_in_group; a < n_atoms; a += G) {
+            const double x0 = x[3 * a], x1 = x[3 * a + 1], x2 = x[3 * a + 2];
+            const double y0 = sy[3 * a], y1 = sy[3 * a + 1], y2 = sy[3 * a + 2];
+            r.m[0] = fma(x0, y0, r.m[0]); r.m[1] = fma(x0, y1, r.m[1]); r.m[2] = fma(x0, y2, r.m[2]);
+            r.m[3] = fma(x1, y0, r.m[3]); r.m[4] = fma(x1, y1, r.m[4]); r.m[5] = fma(x1, y2, r.m[5]);
+            r.m[6] = fma(x2, y0, r.m[6]); r.m[7] = fma(x2, y1, r.m[7]); r.m[8] = fma(x2, y2, r.m[8]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+        for (int off = G >> 1; off > 0; off >>= 1)
+            r.m[q] += __shfl_xor_sync(0xffffffffu, r.m[q], off);
+    return r;
+}
+
 __device__ __forceinline__ double det3(double a, double b, double c, double d, double e,
                                        double f, double g, double h, double i)
 {
@@ -133,22 +178,31 @@ rmsd_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ traces
                  BlockCandR *__restrict__ block_cands, unsigned *__restrict__ counter,
                  msmb200_candidate *__restrict__ out)
 {
-    extern __shared__ __align__(16) float s_c[];   // n_atoms*3 coords + 1 trace
-    const int row_elems = n_atoms * 3 + 1;
-    for (int j = threadIdx.x; j < row_elems; j += blockDim.x) s_c[j] = center[j];
+    constexpr int G = 8;                            // lanes per frame: 4 frames per warp in flight
+    extern __shared__ __align__(16) double s_cd[];  // n_atoms*3 centre coordinates, widened
+    const int n3 = n_atoms * 3;
+    for (int j = threadIdx.x; j < n3; j += blockDim.x) s_cd[j] = (double)center[j];
     __syncthreads();
-    const double Gc = (double)s_c[n_atoms * 3];
+    const double Gc = (double)center[n3];
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane_in_group = lane & (G - 1), group_in_warp = lane / G;
+    const long long warp_group0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / G);
+    const long long n_groups = ((long long)gridDim.x * blockDim.x) / G;
 
     ArgMax best{-INFINITY, 0x7fffffffffffffffLL};
-    for (long long f = warp; f < n; f += n_warps) {
-        const float *x = xyz + f * (long long)n_atoms * 3;
-        Mat3 M = inner_products(x, s_c, n_atoms, lane);
-        if (lane == 0) {
-            const double dv = qcp_rmsd(M, (double)traces[f], Gc, n_atoms);
-            double cur = dist[f];
+    for (long long f0 = warp_group0; f0 < n; f0 += n_groups) {
+        const long long f_raw = f0 + group_in_warp;
+        const bool valid = f_raw < n;
+        const long long f = valid ? f_raw : n - 1;
+        const float *x = xyz + f * (long long)n3;
+        double cur = INFINITY, Gx = 0.0;
+        if (valid && lane_in_group == 0) {           // prefetch before the arithmetic
+            cur = __ldcg(dist + f);
+            Gx = (double)traces[f];
+        }
+        Mat3 M = inner_products_group<G>(x, s_cd, n_atoms, lane_in_group);
+        if (valid && lane_in_group == 0) {
+            const double dv = qcp_rmsd(M, Gx, Gc, n_atoms);
             if (dv < cur) {
                 cur = dv;
                 dist[f] = dv;
@@ -321,12 +375,14 @@ extern "C" int msmb200_rmsd_kcenters_pass(const float *xyz, const float *traces,
 {
     MSMB_REQUIRE(xyz && traces && center && distances && labels && out && workspace && n >= 0 &&
                  n_atoms > 0, "rmsd_kcenters_pass: bad args");
-    const int grid = warp_grid(n);
+    int grid = warp_grid((n + 3) / 4);          // 4 frames per warp iteration
     MSMB_REQUIRE(workspace_bytes >= 16 + sizeof(BlockCandR) * (size_t)grid,
                  "rmsd_kcenters_pass: workspace too small");
     unsigned *counter = reinterpret_cast<unsigned *>(workspace);
     BlockCandR *cands = reinterpret_cast<BlockCandR *>(reinterpret_cast<unsigned char *>(workspace) + 16);
-    size_t smem = (((size_t)n_atoms * 3 + 1) * sizeof(float) + 15) & ~(size_t)15;
+    size_t smem = (((size_t)n_atoms * 3) * sizeof(double) + 15) & ~(size_t)15;
+    if (smem > 48 * 1024)
+        MSMB_CUDA(cudaFuncSetAttribute(rmsd_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rmsd_pass_kernel<<<grid, kRThreads, smem, (cudaStream_t)stream>>>(
         xyz, traces, n, n_atoms, center, center_label, distances, labels, row_offset, cands,
         counter, out);

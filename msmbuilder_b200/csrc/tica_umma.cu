@@ -195,6 +195,22 @@ struct UmmaSmem {
 };
 
 
+// Pull this warp's share of the pair's float64 partials into L2 ahead of the drain: the
+// read-modify-write below is otherwise a chain of dependent DRAM round trips (the partials are
+// evicted between flushes by the frame stream), measured at ~20k cycles per flush.
+__device__ __forceinline__ void flush_prefetch(const UmmaParams &P, int pair, uint32_t cta_rank,
+                                               int quarter, int part, int nparts, int lane)
+{
+    const int row = UM_F * cta_rank + quarter * 32;          // 32 rows = 256 B per column
+    const double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
+    for (int c0 = 32 * part; c0 < 512; c0 += 32 * nparts) {
+        // lane -> column c0 + lane: one 256-byte row segment = two 128-byte lines
+        const double *line = pc + (size_t)(c0 + lane) * UM_D;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(line + 16));
+    }
+}
+
 // Drain this warp's share of the TMEM accumulators into the pair's float64 partials.
 // quarter = warp % 4 (the TMEM lanes a warp may touch); the 16 column chunks of 32 are
 // dealt round-robin to the `nparts` warps that share a quarter.
@@ -395,6 +411,7 @@ tica_umma_kernel(const UmmaParams P)
         int next_flush = 0;
         uint32_t acc_phase = 0;
         auto help_flush = [&]() {
+            flush_prefetch(P, pair, cta_rank, cw & 3, 1 + (cw >> 2), 3, lane);
             mbar_wait(&ctl->acc_full, acc_phase);
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
@@ -478,6 +495,7 @@ tica_umma_kernel(const UmmaParams P)
         const bool dbg_on = P.dbg != nullptr && pair == 0 && cta_rank == 0 && ew == 0 && lane == 0;
         long long d_flush = 0;
         for (int slab = 0; slab < n_slabs; ++slab) {
+            flush_prefetch(P, pair, cta_rank, ew, 0, 3, lane);
             mbar_wait(&ctl->acc_full, acc_phase);
             const long long f0 = dbg_on ? clock64() : 0;
             acc_phase ^= 1;
