@@ -81,7 +81,9 @@ enum {
     MSMB200_TICA_AUTO = 0,      /* tcgen05 3xTF32 when the shape allows, else SIMT f64 */
     MSMB200_TICA_SIMT_F64 = 1,  /* CUDA-core float64, any D, any lag, f32 or f64 input  */
     MSMB200_TICA_UMMA_3XTF32 = 2, /* tcgen05.mma kind::tf32, error-compensated 3-term split */
-    MSMB200_TICA_UMMA_TF32 = 3  /* tcgen05.mma kind::tf32, single pass (fast, ~1e-3)     */
+    MSMB200_TICA_UMMA_TF32 = 3, /* tcgen05.mma kind::tf32, single pass                   */
+    MSMB200_TICA_UMMA_3XBF16 = 4, /* kind::f16 bf16 h/m split, 3 products (~2^-16, K = 16) */
+    MSMB200_TICA_UMMA_6XBF16 = 5  /* bf16 h/m/l split, 6 products (~2^-24)                  */
 };
 
 /* Bytes of DEVICE scratch the call may need for (n_features, engine). */

@@ -112,14 +112,16 @@ extern "C" int msmb200_tica_accumulate(const void *const *seq_ptrs, const int64_
         engine = umma_ok ? MSMB200_TICA_UMMA_3XTF32 : MSMB200_TICA_SIMT_F64;
     if (engine == MSMB200_TICA_SIMT_F64)
         return tica_simt_accumulate(seq_ptrs, seq_rows, n_seq, D, ld, dtype, lag, acc, st);
-    if (engine == MSMB200_TICA_UMMA_3XTF32 || engine == MSMB200_TICA_UMMA_TF32) {
+    if (engine == MSMB200_TICA_UMMA_3XTF32 || engine == MSMB200_TICA_UMMA_TF32 ||
+        engine == MSMB200_TICA_UMMA_3XBF16 || engine == MSMB200_TICA_UMMA_6XBF16) {
         if (!umma_ok) {
             set_error("tcgen05 engine does not take D=%d ld=%lld dtype=%d lag=%d", D,
                       (long long)ld, dtype, lag);
             return MSMB200_E_UNSUPPORTED;
         }
-        return tica_umma_accumulate(seq_ptrs, seq_rows, n_seq, D, ld, lag,
-                                    engine == MSMB200_TICA_UMMA_3XTF32 ? 3 : 1, acc, workspace,
+        const int mode = engine == MSMB200_TICA_UMMA_3XTF32 ? 3 : engine == MSMB200_TICA_UMMA_TF32 ? 1
+                         : engine == MSMB200_TICA_UMMA_3XBF16 ? 13 : 16;
+        return tica_umma_accumulate(seq_ptrs, seq_rows, n_seq, D, ld, lag, mode, acc, workspace,
                                     workspace_bytes, st);
     }
     set_error("tica_accumulate: unknown engine %d", engine);

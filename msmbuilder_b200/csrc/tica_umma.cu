@@ -49,6 +49,7 @@ constexpr int UM_STAGES = 2;                    // raw ring and operand ring dep
 constexpr int UM_TILE_BYTES = UM_KT * UM_F * 4; // 16 KB
 constexpr int UM_RAW_BYTES = 2 * UM_TILE_BYTES;     // raw A, raw B (TMA destinations)
 constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo (UMMA operands)
+constexpr int UM_BF_TILE_BYTES = UM_KT * UM_F * 2;  // bf16 component tile, 8 KB (6 of them fit a stage)
 constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
 constexpr int UM_SBO = 128;                     // next 8-feature group
 constexpr int UM_THREADS = 512;
@@ -65,7 +66,7 @@ struct UmmaParams {
     int n_tiles;
     int n_pairs;                  // clusters launched
     int slab_tiles;
-    int passes;                   // 3 = hi/lo split, 1 = plain tf32
+    int passes;                   // tf32: 3 = hi/lo split, 1 = plain; bf16: 3 = h/m products, 6 = h/m/l
     int collector;                // reuse the A operand through the collector buffer
     const float *shift;           // [D]
     double *partials;             // [n_pairs][2][col][row]  (C_tau', C_00'), column-major so a
@@ -139,21 +140,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
     d |= (uint64_t)1 << 46;
     return d;
 }
-// tf32 x tf32 -> f32, K-major A and B, M = 256 (pair), N = 256
+// (tf32 x tf32 | bf16 x bf16) -> f32, K-major A and B, M = 256 (pair), N = 256
+template <bool BF16>
 __device__ __forceinline__ uint32_t umma_idesc()
 {
     uint32_t d = 0;
     d |= 1u << 4;                     // D format F32
-    d |= 2u << 7;                     // A format TF32
-    d |= 2u << 10;                    // B format TF32
+    d |= (BF16 ? 1u : 2u) << 7;       // A format: BF16 = 1, TF32 = 2
+    d |= (BF16 ? 1u : 2u) << 10;      // B format
     d |= (uint32_t)(256 >> 3) << 17;  // N
     d |= (uint32_t)(256 >> 4) << 24;  // M
     return d;
 }
-#define UMMA_TF32_PAIR(QUAL, tmem_d, da, db, idesc, accumulate) asm volatile( \
+#define UMMA_KIND_PAIR(KIND, QUAL, tmem_d, da, db, idesc, accumulate) asm volatile( \
     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" \
-    "tcgen05.mma.cta_group::2.kind::tf32" QUAL " [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" \
+    "tcgen05.mma.cta_group::2.kind::" KIND QUAL " [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" \
     :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory")
+#define UMMA_TF32_PAIR(QUAL, tmem_d, da, db, idesc, accumulate) \
+    UMMA_KIND_PAIR("tf32", QUAL, tmem_d, da, db, idesc, accumulate)
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db,
+                                               uint32_t idesc, uint32_t accumulate)
+{
+    UMMA_KIND_PAIR("f16", "", tmem_d, da, db, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db,
                                                uint32_t idesc, uint32_t accumulate)
 {
@@ -171,6 +180,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
 __device__ __forceinline__ float tf32_rn(float x)
 {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// same for bfloat16's 8-bit significand; the value stays in a float (low 16 bits zero)
+__device__ __forceinline__ float bf16_rn(float x)
+{
+    return __uint_as_float((__float_as_uint(x) + 0x8000u) & 0xFFFF0000u);
+}
+// two bf16-valued floats -> one 32-bit word (a in the low half = the earlier frame)
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    return (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xFFFF0000u);
 }
 
 #define UM_TMEM_LD32(v, taddr) asm volatile( \
@@ -242,6 +261,7 @@ __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, 
 }
 
 // ---------------------------------------------------------------------------------------
+template <bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 tica_umma_kernel(const UmmaParams P)
 {
@@ -324,7 +344,7 @@ tica_umma_kernel(const UmmaParams P)
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA, one lane) =============
         if (cta_rank == 0 && lane == 0 && my_tiles > 0) {
-            const uint32_t idesc = umma_idesc();
+            const uint32_t idesc = umma_idesc<BF16>();
             const uint32_t ring_addr = smem_u32(op_ring);
             const bool dbg_on = P.dbg != nullptr && pair == 0;
             long long d_wait_conv = 0, d_wait_acc = 0;
@@ -334,10 +354,6 @@ tica_umma_kernel(const UmmaParams P)
             for (int t = 0; t < my_tiles; ++t) {
                 const bool slab_first = t == 0 || ((t + slab_off) % P.slab_tiles) == 0;
                 const bool slab_last = ((t + slab_off + 1) % P.slab_tiles) == 0 || t + 1 == my_tiles;
-                const uint32_t a_hi = ring_addr + stage * UM_STAGE_BYTES;
-                const uint32_t a_lo = a_hi + UM_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * UM_TILE_BYTES;
-                const uint32_t b_lo = a_hi + 3 * UM_TILE_BYTES;
                 long long c0 = dbg_on ? clock64() : 0;
                 mbar_wait(&ctl->conv[stage], phase);
                 long long c1 = dbg_on ? clock64() : 0;
@@ -347,31 +363,66 @@ tica_umma_kernel(const UmmaParams P)
                 }
                 if (dbg_on) { long long c2 = clock64(); d_wait_conv += c1 - c0; d_wait_acc += c2 - c1; }
                 asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t stage_addr = ring_addr + stage * UM_STAGE_BYTES;
+                if constexpr (!BF16) {
+                    const uint32_t a_hi = stage_addr;
+                    const uint32_t a_lo = a_hi + UM_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * UM_TILE_BYTES;
+                    const uint32_t b_lo = a_hi + 3 * UM_TILE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < UM_KT / 8; ++ks) {
-                    const uint32_t off = ks * 2 * UM_LBO;
-                    const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
-                    const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
-                    const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
-                    if (P.passes == 3 && P.collector) {
-                        // the four MMAs that share A = hi, then the two that share A = lo, keep A
-                        // in the collector buffer: 2 instead of 6 A-tile fetches from shared memory
-                        UMMA_TF32_PAIR(".collector::a::fill", tmem, dAh, dBh, idesc, acc);           // C_tau
-                        UMMA_TF32_PAIR(".collector::a::use", tmem, dAh, dBl, idesc, 1u);
-                        UMMA_TF32_PAIR(".collector::a::use", tmem + 256, dAh, dAh, idesc, acc);      // C_00
-                        UMMA_TF32_PAIR(".collector::a::lastuse", tmem + 256, dAh, dAl, idesc, 1u);
-                        UMMA_TF32_PAIR(".collector::a::fill", tmem, dAl, dBh, idesc, 1u);
-                        UMMA_TF32_PAIR(".collector::a::lastuse", tmem + 256, dAl, dAh, idesc, 1u);
-                    } else {
-                        umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
-                        if (P.passes == 3) {
-                            umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
-                            umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                    for (int ks = 0; ks < UM_KT / 8; ++ks) {
+                        const uint32_t off = ks * 2 * UM_LBO;
+                        const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
+                        const uint64_t dAh = umma_desc(a_hi + off), dAl = umma_desc(a_lo + off);
+                        const uint64_t dBh = umma_desc(b_hi + off), dBl = umma_desc(b_lo + off);
+                        if (P.passes == 3 && P.collector) {
+                            // the four MMAs that share A = hi, then the two that share A = lo, keep A
+                            // in the collector buffer: 2 instead of 6 A-tile fetches from shared memory
+                            UMMA_TF32_PAIR(".collector::a::fill", tmem, dAh, dBh, idesc, acc);           // C_tau
+                            UMMA_TF32_PAIR(".collector::a::use", tmem, dAh, dBl, idesc, 1u);
+                            UMMA_TF32_PAIR(".collector::a::use", tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                            UMMA_TF32_PAIR(".collector::a::lastuse", tmem + 256, dAh, dAl, idesc, 1u);
+                            UMMA_TF32_PAIR(".collector::a::fill", tmem, dAl, dBh, idesc, 1u);
+                            UMMA_TF32_PAIR(".collector::a::lastuse", tmem + 256, dAl, dAh, idesc, 1u);
+                        } else {
+                            umma_tf32_pair(tmem, dAh, dBh, idesc, acc);            // C_tau
+                            if (P.passes == 3) {
+                                umma_tf32_pair(tmem, dAh, dBl, idesc, 1u);
+                                umma_tf32_pair(tmem, dAl, dBh, idesc, 1u);
+                            }
+                            umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
+                            if (P.passes == 3) {
+                                umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
+                                umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                            }
                         }
-                        umma_tf32_pair(tmem + 256, dAh, dAh, idesc, acc);      // C_00
-                        if (P.passes == 3) {
-                            umma_tf32_pair(tmem + 256, dAh, dAl, idesc, 1u);
-                            umma_tf32_pair(tmem + 256, dAl, dAh, idesc, 1u);
+                    }
+                } else {
+                    // bf16 components h, m, l of A (unlagged) and B (lagged), 8 KB each:
+                    // x ~ h + m (+ l);  3 products: hh' + hm' + mh' (~2^-16 relative, unbiased);
+                    // 6 products add mm' + hl' + lh' (~2^-24).  K = 16 frames per instruction.
+                    const uint32_t A0 = stage_addr, B0 = stage_addr + 3 * UM_BF_TILE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                        const uint32_t off = ks * 2 * UM_LBO;
+                        const uint32_t acc = (slab_first && ks == 0) ? 0u : 1u;
+                        const uint64_t dAh = umma_desc(A0 + off), dAm = umma_desc(A0 + UM_BF_TILE_BYTES + off),
+                                       dAl = umma_desc(A0 + 2 * UM_BF_TILE_BYTES + off);
+                        const uint64_t dBh = umma_desc(B0 + off), dBm = umma_desc(B0 + UM_BF_TILE_BYTES + off),
+                                       dBl = umma_desc(B0 + 2 * UM_BF_TILE_BYTES + off);
+                        umma_bf16_pair(tmem, dAh, dBh, idesc, acc);                // C_tau
+                        umma_bf16_pair(tmem, dAh, dBm, idesc, 1u);
+                        umma_bf16_pair(tmem, dAm, dBh, idesc, 1u);
+                        umma_bf16_pair(tmem + 256, dAh, dAh, idesc, acc);          // C_00
+                        umma_bf16_pair(tmem + 256, dAh, dAm, idesc, 1u);
+                        umma_bf16_pair(tmem + 256, dAm, dAh, idesc, 1u);
+                        if (P.passes == 6) {
+                            umma_bf16_pair(tmem, dAm, dBm, idesc, 1u);
+                            umma_bf16_pair(tmem, dAh, dBl, idesc, 1u);
+                            umma_bf16_pair(tmem, dAl, dBh, idesc, 1u);
+                            umma_bf16_pair(tmem + 256, dAm, dAm, idesc, 1u);
+                            umma_bf16_pair(tmem + 256, dAh, dAl, idesc, 1u);
+                            umma_bf16_pair(tmem + 256, dAl, dAh, idesc, 1u);
                         }
                     }
                 }
@@ -442,29 +493,70 @@ tica_umma_kernel(const UmmaParams P)
 #pragma unroll
             for (int op = 0; op < 2; ++op) {
                 const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
-                unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
-                unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
+                if constexpr (!BF16) {
+                    unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
+                    unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
 #pragma unroll
-                for (int k = 0; k < UM_RB / 2; ++k) {
-                    const int rb = 2 * k + rb_par;
-                    float a[4];
+                    for (int k = 0; k < UM_RB / 2; ++k) {
+                        const int rb = 2 * k + rb_par;
+                        float a[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = 4 * rb + i;          // frame inside the tile
-                        const float v = *reinterpret_cast<const float *>(
-                            raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                        a[i] = (r < valid) ? v - sh : 0.f;
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = 4 * rb + i;          // frame inside the tile
+                            const float v = *reinterpret_cast<const float *>(
+                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            a[i] = (r < valid) ? v - sh : 0.f;
+                        }
+                        const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
+                        if (op == 0) tsA += s4; else tsB += s4;
+                        float4 hv;
+                        hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
+                        *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
+                        if (split) {
+                            float4 l;
+                            l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
+                            l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
+                            *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
+                        }
                     }
-                    const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
-                    if (op == 0) tsA += s4; else tsB += s4;
-                    float4 hv;
-                    hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
-                    *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
-                    if (split) {
-                        float4 l;
-                        l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
-                        l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
-                        *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
+                } else {
+                    // 16-byte chunk = 8 consecutive frames of this thread's feature
+                    unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
+                    unsigned char *m_buf = h_buf + UM_BF_TILE_BYTES;
+                    unsigned char *l_buf = h_buf + 2 * UM_BF_TILE_BYTES;
+                    const bool six = P.passes == 6;
+#pragma unroll
+                    for (int k = 0; k < UM_KT / 16; ++k) {
+                        const int kb = 2 * k + rb_par;          // block of 8 frames
+                        float a[8], h[8], m[8];
+                        float s8 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 8 * kb + i;
+                            const float v = *reinterpret_cast<const float *>(
+                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            a[i] = (r < valid) ? v - sh : 0.f;
+                            s8 += a[i];
+                            h[i] = bf16_rn(a[i]);
+                            m[i] = bf16_rn(a[i] - h[i]);      // a - h is exact in fp32
+                        }
+                        if (op == 0) tsA += s8; else tsB += s8;
+                        uint4 hw, mw;
+                        hw.x = pack_bf16(h[0], h[1]); hw.y = pack_bf16(h[2], h[3]);
+                        hw.z = pack_bf16(h[4], h[5]); hw.w = pack_bf16(h[6], h[7]);
+                        mw.x = pack_bf16(m[0], m[1]); mw.y = pack_bf16(m[2], m[3]);
+                        mw.z = pack_bf16(m[4], m[5]); mw.w = pack_bf16(m[6], m[7]);
+                        *reinterpret_cast<uint4 *>(h_buf + kb * UM_LBO) = hw;
+                        *reinterpret_cast<uint4 *>(m_buf + kb * UM_LBO) = mw;
+                        if (six) {
+                            float l[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) l[i] = bf16_rn((a[i] - h[i]) - m[i]);
+                            uint4 lw;
+                            lw.x = pack_bf16(l[0], l[1]); lw.y = pack_bf16(l[2], l[3]);
+                            lw.z = pack_bf16(l[4], l[5]); lw.w = pack_bf16(l[6], l[7]);
+                            *reinterpret_cast<uint4 *>(l_buf + kb * UM_LBO) = lw;
+                        }
                     }
                 }
             }
@@ -823,9 +915,12 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.n_seq = n_seq;
     P.n_tiles = (int)tiles;
     P.n_pairs = n_pairs;
-    P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", UM_SLAB_TILES_DEFAULT);
+    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16 (see lib.cu)
+    // bf16 MMAs cover 16 frames per accumulate step (tf32: 8), so twice the frames per slab
+    // carry the same truncation bias
+    P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", bf16 ? 2 * UM_SLAB_TILES_DEFAULT : UM_SLAB_TILES_DEFAULT);
     if (P.slab_tiles < 1) P.slab_tiles = 1;
-    P.passes = passes;
+    P.passes = bf16 ? passes - 10 : passes;
     P.collector = env_int("MSMB200_UMMA_COLLECTOR", 0);
     P.shift = d_shift;
     P.partials = reinterpret_cast<double *>(wsb + w_part);
@@ -842,11 +937,14 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + sizeof(UmmaSmem) + 1024;
         static bool attr_set = false;
         if (!attr_set) {
-            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel,
+            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        tica_umma_kernel<<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+        if (bf16) tica_umma_kernel<true><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+        else tica_umma_kernel<false><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
         MSMB_LAUNCH_CHECK();
     }
     {

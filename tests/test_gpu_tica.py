@@ -192,3 +192,14 @@ def test_umma_single_pass_tf32_is_looser():
     seqs = ar1_numpy(3, 5000, 256, seed=22)
     a, b = _umma_vs_simt(seqs, 10, engine="umma_tf32")
     _assert_moments_close(b, a, 5e-3)
+
+
+@pytest.mark.parametrize("engine,mom_tol", [("umma_3xbf16", 2e-5), ("umma_6xbf16", 5e-6)])
+def test_umma_bf16_engines(engine, mom_tol):
+    # bf16 split: 3 products ~2^-16 per element (unbiased, averages down with n), 6 products ~2^-24
+    lens = [4001, 130, 64, 11, 15, 777, 32, 2048]
+    seqs = [s[:n] for s, n in zip(ar1_numpy(len(lens), 4100, 256, seed=23), lens)]
+    a, b = _umma_vs_simt(seqs, 10, engine=engine)
+    assert a.n_observations_ == b.n_observations_ and a.n_sequences_ == b.n_sequences_
+    _assert_moments_close(b, a, mom_tol)
+    np.testing.assert_allclose(b.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)

@@ -27,8 +27,10 @@ def main():
     torch.cuda.synchronize()
     print("simt_f64: %.1f ms for %d frames; eig %s" % (1e3 * (time.time() - t0), n_seq * L, ref.eigenvalues_[:4]))
     pr = packed(ref)
-    for engine in ("umma_3xtf32", "umma_tf32"):
-        for slab in (8, 16, 32, 64, 100000):
+    engines = os.environ.get("ENGINES", "umma_3xtf32,umma_tf32,umma_3xbf16,umma_6xbf16").split(",")
+    slabs = [int(v) for v in os.environ.get("SLABS", "16,32,64,128,100000").split(",")]
+    for engine in engines:
+        for slab in slabs:
             os.environ["MSMB200_UMMA_SLAB_TILES"] = str(slab)
             m = tICA(n_components=8, lag_time=10, engine=engine)
             m.fit(seqs)
