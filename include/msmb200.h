@@ -78,7 +78,7 @@ size_t msmb200_tica_acc_len(int n_features);
 
 /* Precision / engine selector for K1. */
 enum {
-    MSMB200_TICA_AUTO = 0,      /* tcgen05 3xTF32 when the shape allows, else SIMT f64 */
+    MSMB200_TICA_AUTO = 0,      /* tcgen05 6xBF16 when the shape allows, else SIMT f64 */
     MSMB200_TICA_SIMT_F64 = 1,  /* CUDA-core float64, any D, any lag, f32 or f64 input  */
     MSMB200_TICA_UMMA_3XTF32 = 2, /* tcgen05.mma kind::tf32, error-compensated 3-term split */
     MSMB200_TICA_UMMA_TF32 = 3, /* tcgen05.mma kind::tf32, single pass                   */

@@ -60,8 +60,9 @@ class tICA(BaseEstimator, TransformerMixin):
         Scale the projection by regularised timescales (commute map).
     engine : {'auto', 'simt_f64', 'umma_3xtf32', 'umma_tf32', 'umma_3xbf16', 'umma_6xbf16'}, default='auto'
         Which device kernel accumulates the covariance matrices.  'auto' uses the
-        tcgen05 tensor-core kernel with the error-compensated 3xTF32 split when
-        the shape allows it and the float64 CUDA-core kernel otherwise.
+        tcgen05 tensor-core kernel with the error-compensated 6-product bf16 split
+        (~2^-24 per product) when the shape allows it and the float64 CUDA-core
+        kernel otherwise; 'umma_3xbf16' is the fastest (~2^-16 per product, unbiased).
 
     Attributes
     ----------
