@@ -108,8 +108,8 @@ extern "C" int msmb200_tica_accumulate(const void *const *seq_ptrs, const int64_
                      "tica_accumulate: sequence %d invalid", s);
     cudaStream_t st = (cudaStream_t)stream;
     const bool umma_ok = tica_umma_supported(D, ld, dtype, lag);
-    if (engine == MSMB200_TICA_AUTO)
-        engine = umma_ok ? MSMB200_TICA_UMMA_6XBF16 : MSMB200_TICA_SIMT_F64;
+    if (engine == MSMB200_TICA_AUTO)   // the 256-wide tensor-core tiles beat the float64 kernel from D = 64 up
+        engine = (umma_ok && D >= 64) ? MSMB200_TICA_UMMA_6XBF16 : MSMB200_TICA_SIMT_F64;
     if (engine == MSMB200_TICA_SIMT_F64)
         return tica_simt_accumulate(seq_ptrs, seq_rows, n_seq, D, ld, dtype, lag, acc, st);
     if (engine == MSMB200_TICA_UMMA_3XTF32 || engine == MSMB200_TICA_UMMA_TF32 ||

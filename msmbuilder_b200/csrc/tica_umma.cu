@@ -615,9 +615,11 @@ __global__ void tica_shift_kernel(const float *__restrict__ X, long long n, long
                                   float *__restrict__ shift)
 {
     const long long rows = n < 512 ? n : 512;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) {
+    // shift[] is padded to UM_D entries; features >= D do not exist (TMA zero-fills them)
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < UM_D; c += gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (long long r = 0; r < rows; ++r) s += (double)X[r * ld + c];
+        if (c < D)
+            for (long long r = 0; r < rows; ++r) s += (double)X[r * ld + c];
         shift[c] = (float)(s / (double)rows);
     }
 }
@@ -636,11 +638,11 @@ struct EdgeSeq {
 // grid (n_blocks, D/16): block (b, it) accumulates rows 16*it..16*it+15 of the outputs
 // over sequences b, b + n_blocks, ...
 __global__ void __launch_bounds__(256)
-tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld, int lag,
+tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld, int lag, int Dr,
                        const float *__restrict__ shift, double *__restrict__ E,
                        double *__restrict__ es)
 {
-    constexpr int D = UM_D;
+    constexpr int D = UM_D;       // padded width of every scratch array; Dr <= D real features
     __shared__ double sx[D], sy[D];
     const int tid = threadIdx.x;
     const int i0 = blockIdx.y * 16;
@@ -666,8 +668,8 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
             else if (e < n_rem + lag) { kind = 2; t = e - n_rem; }
             else { kind = 3; t = n - lag + (e - n_rem - lag); }
             __syncthreads();
-            sx[tid] = (double)(X[t * ld + tid] - shift[tid]);
-            if (kind == 0) sy[tid] = (double)(X[(t + lag) * ld + tid] - shift[tid]);
+            sx[tid] = tid < Dr ? (double)(X[t * ld + tid] - shift[tid]) : 0.0;
+            if (kind == 0) sy[tid] = tid < Dr ? (double)(X[(t + lag) * ld + tid] - shift[tid]) : 0.0;
             __syncthreads();
             const double xj = sx[tid];
             if (kind == 0) {
@@ -694,8 +696,8 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int u = 0; u < 16; ++u)
-            atomicAdd(&E[(size_t)m * D * D + (size_t)(i0 + u) * D + tid], acc[m][u]);
-    if (blockIdx.y == 0) {
+            if (tid < Dr) atomicAdd(&E[(size_t)m * D * D + (size_t)(i0 + u) * D + tid], acc[m][u]);
+    if (blockIdx.y == 0 && tid < Dr) {
         atomicAdd(&es[tid], s0);
         atomicAdd(&es[D + tid], st);
         atomicAdd(&es[2 * D + tid], stail);
@@ -708,39 +710,41 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
                           const double *__restrict__ sums, const double *__restrict__ E,
                           const double *__restrict__ es, const float *__restrict__ shift,
                           double n_pairs_total /* sum_s (n_s - lag) */, double n_obs, double n_seq,
-                          double *__restrict__ acc)
+                          int Dr, double *__restrict__ acc)
 {
-    constexpr int D = UM_D;
-    const size_t DD = (size_t)D * D;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // element of a D x D matrix
-    if (idx >= (int)DD) return;
-    const int i = idx / D, j = idx % D;
+    constexpr int D = UM_D;                              // padded scratch width
+    const size_t DD = (size_t)D * D;                     // scratch matrix size
+    const size_t RR = (size_t)Dr * Dr;                   // output matrix size
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // element of a Dr x Dr matrix
+    if (idx >= (int)RR) return;
+    const int i = idx / Dr, j = idx % Dr;
     double ctau = 0.0, c00 = 0.0;
-    const size_t tidx = (size_t)j * D + i;               // partials are column-major
+    const size_t tidx = (size_t)j * D + i;               // partials are column-major, padded
+    const size_t pidx = (size_t)i * D + j;               // edge terms are row-major, padded
     for (int p = 0; p < n_pairs; ++p) {
         ctau += partials[(size_t)p * 2 * DD + tidx];
         c00 += partials[(size_t)p * 2 * DD + DD + tidx];
     }
-    ctau += E[idx];
-    c00 += E[DD + idx];
-    const double ctt = c00 - E[2 * DD + idx] + E[3 * DD + idx];
+    ctau += E[pidx];
+    c00 += E[DD + pidx];
+    const double ctt = c00 - E[2 * DD + pidx] + E[3 * DD + pidx];
     const double si = (double)shift[i], sj = (double)shift[j];
     const double S0i = sums[i] + es[i], S0j = sums[j] + es[j];
     const double Sti = sums[D + i] + es[D + i], Stj = sums[D + j] + es[D + j];
     const double Np = n_pairs_total;
     acc[idx] += ctau + S0i * sj + si * Stj + Np * si * sj;
-    acc[DD + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
-    acc[2 * DD + idx] += ctt + Sti * sj + si * Stj + Np * si * sj;
+    acc[RR + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
+    acc[2 * RR + idx] += ctt + Sti * sj + si * Stj + Np * si * sj;
     if (i == 0) {
         // vectors and counters (one thread per column j)
         const double S0 = S0j, St = Stj;
         const double Sall = S0 + es[2 * D + j];       // all rows = pair rows + last `lag` rows
-        acc[3 * DD + j] += S0 + Np * sj;
-        acc[3 * DD + D + j] += St + Np * sj;
-        acc[3 * DD + 2 * D + j] += Sall + n_obs * sj;
+        acc[3 * RR + j] += S0 + Np * sj;
+        acc[3 * RR + Dr + j] += St + Np * sj;
+        acc[3 * RR + 2 * Dr + j] += Sall + n_obs * sj;
         if (j == 0) {
-            acc[3 * DD + 3 * D] += n_obs;
-            acc[3 * DD + 3 * D + 1] += n_seq;
+            acc[3 * RR + 3 * Dr] += n_obs;
+            acc[3 * RR + 3 * Dr + 1] += n_seq;
         }
     }
 }
@@ -766,7 +770,10 @@ static EncodeTiledFn encode_fn()
 
 bool tica_umma_supported(int D, int64_t ld, int dtype, int lag)
 {
-    return D == UM_D && dtype == MSMB200_F32 && (ld % 4) == 0 && lag >= 1;   // 16-byte row pitch for TMA
+    // any D = 32k <= 256: TMA zero-fills the feature blocks a sequence does not have, so narrower
+    // inputs ride the same 256-wide tiles (at the 256-wide cost: worthwhile from D = 64 up,
+    // lib.cu picks the float64 CUDA-core engine below that)
+    return D >= 32 && D <= UM_D && (D % 32) == 0 && dtype == MSMB200_F32 && (ld % 4) == 0 && lag >= 1;
 }
 
 static constexpr int UM_MAX_PAIRS = 96;
@@ -779,8 +786,8 @@ static size_t ws_fixed_bytes(int D)
 }
 size_t tica_umma_workspace_bytes(int D)
 {
-    if (D != UM_D) return 0;
-    return ws_fixed_bytes(D) + sizeof(double) * 2 * (size_t)D * D * UM_MAX_PAIRS;
+    if (D > UM_D || (D % 32) != 0) return 0;
+    return ws_fixed_bytes(UM_D) + sizeof(double) * 2 * (size_t)UM_D * UM_D * UM_MAX_PAIRS;
 }
 
 static int env_int(const char *name, int dflt)
@@ -856,8 +863,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     n_pairs = env_int("MSMB200_UMMA_PAIRS", n_pairs);
     if (n_pairs > UM_MAX_PAIRS) n_pairs = UM_MAX_PAIRS;
     if (tiles < n_pairs) n_pairs = (int)(tiles > 0 ? tiles : 1);
-    const size_t DD = (size_t)D * D;
-    const size_t need = ws_fixed_bytes(D) + sizeof(double) * 2 * DD * n_pairs;
+    const size_t DD = (size_t)UM_D * UM_D;          // scratch is always 256 wide
+    const size_t need = ws_fixed_bytes(UM_D) + sizeof(double) * 2 * DD * n_pairs;
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
         set_error("tica_accumulate: workspace too small or misaligned (%zu < %zu); size it with "
                   "msmb200_tica_workspace_bytes", workspace_bytes, need);
@@ -887,10 +894,10 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     // big zero-initialised part: caller's workspace  [shift | sums | E | es | partials]
     unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
     size_t woff = 0;
-    const size_t w_shift = woff; woff = align_up(woff + sizeof(float) * D, 256);
-    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * 2 * D, 256);
+    const size_t w_shift = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
+    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * 2 * UM_D, 256);
     const size_t w_E = woff; woff = align_up(woff + sizeof(double) * 4 * DD, 256);
-    const size_t w_es = woff; woff = align_up(woff + sizeof(double) * 3 * D, 256);
+    const size_t w_es = woff; woff = align_up(woff + sizeof(double) * 3 * UM_D, 256);
     const size_t w_part = woff; woff += sizeof(double) * 2 * DD * n_pairs;
     MSMB_CUDA(cudaMemsetAsync(wsb + w_sums, 0, woff - w_sums, st));
 
@@ -950,14 +957,14 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     {
         dim3 grid(n_seq < 64 ? n_seq : 64, D / 16);
         tica_umma_edges_kernel<<<grid, 256, 0, st>>>(
-            reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq, ld, lag, d_shift,
+            reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq, ld, lag, D, d_shift,
             reinterpret_cast<double *>(wsb + w_E), reinterpret_cast<double *>(wsb + w_es));
         MSMB_LAUNCH_CHECK();
     }
-    tica_umma_finalize_kernel<<<(unsigned)((DD + 255) / 256), 256, 0, st>>>(
+    tica_umma_finalize_kernel<<<(unsigned)(((size_t)D * D + 255) / 256), 256, 0, st>>>(
         P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(wsb + w_E),
         reinterpret_cast<const double *>(wsb + w_es), d_shift, n_pairs_total, n_obs,
-        (double)n_seq, acc);
+        (double)n_seq, D, acc);
     MSMB_LAUNCH_CHECK();
     if (d_dbg) {
         long long h[16];

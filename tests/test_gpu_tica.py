@@ -203,3 +203,21 @@ def test_umma_bf16_engines(engine, mom_tol):
     assert a.n_observations_ == b.n_observations_ and a.n_sequences_ == b.n_sequences_
     _assert_moments_close(b, a, mom_tol)
     np.testing.assert_allclose(b.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)
+
+
+@pytest.mark.parametrize("D", [64, 96, 128, 224])
+def test_umma_narrow_feature_counts(D):
+    # D = 32k < 256 rides the 256-wide tensor-core tiles (TMA zero-fills the missing feature blocks)
+    from msmbuilder_b200.decomposition import tICA
+    lens = [3001, 257, 64, 12, 900]
+    seqs = [s[:n] for s, n in zip(ar1_numpy(len(lens), 3100, D, seed=30 + D), lens)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = tICA(n_components=4, lag_time=10, engine="simt_f64").fit(seqs)
+        b = tICA(n_components=4, lag_time=10, engine="auto").fit(seqs)
+        c = tICA(n_components=4, lag_time=10, engine="umma_3xtf32").fit(seqs)
+    for m in (b, c):
+        assert m.n_observations_ == a.n_observations_ and m.n_sequences_ == a.n_sequences_
+        _assert_moments_close(m, a, 5e-6)
+        np.testing.assert_allclose(m.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)
+        np.testing.assert_allclose(m.means_, a.means_, rtol=0, atol=1e-6)
