@@ -209,6 +209,37 @@ int msmb200_rmsd_pdist(const float *xyz, const float *traces, int64_t n, int n_a
                        const int64_t *rows, int64_t n_rows, double *out, void *stream);
 
 /* ======================================================================== *
+ *  Scans that follow the distance kernels (scan_kernels.cu)                *
+ * ======================================================================== */
+/* RegularSpatial (cluster/regularspatial.py:70-77): smallest index i >= start with
+ * values[i] > threshold written to *out_index (device), -1 if none.  `values` is the
+ * running minimum msmb200_kcenters_pass keeps, so "all distances to the centres so far
+ * exceed d_min" is one comparison per frame. */
+int msmb200_first_above(const double *values, int64_t n, int64_t start, double threshold,
+                        int64_t *out_index, void *stream);
+
+/* msm/core.py:487-602 `_transition_counts` on device-resident integer labels.
+ * label_bytes: 4 (int32, what the assignment kernels write) or 8 (int64; INT64_MIN marks
+ * a missing label = the reference's NaN / None, core.py:576-580).
+ *  label_range     -> out_min_max[2] (device): min and max label (INT64_MAX, INT64_MIN if none)
+ *  label_presence  -> flags[span] (device, uint8): flags[l - lo] = 1 for every label present;
+ *                     its non-zero entries in order are np.unique (core.py:544)
+ *  transition_counts: counts[from * n_states + to] += 1 for every t with t + lag inside the same
+ *                     sequence; states are remap[label - remap_lo] (negative = skip) or the
+ *                     label itself when remap == NULL.  (sliding_window=False is the same call
+ *                     on strided sequences at lag 1, exactly core.py:540-542.)  seq_offsets:
+ *                     n_seq + 1 device int64 row offsets.  counts (device int64, n_states^2)
+ *                     is accumulated into. */
+int msmb200_label_range(const void *labels, int64_t n, int label_bytes, int64_t *out_min_max,
+                        void *stream);
+int msmb200_label_presence(const void *labels, int64_t n, int label_bytes, int64_t lo,
+                           int64_t span, uint8_t *flags, void *stream);
+int msmb200_transition_counts(const void *labels, int label_bytes, const int64_t *seq_offsets,
+                              int64_t n_seq, int64_t n_total, int64_t lag,
+                              const int32_t *remap, int64_t remap_lo, int64_t remap_len,
+                              int32_t n_states, int64_t *counts, void *stream);
+
+/* ======================================================================== *
  *  Host k-medoids on a condensed distance matrix (npass == 0 branch)       *
  *  replaces _kmedoids.kmedoids / contigify_ids                             *
  *           (cluster/_kmedoids.pyx:23-117 -> cluster/src/kmedoids.cc)      *
@@ -218,6 +249,13 @@ int msmb200_rmsd_pdist(const float *xyz, const float *traces, int64_t n, int n_a
 int msmb200_kmedoids(int64_t n_clusters, int64_t n_elements, const double *distmatrix,
                      int64_t *clusterid /* in: labels, out: medoid element ids */,
                      double *error, int64_t *ifound);
+/* n_pass >= 2 random restarts (kmedoids.cc:160-250 as called by cluster/kmedoids.py:92-94).
+ * starts: (n_pass, n_elements) initial labels in [0, n_clusters), drawn by the caller with
+ * the RandomState calls of kmedoids.cc:314-383; clusterid in: the solution to beat
+ * (zeros from _kmedoids.pyx:97), out: medoid element ids of the best pass. */
+int msmb200_kmedoids_restarts(int64_t n_clusters, int64_t n_elements, const double *distmatrix,
+                              int64_t n_pass, const int64_t *starts, int64_t *clusterid,
+                              double *error, int64_t *ifound);
 /* ids relabelled in place in order of first appearance; keys[r] = old id of r */
 int msmb200_contigify_ids(int64_t *ids, int64_t length, int64_t *keys,
                           int64_t *n_keys);

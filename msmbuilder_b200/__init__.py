@@ -9,3 +9,10 @@ lists of sequences); the arithmetic runs as hand-written sm_100a CUDA behind the
 C ABI in include/msmb200.h.  No CPU fallback.
 """
 __version__ = "0.1.0"
+
+
+def device_sequences(sequences):
+    """List of host arrays -> list of CUDA tensors in one device allocation
+    (upload once, then hand the same list to tICA and to the clusterers)."""
+    from ._device import device_sequences as _ds
+    return _ds(sequences)

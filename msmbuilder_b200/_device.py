@@ -119,6 +119,16 @@ class FrameStore(object):
         return [concat[int(o): int(o) + n] for o, n in zip(self.offsets[:-1], self.lengths)]
 
 
+def device_sequences(sequences):
+    """Upload a list of host sequences ONCE: returns CUDA tensors that sit back to
+    back in one allocation, so tICA.fit / transform and every clusterer's
+    ``_concat`` (cluster/base.py:55-58 in the reference) use them without a
+    further copy.  Host arrays are copied slot by slot (pinned memory goes at
+    PCIe rate); CUDA tensors are adopted when already contiguous."""
+    store = FrameStore(sequences)
+    return store.split(store.data)
+
+
 class Workspace(object):
     """Grow-only device scratch buffer keyed by purpose."""
 

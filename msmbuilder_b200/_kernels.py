@@ -68,19 +68,27 @@ class KCentersState(object):
             _lib.call("msmb200_candidate_from_row", dev.ptr(self.data), int(local_row), self.d,
                       self.d, self.dtype, self.row_offset, dev.ptr(cand), dev.stream_ptr())
 
-    def run_pass(self, center_cand, label, out_cand=None):
+    def run_pass(self, center_cand, label, out_cand=None, start=0):
         """One pass against the centre stored in `center_cand`; this shard's
-        farthest frame is written to `out_cand` (default: self.local)."""
+        farthest frame is written to `out_cand` (default: self.local).  `start`
+        restricts the pass to rows [start, n) (RegularSpatial never looks back)."""
         out = self.local if out_cand is None else out_cand
+        start = int(start)
+        n = self.n - start
+        if n <= 0:
+            return out
+        data = self.data[start:]
+        dist = self.distances[start:]
+        lab = self.labels[start:]
         if self.rmsd:
-            _lib.call("msmb200_rmsd_kcenters_pass", dev.ptr(self.data), dev.ptr(self.traces),
-                      self.n, self.n_atoms, self.payload_ptr(center_cand), int(label),
-                      dev.ptr(self.distances), dev.ptr(self.labels), self.row_offset,
+            _lib.call("msmb200_rmsd_kcenters_pass", dev.ptr(data), dev.ptr(self.traces[start:]),
+                      n, self.n_atoms, self.payload_ptr(center_cand), int(label),
+                      dev.ptr(dist), dev.ptr(lab), self.row_offset + start,
                       dev.ptr(out), dev.ptr(self.ws), self.ws.numel(), dev.stream_ptr())
         else:
-            _lib.call("msmb200_kcenters_pass", dev.ptr(self.data), self.n, self.d, self.d,
+            _lib.call("msmb200_kcenters_pass", dev.ptr(data), n, self.d, self.d,
                       self.dtype, self.metric, self.payload_ptr(center_cand), int(label),
-                      dev.ptr(self.distances), dev.ptr(self.labels), self.row_offset,
+                      dev.ptr(dist), dev.ptr(lab), self.row_offset + start,
                       dev.ptr(out), dev.ptr(self.ws), self.ws.numel(), dev.stream_ptr())
         return out
 
@@ -103,6 +111,33 @@ def kcenters_fit(data, n_clusters, metric, seed_index, traces=None):
         st.run_pass(ring[i], i, out_cand=ring[i + 1])
     ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
     return ids, st.distances, st.labels
+
+
+def regular_spatial_fit(data, d_min, metric, traces=None):
+    """RegularSpatial.fit (cluster/regularspatial.py:70-77): frame i becomes a centre
+    when every centre found before it is farther than d_min.  The reference asks
+    that question frame by frame (one `dist` call per frame against the centre
+    list); here each new centre costs ONE streaming pass over the frames after it
+    (running minimum, same arithmetic as K2) plus one scan for the first frame
+    whose minimum still exceeds d_min -- identical centres, O(n_centres) passes.
+
+    Returns the list of centre indices."""
+    st = KCentersState(data, metric, traces=traces)
+    cand = torch.zeros(st.cand_bytes, dtype=torch.uint8, device="cuda")
+    nxt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ids = [0]
+    c = 0
+    d_min = float(d_min)
+    while True:
+        st.seed(cand, c)
+        st.run_pass(cand, len(ids) - 1, start=c + 1)
+        _lib.call("msmb200_first_above", dev.ptr(st.distances), st.n, c + 1, d_min,
+                  dev.ptr(nxt), dev.stream_ptr())
+        c = int(nxt.item())
+        if c < 0:
+            break
+        ids.append(c)
+    return ids
 
 
 # --------------------------------------------------------------------------- K3
@@ -229,11 +264,30 @@ def rmsd_pdist(xyz, traces, rows=None):
 
 
 # ------------------------------------------------------------------- host k-medoids
+def _random_starts(n_clusters, n_elements, n_pass, random):
+    """The initial assignments kmedoids.cc:314-383 would draw inside C: per pass
+    n_clusters - 1 binomials (every cluster keeps one element) and one shuffle,
+    on the same RandomState in the same order."""
+    starts = np.zeros((n_pass, n_elements), dtype=np.int64)
+    for p in range(n_pass):
+        row = starts[p]
+        left = n_elements - n_clusters
+        k = 0
+        for i in range(n_clusters - 1):
+            j = int(random.binomial(float(left), 1.0 / (n_clusters - i)))
+            left -= j
+            j += k + 1
+            row[k:j] = i
+            k = j
+        row[k:] = n_clusters - 1
+        random.shuffle(row)
+    return starts
+
+
 def kmedoids(n_clusters, distmatrix, n_pass, clusterid=None, random_state=None):
-    """_kmedoids.kmedoids (cluster/_kmedoids.pyx:23-107), n_pass == 0 only."""
-    if n_pass != 0:
-        raise NotImplementedError("only n_pass == 0 is on the hot path "
-                                  "(minibatchkmedoids.py:116-118)")
+    """_kmedoids.kmedoids (cluster/_kmedoids.pyx:23-107): n_pass == 0 starts from
+    `clusterid`, n_pass >= 1 from random assignments (cluster/kmedoids.py:92-94)."""
+    from sklearn.utils import check_random_state
     dm = np.ascontiguousarray(distmatrix, dtype=np.float64)
     n_elements = int(1 + np.sqrt(8 * len(dm) + 1) / 2.0)
     if len(dm) != (n_elements * (n_elements - 1) / 2):
@@ -245,12 +299,23 @@ def kmedoids(n_clusters, distmatrix, n_pass, clusterid=None, random_state=None):
                          'number of elements (%d)' % (n_clusters, n_elements))
     if clusterid is not None and len(clusterid) != n_elements:
         raise ValueError('clusterid must be None or an array of length n_elements')
+    if n_pass < 0:
+        raise ValueError('n_pass must be greater than or equal to zero.')
     cid = np.zeros(n_elements, dtype=np.int64) if clusterid is None else \
         np.array(clusterid, dtype=np.int64, copy=True)
+    random = check_random_state(random_state)
     err = ctypes.c_double(0.0)
     ifound = ctypes.c_int64(0)
-    _lib.call("msmb200_kmedoids", int(n_clusters), n_elements, dev.ptr(dm), dev.ptr(cid),
-              ctypes.byref(err), ctypes.byref(ifound))
+    if n_pass >= 2:
+        starts = _random_starts(int(n_clusters), n_elements, int(n_pass), random)
+        _lib.call("msmb200_kmedoids_restarts", int(n_clusters), n_elements, dev.ptr(dm),
+                  int(n_pass), dev.ptr(starts), dev.ptr(cid), ctypes.byref(err),
+                  ctypes.byref(ifound))
+    else:
+        if n_pass == 1:           # in place on the random start (kmedoids.cc:165-166)
+            cid = _random_starts(int(n_clusters), n_elements, 1, random)[0].copy()
+        _lib.call("msmb200_kmedoids", int(n_clusters), n_elements, dev.ptr(dm), dev.ptr(cid),
+                  ctypes.byref(err), ctypes.byref(ifound))
     return cid.astype(np.intp, copy=False), err.value, int(ifound.value)
 
 

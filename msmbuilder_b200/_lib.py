@@ -60,7 +60,14 @@ SIGNATURES = {
     "msmb200_rmsd_pdist": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp]),
     "msmb200_kmedoids": (c_int, [c_i64, c_i64, c_vp, c_vp, ctypes.POINTER(c_dbl),
                                  ctypes.POINTER(c_i64)]),
+    "msmb200_kmedoids_restarts": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_vp,
+                                          ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64)]),
     "msmb200_contigify_ids": (c_int, [c_vp, c_i64, c_vp, ctypes.POINTER(c_i64)]),
+    "msmb200_first_above": (c_int, [c_vp, c_i64, c_i64, c_dbl, c_vp, c_vp]),
+    "msmb200_label_range": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "msmb200_label_presence": (c_int, [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp]),
+    "msmb200_transition_counts": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_i64, c_vp,
+                                          c_i64, c_i64, c_i32, c_vp, c_vp]),
 }
 
 _lib = None

@@ -4,5 +4,8 @@ from .base import MultiSequenceClusterMixin
 from .kcenters import KCenters
 from .minibatchkmedoids import MiniBatchKMedoids
 from .minibatchkmeans import MiniBatchKMeans
+from .regularspatial import RegularSpatial
+from .kmedoids import KMedoids
 
-__all__ = ['KCenters', 'MiniBatchKMedoids', 'MiniBatchKMeans', 'MultiSequenceClusterMixin']
+__all__ = ['KCenters', 'MiniBatchKMedoids', 'MiniBatchKMeans', 'RegularSpatial', 'KMedoids',
+           'MultiSequenceClusterMixin']

@@ -77,6 +77,30 @@ double reassign(const Problem &P, const std::vector<int64_t> &medoid,
     return total;
 }
 
+// One descent from the assignment in member_of: iterate until the objective stops
+// improving or a snapshot (taken whenever the sweep number is a multiple of a
+// period that doubles after each snapshot: sweeps 0, 20, 40, 80, ...) comes back.
+double descend(const Problem &P, std::vector<int64_t> &member_of, std::vector<int64_t> &medoid)
+{
+    std::vector<int64_t> snapshot(P.n);
+    std::vector<double> spread(P.k);
+    double total = DBL_MAX;
+    int64_t sweep = 0, period = 10;
+    for (;;) {
+        const double before = total;
+        if (sweep % period == 0) {
+            snapshot = member_of;
+            if (period < INT64_MAX / 2) period *= 2;
+        }
+        ++sweep;
+        pick_medoids(P, member_of, medoid, spread);
+        total = reassign(P, medoid, member_of);
+        if (total >= before) break;
+        if (snapshot == member_of) break;
+    }
+    return total;
+}
+
 }  // namespace
 
 extern "C" int msmb200_kmedoids(int64_t n_clusters, int64_t n_elements,
@@ -94,26 +118,8 @@ extern "C" int msmb200_kmedoids(int64_t n_clusters, int64_t n_elements,
 
     const Problem P{n_clusters, n_elements, distmatrix};
     std::vector<int64_t> member_of(clusterid, clusterid + n_elements);
-    std::vector<int64_t> snapshot(n_elements), medoid(n_clusters, 0);
-    std::vector<double> spread(n_clusters);
-
-    // Iterate until the objective stops improving or a snapshot (taken whenever
-    // the sweep number is a multiple of a period that doubles after each
-    // snapshot: sweeps 0, 20, 40, 80, ...) comes back.
-    double total = DBL_MAX;
-    int64_t sweep = 0, period = 10;
-    for (;;) {
-        const double before = total;
-        if (sweep % period == 0) {
-            snapshot = member_of;
-            if (period < INT64_MAX / 2) period *= 2;
-        }
-        ++sweep;
-        pick_medoids(P, member_of, medoid, spread);
-        total = reassign(P, medoid, member_of);
-        if (total >= before) break;
-        if (snapshot == member_of) break;
-    }
+    std::vector<int64_t> medoid(n_clusters, 0);
+    const double total = descend(P, member_of, medoid);
 
     // Output convention: the label of a cluster is the element number of its
     // medoid.  If the solution is literally the input (cannot happen for label
@@ -130,6 +136,45 @@ extern "C" int msmb200_kmedoids(int64_t n_clusters, int64_t n_elements,
     } else {
         *ifound = 0;
         for (int64_t e = 0; e < n_elements; ++e) clusterid[e] = member_of[e];
+    }
+    return MSMB200_OK;
+}
+
+// Random restarts (the npass > 1 branch of kmedoids.cc:160-250, used by
+// cluster/kmedoids.py:92-94).  The reference draws each start from a Python
+// RandomState inside C (kmedoids.cc:314-383); here the caller draws all n_pass
+// starts with the same RandomState calls in the same order and hands them over
+// as an (n_pass, n_elements) table, so the host loop stays free of Python.
+extern "C" int msmb200_kmedoids_restarts(int64_t n_clusters, int64_t n_elements,
+                                         const double *distmatrix, int64_t n_pass,
+                                         const int64_t *starts, int64_t *clusterid,
+                                         double *error, int64_t *ifound)
+{
+    if (!distmatrix || !clusterid || !error || !ifound || !starts || n_clusters <= 0 ||
+        n_elements <= 0 || n_pass < 2)
+        return MSMB200_E_INVALID;
+    *ifound = 0;
+    *error = DBL_MAX;
+    if (n_elements < n_clusters) return MSMB200_OK;
+    *ifound = -1;                      // kmedoids.cc:147: counts up from -1
+    for (int64_t i = 0; i < n_pass * n_elements; ++i)
+        if (starts[i] < 0 || starts[i] >= n_clusters) return MSMB200_E_INVALID;
+
+    const Problem P{n_clusters, n_elements, distmatrix};
+    std::vector<int64_t> member_of(n_elements), medoid(n_clusters, 0);
+    for (int64_t pass = 0; pass < n_pass; ++pass) {
+        member_of.assign(starts + pass * n_elements, starts + (pass + 1) * n_elements);
+        const double total = descend(P, member_of, medoid);
+        // keep the best solution; count how often the kept one was found again
+        int64_t e = 0;
+        while (e < n_elements && clusterid[e] == medoid[member_of[e]]) ++e;
+        if (e == n_elements) {
+            ++*ifound;
+        } else if (total < *error) {
+            *ifound = 1;
+            *error = total;
+            for (int64_t j = 0; j < n_elements; ++j) clusterid[j] = medoid[member_of[j]];
+        }
     }
     return MSMB200_OK;
 }

@@ -7,6 +7,8 @@ libdistance oracle.  These travel to the GPU box (the reference .py files cannot
       (seed draw :84, strict `d < distances_` update :93-95, first-max argmax :97)
   minibatch_kmedoids_fit .. msmbuilder/cluster/minibatchkmedoids.py:90-140
       (RandomState call order :99,:100,:108 is part of the contract)
+  regular_spatial_fit ..... msmbuilder/cluster/regularspatial.py:70-77
+  kmedoids_fit ............ msmbuilder/cluster/kmedoids.py:80-100
   split / split_indices ... msmbuilder/cluster/base.py:76-88
 
 Pinned in tests/test_oracle_cluster.py against the reference's own
@@ -92,6 +94,31 @@ def minibatch_kmedoids_fit(X, n_clusters, max_iter=5, batch_size=100,
     final_labels, inertia = assign_fn(X, centers)
     return dict(cluster_ids_=cluster_ids, cluster_centers_=centers,
                 labels_=final_labels, inertia_=inertia, n_iter_=done)
+
+
+def regular_spatial_fit(X, d_min, metric="euclidean", impl="port"):
+    """regularspatial.py:70-77: frame i joins the centres when all its distances to
+    the centres so far exceed d_min.  Returns (cluster_center_indices_, cluster_centers_)."""
+    X = _as_float(X)
+    ids = [0]
+    for i in range(1, len(X)):
+        d = lo.dist(X, X[i], metric, np.array(ids, dtype=np.intp), impl=impl)
+        if np.all(d > d_min):
+            ids.append(i)
+    return ids, X[np.array(ids)]
+
+
+def kmedoids_fit(X, n_clusters, n_passes=1, metric="euclidean", random_state=None, impl="port"):
+    """kmedoids.py:80-100: full pdist, restarted k-medoids, relabel by first appearance.
+    Returns dict(cluster_ids_, labels_, inertia_, cluster_centers_)."""
+    X = _as_float(X)
+    dmat = lo.pdist(X, metric, impl=impl)
+    ids, inertia, _ = lo.kmedoids(n_clusters, dmat, n_passes, random_state=random_state, impl=impl)
+    labels, mapping = lo.contigify_ids(ids, impl=impl)
+    smapping = sorted(mapping.items(), key=itemgetter(1))
+    cluster_ids = np.array(smapping)[:, 0]
+    return dict(cluster_ids_=cluster_ids, labels_=labels, inertia_=inertia,
+                cluster_centers_=X[cluster_ids])
 
 
 def split(concat, lengths):

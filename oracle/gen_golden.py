@@ -92,12 +92,70 @@ def gen_cluster():
     print("wrote cluster_small with", len(out), "arrays")
 
 
+def gen_cluster_more():
+    """RegularSpatial / KMedoids from the reference classes, verbatim."""
+    RegularSpatial, KMedoids = ref_loader.load_more_clusterers()
+    out = {}
+    for metric, d_min in (("euclidean", 4.0), ("cityblock", 8.0), ("chebyshev", 2.5)):
+        for dtype in ("float32", "float64"):
+            seqs = cluster_inputs(31, 3, 300, 5, np.dtype(dtype))
+            rs = RegularSpatial(d_min=d_min, metric=metric).fit(seqs)
+            key = "rs_%s_%s_" % (metric, dtype)
+            out[key + "d_min"] = d_min
+            out[key + "ids"] = np.asarray(rs.cluster_center_indices_)
+            out[key + "centers"] = rs.cluster_centers_
+            out[key + "predict"] = np.concatenate(rs.predict(seqs))
+            for n_passes in (1, 4):
+                km = KMedoids(n_clusters=5, n_passes=n_passes, metric=metric, random_state=7).fit(seqs)
+                key = "km%d_%s_%s_" % (n_passes, metric, dtype)
+                out[key + "ids"] = np.asarray(km.cluster_ids_)
+                out[key + "labels"] = np.concatenate(km.labels_)
+                out[key + "inertia"] = km.inertia_
+    np.savez_compressed(os.path.join(GOLD, "cluster_more.npz"), **out)
+    print("wrote cluster_more with", len(out), "arrays")
+
+
+def msm_inputs(case):
+    rs = np.random.RandomState(100 + case)
+    n_states = (4, 9, 70, 200)[case]
+    seqs = []
+    for _ in range(5):
+        n = int(rs.randint(1, 3000))
+        y = rs.randint(0, n_states, size=n)
+        if case == 1:
+            y = y * 5 - 7                       # non-contiguous, negative labels
+        seqs.append(y.astype(np.int64))
+    return seqs
+
+
+def gen_msm():
+    """_transition_counts (msm/core.py:487-602) from the reference function, verbatim."""
+    tc = ref_loader.load_transition_counts()
+    out = {"n_cases": 4}
+    for case, (lag, sliding) in enumerate([(1, True), (3, True), (4, False), (7, True)]):
+        seqs = msm_inputs(case)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            c, m = tc(seqs, lag_time=lag, sliding_window=sliding)
+        out["lens_%d" % case] = np.array([len(s) for s in seqs])
+        out["labels_%d" % case] = np.concatenate(seqs)
+        out["lag_%d" % case] = lag
+        out["sliding_%d" % case] = sliding
+        out["counts_%d" % case] = c
+        out["classes_%d" % case] = np.array(sorted(int(k) for k in m.keys()))
+    np.savez_compressed(os.path.join(GOLD, "msm_counts.npz"), **out)
+    print("wrote msm_counts")
+
+
 def main():
+    import sys
     if not ref_loader.available():
         raise SystemExit("reference tree absent: goldens can only be generated in the build container")
     os.makedirs(GOLD, exist_ok=True)
-    gen_tica()
-    gen_cluster()
+    which = sys.argv[1:] or ["tica", "cluster", "cluster_more", "msm"]
+    for name in which:
+        {"tica": gen_tica, "cluster": gen_cluster, "cluster_more": gen_cluster_more,
+         "msm": gen_msm}[name]()
 
 
 if __name__ == "__main__":

@@ -55,6 +55,12 @@ class _Lib:
         self.lib = ctypes.CDLL(path)
         self.prefix = "oracle_" if impl == "port" else "ref_"
 
+    def pylib(self):
+        """Same library through PyDLL (GIL held) for entry points that call back into Python."""
+        if getattr(self, "_pylib", None) is None:
+            self._pylib = ctypes.PyDLL(self.lib._name)
+        return self._pylib
+
     def fn(self, name, restype):
         f = getattr(self.lib, self.prefix + name)
         f.restype = restype
@@ -172,12 +178,29 @@ def sumdist(X, metric, pair_indices, impl="port"):
                    _c_i64(X.shape[1]), _ptr(pairs), _c_i64(pairs.shape[0])))
 
 
+def random_assignment(n_clusters, n_elements, random):
+    """kmedoids.cc:314-383: cluster sizes from successive binomials (each cluster
+    keeps at least one element), then one shuffle.  Same RandomState calls, same order."""
+    cid = np.zeros(n_elements, dtype=np.int64)
+    n = n_elements - n_clusters
+    k = 0
+    for i in range(n_clusters - 1):
+        j = int(random.binomial(float(n), 1.0 / (n_clusters - i)))
+        n -= j
+        j += k + 1
+        cid[k:j] = i
+        k = j
+    cid[k:] = n_clusters - 1
+    random.shuffle(cid)
+    return cid
+
+
 def kmedoids(n_clusters, distmatrix, n_pass, clusterid=None, random_state=None,
              impl="port"):
-    """_kmedoids.pyx:23-107 restricted to n_pass == 0 (all the hot path uses)."""
-    if n_pass != 0:
-        raise NotImplementedError("oracle covers n_pass == 0 only "
-                                  "(minibatchkmedoids.py:116-118)")
+    """_kmedoids.pyx:23-107.  impl='reference' runs the reference C++ for every
+    n_pass; impl='port' restates the restart loop (kmedoids.cc:181-250) in Python
+    over the C port of one descent."""
+    from sklearn.utils import check_random_state
     dm = np.ascontiguousarray(distmatrix, dtype=np.float64)
     n_elements = int(1 + np.sqrt(8 * len(dm) + 1) / 2.0)
     if len(dm) != (n_elements * (n_elements - 1) / 2):
@@ -186,21 +209,56 @@ def kmedoids(n_clusters, distmatrix, n_pass, clusterid=None, random_state=None,
     if n_clusters > n_elements:
         raise ValueError("Number of clusters requested (%d) greater than "
                          "number of elements (%d)" % (n_clusters, n_elements))
+    if clusterid is not None and len(clusterid) != n_elements:
+        raise ValueError("clusterid must be None or an array of length n_elements")
+    if n_pass < 0:
+        raise ValueError("n_pass must be greater than or equal to zero.")
     if clusterid is None:
         cid = np.zeros(n_elements, dtype=np.int64)
     else:
-        if len(clusterid) != n_elements:
-            raise ValueError("clusterid must be None or an array of length n_elements")
         cid = np.array(clusterid, dtype=np.int64, copy=True)
+    random = check_random_state(random_state)
     err = _c_dbl(0.0)
     L = get(impl)
-    if impl == "port":
-        f = L.fn("kmedoids", ctypes.c_int)
-    else:
-        f = L.fn("kmedoids_npass0", _c_i64)
-    ifound = f(_c_i64(n_clusters), _c_i64(n_elements), _ptr(dm), _ptr(cid),
-               ctypes.byref(err))
-    return cid.astype(np.intp, copy=False), err.value, int(ifound)
+    if impl == "reference":
+        if n_pass == 0:
+            ifound = L.fn("kmedoids_npass0", _c_i64)(
+                _c_i64(n_clusters), _c_i64(n_elements), _ptr(dm), _ptr(cid), ctypes.byref(err))
+        else:
+            f = getattr(L.pylib(), "ref_kmedoids_npass")
+            f.restype = _c_i64
+            ifound = f(_c_i64(n_clusters), _c_i64(n_elements), _ptr(dm), _c_i64(n_pass),
+                       _ptr(cid), ctypes.py_object(random), ctypes.byref(err))
+        return cid.astype(np.intp, copy=False), err.value, int(ifound)
+
+    descent = L.fn("kmedoids", ctypes.c_int)
+    if n_pass == 0:
+        ifound = descent(_c_i64(n_clusters), _c_i64(n_elements), _ptr(dm), _ptr(cid),
+                         ctypes.byref(err))
+        return cid.astype(np.intp, copy=False), err.value, int(ifound)
+    if n_pass == 1:
+        # tclusterid IS clusterid (kmedoids.cc:165-166): one descent from a random start
+        cid = random_assignment(n_clusters, n_elements, random)
+        ifound = descent(_c_i64(n_clusters), _c_i64(n_elements), _ptr(dm), _ptr(cid),
+                         ctypes.byref(err))
+        return cid.astype(np.intp, copy=False), err.value, int(ifound)
+    best = float(np.finfo(np.float64).max)
+    ifound = -1
+    for _ in range(n_pass):
+        t = random_assignment(n_clusters, n_elements, random)
+        descent(_c_i64(n_clusters), _c_i64(n_elements), _ptr(dm), _ptr(t), ctypes.byref(err))
+        total = 0.0
+        for i in range(n_elements):        # same summation order as kmedoids.cc:213-233
+            if t[i] != i:
+                total += dm[condensed_index(i, int(t[i]), n_elements)]
+        # kmedoids.cc:237-249: t now holds centroid ids; compare with the kept solution
+        if np.array_equal(cid, t):
+            ifound += 1
+        elif total < best:
+            ifound = 1
+            best = total
+            cid[:] = t
+    return cid.astype(np.intp, copy=False), best, int(ifound)
 
 
 def contigify_ids(ids, impl="port"):

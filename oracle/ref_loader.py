@@ -164,3 +164,41 @@ def load_cluster():
                         os.path.join("cluster", "minibatchkmedoids.py"))
         _loaded["cluster"] = (kc.KCenters, mb.MiniBatchKMedoids, base.MultiSequenceClusterMixin)
     return _loaded["cluster"]
+
+
+def _numpy_aliases():
+    """msm/core.py:560-562 uses np.int / np.float (gone since NumPy 1.24)."""
+    import numpy as np
+    for name, typ in (("int", int), ("float", float)):
+        if not hasattr(np, name):
+            setattr(np, name, typ)
+    if not hasattr(np, "row_stack"):
+        np.row_stack = np.vstack
+
+
+def load_transition_counts():
+    """Returns the reference's `_transition_counts` (msm/core.py:487-602), unmodified.
+    `msmbuilder.msm._ratematrix` (Cython, not on this path) is an empty stand-in."""
+    if "msm_core" not in _loaded:
+        _common()
+        _numpy_aliases()
+        pkg = _stub_package("msmbuilder.msm")
+        rm = types.ModuleType("msmbuilder.msm._ratematrix")
+        sys.modules["msmbuilder.msm._ratematrix"] = rm
+        pkg._ratematrix = rm
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = _load_file("msmbuilder.msm.core", os.path.join("msm", "core.py"))
+        _loaded["msm_core"] = mod
+    return _loaded["msm_core"]._transition_counts
+
+
+def load_more_clusterers():
+    """Returns (RegularSpatial, KMedoids): cluster/regularspatial.py:106 and
+    cluster/kmedoids.py:144, unmodified, over the same stand-ins as load_cluster()."""
+    if "cluster_more" not in _loaded:
+        load_cluster()
+        rs = _load_file("msmbuilder.cluster.regularspatial", os.path.join("cluster", "regularspatial.py"))
+        km = _load_file("msmbuilder.cluster.kmedoids", os.path.join("cluster", "kmedoids.py"))
+        _loaded["cluster_more"] = (rs.RegularSpatial, km.KMedoids)
+    return _loaded["cluster_more"]

@@ -36,6 +36,13 @@
 
 /* kmedoids.cc verbatim; its one py2-only symbol is mapped by
  * -DPyInt_AsLong=PyLong_AsLong on the command line. */
+/* kmedoids.cc:47-58 `initialize_numpy` is declared `static int` under Python 3 but has
+ * no return statement; g++ >= 8 treats falling off its end as unreachable and the call
+ * crashes.  Without touching the source: pull in the NumPy header first (its include guard
+ * makes the later #include a no-op) and let the `import_array()` statement itself return. */
+#include <numpy/arrayobject.h>
+#undef import_array
+#define import_array() do { return _import_array() < 0 ? 0 : 1; } while (0)
 #include "kmedoids.cc"
 
 extern "C" {
@@ -115,6 +122,16 @@ int64_t ref_kmedoids_npass0(int64_t k, int64_t n, double *dm, int64_t *clusterid
 {
     npy_intp ifound = 0;
     kmedoids(k, n, dm, 0, (npy_intp *)clusterid, NULL, error, &ifound);
+    return ifound;
+}
+
+/* any npass: `random` is a borrowed numpy RandomState whose binomial/shuffle methods
+ * kmedoids.cc:314-383 calls.  Must be entered with the GIL held (ctypes.PyDLL). */
+int64_t ref_kmedoids_npass(int64_t k, int64_t n, double *dm, int64_t npass,
+                           int64_t *clusterid, PyObject *random, double *error)
+{
+    npy_intp ifound = 0;
+    kmedoids(k, n, dm, npass, (npy_intp *)clusterid, random, error, &ifound);
     return ifound;
 }
 

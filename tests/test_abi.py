@@ -72,3 +72,22 @@ def test_host_kmedoids_matches_oracle():
         K.kmedoids(3, np.zeros(4), 0, None)          # not a triangular number
     with pytest.raises(ValueError):
         K.kmedoids(9, np.zeros(3), 0, None)          # more clusters than elements
+
+
+def test_host_kmedoids_restarts_match_oracle():
+    # n_pass >= 1 (cluster/kmedoids.py:92-94): same RandomState draws, same kept solution
+    from msmbuilder_b200 import _kernels as K
+    rs = np.random.RandomState(1)
+    for trial in range(20):
+        n, k = int(rs.randint(6, 90)), int(rs.randint(1, 8))
+        n_pass = int(rs.randint(1, 6))
+        X = rs.randn(n, 3)
+        if trial % 5 == 0:
+            X = np.round(X)                # ties
+        dm = lo.pdist(X, "euclidean")
+        a = lo.kmedoids(k, dm, n_pass, random_state=trial)
+        b = K.kmedoids(k, dm, n_pass, random_state=trial)
+        np.testing.assert_array_equal(a[0], b[0])
+        assert a[1] == b[1] and a[2] == b[2], (trial, a[1:], b[1:])
+    with pytest.raises(ValueError):
+        K.kmedoids(3, np.zeros(10), -1)

@@ -93,3 +93,57 @@ def test_sqeuclidean_same_labels_and_dtype_agreement():
     d = co.kcenters_fit(X32.astype(np.float64), 8, "euclidean", random_state=0)
     np.testing.assert_array_equal(c["labels_"], d["labels_"])
     np.testing.assert_allclose(c["distances_"], d["distances_"], rtol=1e-6)
+
+
+# ----------------------------------------------------------------- SURVEY 8f-3 consumers
+MORE = [("euclidean", 4.0), ("cityblock", 8.0), ("chebyshev", 2.5)]
+
+
+@pytest.mark.parametrize("metric,d_min", MORE)
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_regular_spatial_and_kmedoids_oracle_match_golden(golden_dir, metric, d_min, dtype):
+    g = np.load(os.path.join(golden_dir, "cluster_more.npz"))
+    seqs = cluster_inputs(31, 3, 300, 5, np.dtype(dtype))
+    X = np.concatenate(seqs)
+    ids, centers = co.regular_spatial_fit(X, d_min, metric)
+    key = "rs_%s_%s_" % (metric, dtype)
+    np.testing.assert_array_equal(co.split_indices(ids, [300] * 3), g[key + "ids"])
+    np.testing.assert_array_equal(centers, g[key + "centers"])
+    pred, _ = lo.assign_nearest(X, centers, metric)
+    np.testing.assert_array_equal(pred, g[key + "predict"])
+    for n_passes in (1, 4):
+        r = co.kmedoids_fit(X, 5, n_passes, metric, random_state=7)
+        key = "km%d_%s_%s_" % (n_passes, metric, dtype)
+        np.testing.assert_array_equal(co.split_indices(r["cluster_ids_"], [300] * 3), g[key + "ids"])
+        np.testing.assert_array_equal(r["labels_"], g[key + "labels"])
+        assert r["inertia_"] == float(g[key + "inertia"])
+
+
+@needs_ref
+def test_kmedoids_restarts_port_matches_reference_cxx():
+    # the restart loop of kmedoids.cc:160-250 incl. its RandomState use (:314-383)
+    rs = np.random.RandomState(5)
+    for n, k, n_pass in ((30, 3, 1), (80, 6, 2), (120, 9, 7), (12, 12, 3), (9, 1, 2)):
+        X = rs.randn(n, 3)
+        dm = lo.pdist(X, "euclidean", impl="reference")
+        a = lo.kmedoids(k, dm, n_pass, random_state=11, impl="reference")
+        b = lo.kmedoids(k, dm, n_pass, random_state=11, impl="port")
+        np.testing.assert_array_equal(a[0], b[0])
+        assert a[1] == b[1] and a[2] == b[2]
+
+
+@needs_ref
+def test_more_clusterers_match_verbatim_reference():
+    RegularSpatial, KMedoids = ref_loader.load_more_clusterers()
+    rs = np.random.RandomState(2)
+    seqs = [rs.randn(120, 3).astype(np.float32) for _ in range(3)]
+    X = np.concatenate(seqs)
+    ref = RegularSpatial(d_min=1.2, metric="euclidean").fit(seqs)
+    ids, centers = co.regular_spatial_fit(X, 1.2, "euclidean")
+    np.testing.assert_array_equal(ref.cluster_center_indices_, co.split_indices(ids, [120] * 3))
+    assert ref.n_clusters_ == len(ids)
+    km = KMedoids(n_clusters=4, n_passes=3, random_state=0).fit(seqs)
+    r = co.kmedoids_fit(X, 4, 3, "euclidean", random_state=0)
+    np.testing.assert_array_equal(km.cluster_ids_, co.split_indices(r["cluster_ids_"], [120] * 3))
+    np.testing.assert_array_equal(np.concatenate(km.labels_), r["labels_"])
+    assert km.inertia_ == r["inertia_"]
