@@ -50,7 +50,11 @@ class MultiSequenceClusterMixin(object):
 
     def _concat(self, sequences):
         from .._device import FrameStore
-        seqs = list(sequences)
+        if hasattr(sequences, 'to_device'):
+            # io.NumpyDirStream: files go straight into their slots of one device buffer
+            seqs = sequences.to_device()
+        else:
+            seqs = list(sequences)
         self.__lengths = [len(s) for s in seqs]
         if len(seqs) == 0:
             raise TypeError('sequences must be a list of numpy arrays '

@@ -263,7 +263,9 @@ class tICA(BaseEstimator, TransformerMixin):
                     X = X.unsqueeze(0)
                 if X.dtype not in (torch.float32, torch.float64):
                     X = X.to(torch.float64)
-                nbytes = 0 if X.is_cuda else X.numel() * X.element_size()
+                # device tensors count too: a lazy stream (io.NumpyDirStream) must not
+                # pile its whole dataset up in `batch`
+                nbytes = X.numel() * X.element_size()
             else:
                 X = np.atleast_2d(np.asarray(X))
                 if X.dtype not in (np.float32, np.float64):

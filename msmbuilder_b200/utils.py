@@ -28,6 +28,12 @@ def is_trajectory(x):
 def check_iter_of_sequences(sequences, allow_trajectory=False, ndim=2, max_iter=None):
     """Raise ValueError('sequences must be a list of sequences') unless every
     inspected item is an ``ndim``-dimensional array (or an allowed trajectory)."""
+    if hasattr(sequences, "shapes") and hasattr(sequences, "to_device"):
+        # io.NumpyDirStream: look at the file headers instead of uploading anything
+        for shape, _ in sequences.shapes():
+            if len(shape) != ndim and not (allow_trajectory and len(shape) == 3):
+                raise ValueError('sequences must be a list of sequences')
+        return
     ok = True
     for i, X in enumerate(sequences):
         if is_trajectory(X):

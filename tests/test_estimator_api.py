@@ -3,6 +3,7 @@ clone / pickle / get_params, numpydoc Parameters == __init__ (the reference's CL
 derives flags from that: msmbuilder/cmdline.py:334-384), base class
 (tests/test_estimator_subclassing.py:52-55), error behaviour."""
 import inspect
+import os
 import pickle
 import re
 
@@ -11,7 +12,8 @@ import pytest
 from sklearn.base import BaseEstimator as SkBase, clone
 
 from msmbuilder_b200.base import BaseEstimator
-from msmbuilder_b200.cluster import KCenters, MiniBatchKMedoids, MiniBatchKMeans
+from msmbuilder_b200.cluster import (KCenters, MiniBatchKMedoids, MiniBatchKMeans, RegularSpatial,
+                                     KMedoids)
 from msmbuilder_b200.decomposition import tICA
 from msmbuilder_b200.utils import check_iter_of_sequences, array2d
 
@@ -21,6 +23,9 @@ REF_SIGNATURES = {
     KCenters: ["n_clusters", "metric", "random_state"],
     MiniBatchKMedoids: ["n_clusters", "max_iter", "batch_size", "metric", "max_no_improvement",
                         "random_state"],
+    # regularspatial.py:65, kmedoids.py:73-74
+    RegularSpatial: ["d_min", "metric"],
+    KMedoids: ["n_clusters", "n_passes", "metric", "random_state"],
 }
 REF_DEFAULTS = {
     tICA: dict(n_components=None, lag_time=1, shrinkage=None, kinetic_mapping=False,
@@ -28,10 +33,12 @@ REF_DEFAULTS = {
     KCenters: dict(n_clusters=8, metric='euclidean', random_state=None),
     MiniBatchKMedoids: dict(n_clusters=8, max_iter=5, batch_size=100, metric='euclidean',
                             max_no_improvement=10, random_state=None),
+    RegularSpatial: dict(metric='euclidean'),
+    KMedoids: dict(n_clusters=8, n_passes=1, metric='euclidean', random_state=None),
 }
 
 
-@pytest.mark.parametrize("cls", [tICA, KCenters, MiniBatchKMedoids])
+@pytest.mark.parametrize("cls", [tICA, KCenters, MiniBatchKMedoids, RegularSpatial, KMedoids])
 def test_signature_matches_reference(cls):
     params = inspect.signature(cls.__init__).parameters
     names = [p for p in params if p != "self"]
@@ -42,9 +49,10 @@ def test_signature_matches_reference(cls):
         assert params[extra].default is not inspect.Parameter.empty
 
 
-@pytest.mark.parametrize("cls", [tICA, KCenters, MiniBatchKMedoids, MiniBatchKMeans])
+@pytest.mark.parametrize("cls", [tICA, KCenters, MiniBatchKMedoids, MiniBatchKMeans, RegularSpatial,
+                                 KMedoids])
 def test_clone_pickle_base(cls):
-    est = cls()
+    est = cls(d_min=1.0) if cls is RegularSpatial else cls()
     assert isinstance(est, BaseEstimator) and isinstance(est, SkBase)
     c = clone(est)
     assert c.get_params() == est.get_params()
@@ -52,7 +60,7 @@ def test_clone_pickle_base(cls):
     assert isinstance(est.summarize() if cls is MiniBatchKMeans else "x", str)
 
 
-@pytest.mark.parametrize("cls", [tICA, KCenters, MiniBatchKMedoids])
+@pytest.mark.parametrize("cls", [tICA, KCenters, MiniBatchKMedoids, RegularSpatial, KMedoids])
 def test_numpydoc_parameters_cover_init(cls):
     doc = cls.__doc__
     sect = doc[doc.index("Parameters"):doc.index("Attributes")]
@@ -105,3 +113,26 @@ def test_tica_state_names_and_packed_fold():
     bad[-3] = np.nan
     with pytest.raises(ValueError):
         t._add_packed(bad)
+
+
+def test_npy_stream_host_side(tmp_path):
+    """io.NumpyDirStream without a GPU: file discovery, header shapes, validation."""
+    from msmbuilder_b200.io import NumpyDirStream, save_sequences
+    from msmbuilder_b200.utils import check_iter_of_sequences
+    from msmbuilder_b200 import _lib
+    seqs = [np.zeros((5, 3), np.float32), np.ones((2, 3), np.float64), np.zeros((0, 3), np.float32)]
+    path = save_sequences(str(tmp_path / "ds"), seqs)
+    open(os.path.join(path, "PROVENANCE.txt"), "w").write("x")        # ignored like dataset.py:329
+    s = NumpyDirStream(path)
+    assert len(s) == 3 and s.keys() == [0, 1, 2]
+    assert [sh for sh, _ in s.shapes()] == [(5, 3), (2, 3), (0, 3)]
+    check_iter_of_sequences(s)
+    save_sequences(str(tmp_path / "bad"), [np.zeros(4)])
+    with pytest.raises(ValueError):
+        check_iter_of_sequences(NumpyDirStream(str(tmp_path / "bad")))
+    with pytest.raises(ValueError):
+        NumpyDirStream(str(tmp_path))                                   # no .npy items
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.Msmb200Error):
+            next(iter(s))

@@ -221,3 +221,72 @@ def test_upload_once_pipeline_equals_host_calls():
     c_dev, _ = tc(kc_dev.labels_, lag_time=5)
     c_ref, _ = mo.transition_counts(kc_host.labels_, 5)
     np.testing.assert_array_equal(c_dev, c_ref)
+
+
+# ------------------------------------------------------------------ .npy directory stream (8f-2)
+def _write_dataset(tmp_path, dtype=np.float32):
+    from msmbuilder_b200.io import save_sequences
+    from msmbuilder_b200.synthetic import ar1_numpy
+    seqs = ar1_numpy(5, 3000, 32, seed=9, dtype=dtype)
+    seqs = [seqs[0], seqs[1][:7], seqs[2][:1234], seqs[3], seqs[4][:2999]]   # ragged, one too short
+    return seqs, save_sequences(str(tmp_path / "ds"), seqs)
+
+
+def test_npy_stream_feeds_tica_and_clusterers(tmp_path):
+    import warnings
+    import torch
+    from msmbuilder_b200.io import NumpyDirStream
+    from msmbuilder_b200.decomposition import tICA
+    from msmbuilder_b200.cluster import KCenters
+    seqs, path = _write_dataset(tmp_path)
+    stream = NumpyDirStream(path, prefetch=2)
+    assert len(stream) == 5 and [s for s, _ in stream.shapes()] == [x.shape for x in seqs]
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                      # the 7-frame sequence is skipped
+        a = tICA(n_components=3, lag_time=10).fit(seqs)
+        b = tICA(n_components=3, lag_time=10).fit(stream)
+    assert a.n_sequences_ == b.n_sequences_ == 4 and a.n_observations_ == b.n_observations_
+    # same kernel on the same frames; only the host-side order of the float64 folds differs
+    np.testing.assert_allclose(a.eigenvalues_, b.eigenvalues_, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(a._outer_0_to_T_lagged, b._outer_0_to_T_lagged, rtol=1e-13)
+
+    # iterating twice gives the same tensors; an abandoned iteration does not hang
+    first = [t.cpu().numpy() for t in stream]
+    for x, y in zip(first, seqs):
+        np.testing.assert_array_equal(x, y)
+    for i, t in enumerate(stream):
+        assert t.is_cuda
+        if i == 1:
+            break
+
+    dseqs = stream.to_device()
+    assert dseqs[1].data_ptr() == dseqs[0].data_ptr() + seqs[0].nbytes
+    for x, y in zip(dseqs, seqs):
+        np.testing.assert_array_equal(x.cpu().numpy(), y)
+
+    ka = KCenters(n_clusters=7, random_state=2).fit(seqs)
+    kb = KCenters(n_clusters=7, random_state=2).fit(stream)
+    assert ka.cluster_ids_ == kb.cluster_ids_
+    for x, y in zip(ka.labels_, kb.labels_):
+        np.testing.assert_array_equal(x, y)
+    for x, y in zip(ka.predict(seqs), kb.predict(stream)):
+        np.testing.assert_array_equal(x, y)
+    for x, y in zip(a.transform(seqs), b.transform(stream)):
+        np.testing.assert_array_equal(x, y.cpu().numpy())
+
+
+def test_npy_stream_small_stage_batches(tmp_path):
+    # force one accumulate call per sequence: results must not depend on batching
+    import warnings
+    from msmbuilder_b200.io import NumpyDirStream
+    from msmbuilder_b200.decomposition import tICA
+    seqs, path = _write_dataset(tmp_path, np.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = tICA(n_components=2, lag_time=3).fit(seqs)
+        b = tICA(n_components=2, lag_time=3)
+        b._stage_bytes = 1
+        b.fit(NumpyDirStream(path, prefetch=1))
+    np.testing.assert_allclose(a.eigenvalues_, b.eigenvalues_, rtol=0, atol=1e-12)
+    assert a.n_observations_ == b.n_observations_

@@ -87,9 +87,39 @@ def kmedoids_case(n, d, k, n_passes):
           % (n, d, k, n_passes, ms, pairs / ms / 1e6, dt * 1e3, km.inertia_))
 
 
+def stream_case(n_files, length, d):
+    """tICA.fit on a directory of .npy files: list of np.load arrays vs NumpyDirStream."""
+    import shutil
+    import tempfile
+    from msmbuilder_b200.decomposition import tICA
+    from msmbuilder_b200.io import NumpyDirStream, save_sequences
+    tmp = tempfile.mkdtemp(prefix="msmb200_ds_")
+    try:
+        X = ar1_device(n_files, length, d, seed=5)
+        save_sequences(tmp, [X[i * length:(i + 1) * length].cpu().numpy() for i in range(n_files)])
+        del X
+        nbytes = n_files * length * d * 4
+        stream = NumpyDirStream(tmp, prefetch=2)
+        for label, make in (("np.load list", lambda: [np.load(f) for f in stream.files]),
+                            ("NumpyDirStream", lambda: stream)):
+            best = 1e9
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                m = tICA(n_components=4, lag_time=10).fit(make())
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            print("tICA.fit %d x %d x %d from .npy (page cache), %s: %.1f ms = %.2f GB/s, %.1f M frames/s, "
+                  "lambda0 %.6f" % (n_files, length, d, label, best * 1e3, nbytes / best / 1e9,
+                                    n_files * length / best / 1e6, m.eigenvalues_[0]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
     _lib.require_gpu()
     for n_states, sticky in ((8, 1), (8, 0), (90, 1), (500, 1), (2000, 1), (2000, 0)):
         counts_case(50_000_000, n_states, 10, sticky)
     regular_spatial_case(2_000_000, 64, 50)
     kmedoids_case(8000, 64, 10, 3)
+    stream_case(40, 100000, 256)
