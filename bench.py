@@ -238,7 +238,7 @@ def run_ours(args):
     n_total = n_seq_total * L
     row_offset = s0 * L
 
-    X = ar1_device(n_seq, L, D, seed=1000 + rank)
+    X = ar1_device(n_seq, L, D, seed=1000, first_seq=s0)   # same global dataset for every N
     torch.cuda.synchronize()
     seqs = [X[i * L:(i + 1) * L] for i in range(n_seq)]
     est = tICA(n_components=4, lag_time=lag, engine=args.engine)
@@ -420,7 +420,8 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": dominant, "roofline_all": [roof_k1, roof_k2],
         "phases_ms": {"tica_fit": tica_s * 1e3, "kcenters_fit": kc_s * 1e3},
-        "tica_engine": args.engine, "check": {"eigenvalues": eig},
+        "tica_engine": args.engine,
+        "check": {"eigenvalues": eig, "kcenters_ids": [int(i) for i in state["ids"].cpu().numpy()]},
     }
 
     if ws == 1 and not args.no_cpu_baseline:

@@ -59,6 +59,13 @@ class _Staging(object):
             self.bufs[j] = torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory()
         return j, self.bufs[j]
 
+    def drain(self):
+        """Wait until no copy reads any buffer (they are about to be released: the
+        pinned allocator does not know about copies issued from NumPy views)."""
+        for ev in self.events:
+            if ev is not None:
+                ev.synchronize()
+
 
 class NumpyDirStream(object):
     """Lazy, re-iterable collection of sequences stored as .npy files.
@@ -165,6 +172,7 @@ class NumpyDirStream(object):
                 except queue.Empty:
                     pass
                 th.join(timeout=0.01)
+            staging.drain()
 
     # ------------------------------------------------------------------ one allocation
     def to_device(self):
@@ -195,4 +203,5 @@ class NumpyDirStream(object):
             _, last = self._upload(a, staging, copy_stream, dst=data[int(offsets[i]):int(offsets[i + 1])])
         if last is not None:
             torch.cuda.current_stream().wait_event(last)
+        staging.drain()
         return [data[int(o):int(o) + n] for o, n in zip(offsets[:-1], lengths)]

@@ -39,8 +39,13 @@ def ar1_numpy(n_seq, length, D, seed=0, dtype=np.float32):
     return out
 
 
-def ar1_device(n_seq, length, D, seed=0, block=128, seqs_per_chunk=None, out=None):
+def ar1_device(n_seq, length, D, seed=0, block=128, seqs_per_chunk=None, out=None, first_seq=0):
     """(n_seq * length, D) float32 CUDA tensor holding n_seq back-to-back sequences.
+
+    `seed` fixes the process (mixing matrix, means); the noise of sequence j is drawn
+    from its own generator seeded by (seed, first_seq + j), so a rank that generates
+    sequences [first_seq, first_seq + n_seq) of a global dataset gets exactly the
+    frames any other sharding would give it.
 
     Blocked linear recurrence: inside a block of `block` frames the AR(1) response
     is a (block x block) lower-triangular Toeplitz product per feature; the carry
@@ -53,7 +58,6 @@ def ar1_device(n_seq, length, D, seed=0, block=128, seqs_per_chunk=None, out=Non
     mud = torch.from_numpy(mu).to(dev, torch.float32)
     phid = torch.from_numpy(phi).to(dev, torch.float64)
     g = torch.Generator(device=dev)
-    g.manual_seed(seed)
     B = block
     nb = (length + B - 1) // B
     Lp = nb * B
@@ -72,19 +76,28 @@ def ar1_device(n_seq, length, D, seed=0, block=128, seqs_per_chunk=None, out=Non
         seqs_per_chunk = max(1, int((1 << 28) // max(1, Lp * D)))   # ~1 GiB of float32 per temp
     for s0 in range(0, n_seq, seqs_per_chunk):
         s = min(seqs_per_chunk, n_seq - s0)
-        eps = torch.randn((s, nb, B, D), generator=g, device=dev, dtype=torch.float32) * sig
-        # within-block response: y[s, b, i, d] = sum_j T[d, i, j] eps[s, b, j, d]
-        e = eps.permute(3, 2, 0, 1).reshape(D, B, s * nb)      # (D, B, s*nb)
-        y = torch.bmm(T, e).reshape(D, B, s, nb).permute(2, 3, 1, 0).contiguous()  # (s, nb, B, D)
+        eps = torch.empty((s, nb, B, D), device=dev, dtype=torch.float32)
+        carry = torch.empty((s, D), device=dev, dtype=torch.float32)               # z_{-1}
+        for j in range(s):
+            g.manual_seed((int(seed) * 1000003 + int(first_seq) + s0 + j) % (2 ** 63 - 1))
+            torch.randn((nb, B, D), generator=g, out=eps[j])
+            torch.randn((D,), generator=g, out=carry[j])
+        eps *= sig
+        # within-block response: y[s, b, i, d] = sum_j T[d, i, j] eps[s, b, j, d]; one bmm per
+        # sequence so that its shape (and with it the cuBLAS kernel and the bits) never
+        # depends on how many sequences this call generates
+        y = torch.empty((s, nb, B, D), device=dev, dtype=torch.float32)
+        for j in range(s):
+            e = eps[j].permute(2, 1, 0).contiguous()             # (D, B, nb)
+            y[j] = torch.bmm(T, e).permute(2, 1, 0)              # (nb, B, D)
         del eps, e
-        carry = torch.randn((s, D), generator=g, device=dev, dtype=torch.float32)   # z_{-1}
         for b in range(nb):
             y[:, b] += decay[None] * carry[:, None, :]
             carry = y[:, b, B - 1, :].clone()
-        z = y.reshape(s, Lp, D)[:, :length, :]
-        x = torch.matmul(z, Qd) + mud
-        out[s0 * length:(s0 + s) * length] = x.reshape(s * length, D)
-        del y, z, x
+        for j in range(s):
+            z = y[j].reshape(Lp, D)[:length]
+            out[(s0 + j) * length:(s0 + j + 1) * length] = torch.matmul(z, Qd) + mud
+        del y, z
     return out
 
 

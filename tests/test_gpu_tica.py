@@ -221,3 +221,22 @@ def test_umma_narrow_feature_counts(D):
         _assert_moments_close(m, a, 5e-6)
         np.testing.assert_allclose(m.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)
         np.testing.assert_allclose(m.means_, a.means_, rtol=0, atol=1e-6)
+
+
+def test_synthetic_dataset_is_independent_of_sharding():
+    # bench.py generates rank r's sequences with first_seq = its offset: any N sees the same frames
+    import torch
+    from msmbuilder_b200.synthetic import ar1_device
+    whole = ar1_device(7, 1500, 32, seed=11)
+    parts = torch.cat([ar1_device(3, 1500, 32, seed=11, first_seq=0),
+                       ar1_device(1, 1500, 32, seed=11, first_seq=3),
+                       ar1_device(3, 1500, 32, seed=11, first_seq=4, seqs_per_chunk=2)])
+    assert torch.equal(whole, parts)
+    other = ar1_device(7, 1500, 32, seed=12)
+    assert not torch.equal(whole, other)
+    # statistics: lag-1 autocorrelation of the slowest latent direction is ~0.999
+    x = whole[:1500].double()
+    x = x - x.mean(0)
+    c0 = (x[:-1] * x[:-1]).sum()
+    c1 = (x[:-1] * x[1:]).sum()
+    assert 0.5 < float(c1 / c0) < 1.0
