@@ -388,9 +388,10 @@ def run_ours(args):
     hbm_ach = bytes_per_pass / pass_s / 1e9
     flops_tica = 4.0 * D * D * (n_total / ws)              # algorithmic: two rank-1 DxD updates / frame
     # tensor peak for the engine's MMA kind: bf16 = measured sustained cuBLAS bf16; tf32 = half of it
-    is_bf16 = args.engine in ("auto", "umma_3xbf16", "umma_6xbf16")
+    is_bf16 = args.engine in ("auto", "umma_3xf16", "umma_3xbf16", "umma_6xbf16")   # kind::f16 MMAs
     tf32_peak = peaks["bf16_sustained"] if is_bf16 else peaks["bf16_sustained"] / 2.0
-    issued = {"auto": 6, "umma_6xbf16": 6, "umma_3xbf16": 3, "umma_3xtf32": 3, "umma_tf32": 1}.get(args.engine, 1)
+    issued = {"auto": 3, "umma_3xf16": 3, "umma_6xbf16": 6, "umma_3xbf16": 3, "umma_3xtf32": 3,
+              "umma_tf32": 1}.get(args.engine, 1)
     tica_ach = flops_tica / tica_s / 1e12
     roof_k2 = {"kernel": "kcenters_pass_kernel", "bound": "hbm", "achieved": hbm_ach,
                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
@@ -399,7 +400,7 @@ def run_ours(args):
                "share_of_step": kc_s / (ms_per_step / 1e3)}
     roof_k1 = {"kernel": "tica_accumulate(%s)" % args.engine, "bound": "tensor", "achieved": tica_ach,
                "peak": tf32_peak, "unit": "TFLOP/s", "frac": tica_ach / tf32_peak, "traffic": None,
-               "peak_source": peaks["source"] + ("; sustained bf16" if is_bf16 else
+               "peak_source": peaks["source"] + ("; sustained bf16 (kind::f16 MMAs run at the same rate)" if is_bf16 else
                                                    "; TF32 dense taken as 1/2 of the measured sustained bf16"),
                "algorithmic_flops_per_launch": flops_tica, "ms_per_launch": tica_s * 1e3,
                "issued_mma_products": issued, "issued_frac": issued * tica_ach / tf32_peak,
@@ -410,7 +411,8 @@ def run_ours(args):
         "metric": "frames/sec tICA fit + KCenters assign", "value": value, "unit": "frames/s",
         "n_gpus": ws, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": {"auto": "f32 in; bf16x6 split tensor-core products (~2^-24), fp32 TMEM slabs -> f64 (tICA); f64 distances (KCenters)",
+        "dtype": {"auto": "f32 in; fp16x3 split tensor-core products of the scaled frames (~2^-22), fp32 TMEM slabs -> f64 (tICA); f64 distances (KCenters)",
+                  "umma_3xf16": "f32 in; fp16x3 split tensor-core products (~2^-22), fp32 TMEM slabs -> f64; f64 distances",
                   "umma_6xbf16": "f32 in; bf16x6 split tensor-core products, fp32 TMEM slabs -> f64; f64 distances",
                   "umma_3xbf16": "f32 in; bf16x3 split tensor-core products (~2^-16), fp32 TMEM slabs -> f64; f64 distances",
                   "umma_3xtf32": "f32 in; tf32x3 split tensor-core products (~2^-21), fp32 TMEM slabs -> f64; f64 distances",

@@ -78,12 +78,15 @@ size_t msmb200_tica_acc_len(int n_features);
 
 /* Precision / engine selector for K1. */
 enum {
-    MSMB200_TICA_AUTO = 0,      /* tcgen05 6xBF16 when the shape allows, else SIMT f64 */
+    MSMB200_TICA_AUTO = 0,      /* tcgen05 3xF16 when the shape allows, else SIMT f64 */
     MSMB200_TICA_SIMT_F64 = 1,  /* CUDA-core float64, any D, any lag, f32 or f64 input  */
     MSMB200_TICA_UMMA_3XTF32 = 2, /* tcgen05.mma kind::tf32, error-compensated 3-term split */
     MSMB200_TICA_UMMA_TF32 = 3, /* tcgen05.mma kind::tf32, single pass                   */
     MSMB200_TICA_UMMA_3XBF16 = 4, /* kind::f16 bf16 h/m split, 3 products (~2^-16, K = 16) */
-    MSMB200_TICA_UMMA_6XBF16 = 5  /* bf16 h/m/l split, 6 products (~2^-24)                  */
+    MSMB200_TICA_UMMA_6XBF16 = 5, /* bf16 h/m/l split, 6 products (~2^-24)                  */
+    MSMB200_TICA_UMMA_3XF16 = 6   /* kind::f16 fp16 h/l split of the per-feature power-of-two
+                                     scaled frame, 3 products (~2^-22, K = 16); a value outside
+                                     fp16's range reruns the call as 6XBF16 on the stream   */
 };
 
 /* Bytes of DEVICE scratch the call may need for (n_features, engine). */

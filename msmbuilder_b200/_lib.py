@@ -16,10 +16,11 @@ VECTOR_METRICS = ("euclidean", "sqeuclidean", "cityblock", "chebyshev",
                   "canberra", "braycurtis", "hamming", "jaccard")
 F32, F64 = 0, 1
 TICA_AUTO, TICA_SIMT_F64, TICA_UMMA_3XTF32, TICA_UMMA_TF32 = 0, 1, 2, 3
-TICA_UMMA_3XBF16, TICA_UMMA_6XBF16 = 4, 5
+TICA_UMMA_3XBF16, TICA_UMMA_6XBF16, TICA_UMMA_3XF16 = 4, 5, 6
 ENGINES = {"auto": TICA_AUTO, "simt_f64": TICA_SIMT_F64,
            "umma_3xtf32": TICA_UMMA_3XTF32, "umma_tf32": TICA_UMMA_TF32,
-           "umma_3xbf16": TICA_UMMA_3XBF16, "umma_6xbf16": TICA_UMMA_6XBF16}
+           "umma_3xbf16": TICA_UMMA_3XBF16, "umma_6xbf16": TICA_UMMA_6XBF16,
+           "umma_3xf16": TICA_UMMA_3XF16}
 
 # name -> (restype, argtypes); kept in one table so tests can check that the
 # library exports every symbol the header declares.

@@ -56,6 +56,36 @@ __device__ __forceinline__ double group_combine(double v, int G)
     return v;
 }
 
+// R sums (maxima) over the G lanes of a group at once.  While the lanes fold (xor offsets
+// G/2, G/4, ...) they also split the R values between them, so level l moves R/2^l doubles
+// instead of R; after log2(R) levels every lane carries ONE value, finished by a plain
+// butterfly.  Lane `lig` returns the total of value j = sum over the first log2(R) levels of
+// (bit `off` of lig set ? m/2 : 0); the G/R lanes that differ only in lower bits all hold it.
+// The additions pair up exactly like group_combine's, so the results are bit-identical to it.
+// Needs R a power of two, G >= R.
+template <bool IS_MAX, int R>
+__device__ __forceinline__ double group_reduce_split(double (&v)[R], int G, int lig)
+{
+    int off = G >> 1;
+#pragma unroll
+    for (int m = R; m > 1; m >>= 1, off >>= 1) {
+        const bool up = (lig & off) != 0;
+#pragma unroll
+        for (int i = 0; i < m / 2; ++i) {
+            const double send = up ? v[i] : v[i + m / 2];
+            const double keep = up ? v[i + m / 2] : v[i];
+            const double o = __shfl_xor_sync(0xffffffffu, send, off);
+            v[i] = IS_MAX ? fmax(keep, o) : keep + o;
+        }
+    }
+    double r = v[0];
+    for (; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, r, off);
+        r = IS_MAX ? fmax(r, o) : r + o;
+    }
+    return r;
+}
+
 // (value, index) arg-max with lowest-index tie-break == np.argmax first-max.
 struct ArgMax {
     double v;

@@ -151,9 +151,11 @@ kcenters_pass_kernel(const T *__restrict__ X, long long n, int d, long long ld,
 // K2 fast path (float32 frames, 16-byte vector loads, d/4 == ITERS * G):
 // each sub-warp group streams R frames per iteration with all R*ITERS 16-byte
 // loads issued before the first use (bytes in flight per warp: R * 4 * d), the
-// centre lives in registers, the R float64 reductions are interleaved, and lane
-// j of a group owns the running-minimum update of frame j (its distances[] value
-// is prefetched before the arithmetic).  Same arithmetic as the generic kernel.
+// centre lives in registers, the R float64 group sums share one split reduction
+// (group_reduce_split: 6 instead of 20 shuffle rounds at R = 4, G = 32), each frame's
+// running-minimum update belongs to one lane (its distances[] value is prefetched
+// before the arithmetic) and only that lane's sqrt is taken.  Same arithmetic,
+// bit for bit, as the generic kernel.
 // ---------------------------------------------------------------------------
 template <int METRIC, int ITERS, int R>
 __global__ void __launch_bounds__(kThreads)
@@ -179,25 +181,42 @@ kcenters_pass_fast_kernel(const float *__restrict__ X, long long n, int d, long 
 
     ArgMax best{-INFINITY, 0x7fffffffffffffffLL};
 
-    for (long long it = 0; (it * R) * NG + warp_gid0 < n; ++it) {
+    // frame of an iteration whose sum ends up in this lane (group_reduce_split), and whether
+    // this lane is the one of the G/R holders that does the running-minimum update
+    int jsel = 0;
+    {
+        int off = G >> 1;
+#pragma unroll
+        for (int m = R; m > 1; m >>= 1, off >>= 1)
+            if (lane_in_group & off) jsel += m >> 1;
+    }
+    const bool owner = (lane_in_group & (G / R - 1)) == 0;
+
+    // one iteration = R frames per group; FULL iterations (every row of every group of the
+    // warp in range) skip the row clamps and validity tests
+    const long long stride_j = NG * ld4;                        // float4 units from frame j to j + 1
+    const float4 *pfull = X4 + gid * ld4 + lane_in_group;       // frame 0 of the current full iteration
+    auto iteration = [&](long long it, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         long long rr[R];
         float4 x[R][ITERS];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             rr[j] = (it * R + j) * NG + gid;
-            const long long rc = rr[j] < n ? rr[j] : n - 1;
-            const float4 *p = X4 + rc * ld4 + lane_in_group;
+            const long long rc = (FULL || rr[j] < n) ? rr[j] : n - 1;
+            // full iterations walk a running pointer (adds only, no 64-bit multiplies)
+            const float4 *p = FULL ? pfull + j * stride_j : X4 + rc * ld4 + lane_in_group;
 #pragma unroll
             for (int i = 0; i < ITERS; ++i) x[j][i] = ldg_stream(p + i * G);
         }
         long long myrow = -1;
 #pragma unroll
         for (int j = 0; j < R; ++j)
-            if (lane_in_group == j && rr[j] < n) myrow = rr[j];
+            if (owner && jsel == j && (FULL || rr[j] < n)) myrow = rr[j];
         double cur = INFINITY;
         if (myrow >= 0) cur = __ldcg(dist + myrow);
 
-        double dv[R];
+        double va[R], vb[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             double a = 0.0, b = 0.0;
@@ -208,14 +227,15 @@ kcenters_pass_fast_kernel(const float *__restrict__ X, long long n, int d, long 
                 M::acc(a, b, x[j][i].z, c[i].z);
                 M::acc(a, b, x[j][i].w, c[i].w);
             }
-            a = group_combine<M::kIsMax>(a, G);
-            if (M::kTwoAcc) b = group_combine<false>(b, G);
-            dv[j] = M::fin(a, b, d);
+            va[j] = a;
+            vb[j] = b;
         }
-        double mine = 0.0;
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-            if (lane_in_group == j) mine = dv[j];
+        // R group sums for the price of ~one: the lanes split the frames while they reduce
+        // (same addition tree as group_combine, so the values are bit-identical to it), then
+        // ONE finishing step (the sqrt) per lane instead of R
+        const double ra = group_reduce_split<M::kIsMax, R>(va, G, lane_in_group);
+        const double rb = M::kTwoAcc ? group_reduce_split<false, R>(vb, G, lane_in_group) : 0.0;
+        const double mine = M::fin(ra, rb, d);
         if (myrow >= 0) {
             if (mine < cur) {            // strict: kcenters.py:93
                 cur = mine;
@@ -227,7 +247,15 @@ kcenters_pass_fast_kernel(const float *__restrict__ X, long long n, int d, long 
                 best.i = myrow;
             }
         }
+    };
+    // rows of iteration `it` span [(it*R)*NG + warp_gid0, (it*R + R-1)*NG + warp_gid0 + 32/G)
+    long long it = 0;
+    for (; (it * R + R - 1) * NG + warp_gid0 + (32 / G) <= n; ++it) {
+        iteration(it, std::true_type());
+        pfull += R * stride_j;
     }
+    for (; (it * R) * NG + warp_gid0 < n; ++it)
+        iteration(it, std::false_type());
     pass_publish<float>(best, X, n, d, ld, row_offset, block_cands, counter, out);
 }
 

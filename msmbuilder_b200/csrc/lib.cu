@@ -109,18 +109,19 @@ extern "C" int msmb200_tica_accumulate(const void *const *seq_ptrs, const int64_
     cudaStream_t st = (cudaStream_t)stream;
     const bool umma_ok = tica_umma_supported(D, ld, dtype, lag);
     if (engine == MSMB200_TICA_AUTO)   // the 256-wide tensor-core tiles beat the float64 kernel from D = 64 up
-        engine = (umma_ok && D >= 64) ? MSMB200_TICA_UMMA_6XBF16 : MSMB200_TICA_SIMT_F64;
+        engine = (umma_ok && D >= 64) ? MSMB200_TICA_UMMA_3XF16 : MSMB200_TICA_SIMT_F64;
     if (engine == MSMB200_TICA_SIMT_F64)
         return tica_simt_accumulate(seq_ptrs, seq_rows, n_seq, D, ld, dtype, lag, acc, st);
     if (engine == MSMB200_TICA_UMMA_3XTF32 || engine == MSMB200_TICA_UMMA_TF32 ||
-        engine == MSMB200_TICA_UMMA_3XBF16 || engine == MSMB200_TICA_UMMA_6XBF16) {
+        engine == MSMB200_TICA_UMMA_3XBF16 || engine == MSMB200_TICA_UMMA_6XBF16 ||
+        engine == MSMB200_TICA_UMMA_3XF16) {
         if (!umma_ok) {
             set_error("tcgen05 engine does not take D=%d ld=%lld dtype=%d lag=%d", D,
                       (long long)ld, dtype, lag);
             return MSMB200_E_UNSUPPORTED;
         }
         const int mode = engine == MSMB200_TICA_UMMA_3XTF32 ? 3 : engine == MSMB200_TICA_UMMA_TF32 ? 1
-                         : engine == MSMB200_TICA_UMMA_3XBF16 ? 13 : 16;
+                         : engine == MSMB200_TICA_UMMA_3XBF16 ? 13 : engine == MSMB200_TICA_UMMA_3XF16 ? 23 : 16;
         return tica_umma_accumulate(seq_ptrs, seq_rows, n_seq, D, ld, lag, mode, acc, workspace,
                                     workspace_bytes, st);
     }

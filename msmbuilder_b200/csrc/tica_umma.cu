@@ -69,6 +69,9 @@ struct UmmaParams {
     int passes;                   // tf32: 3 = hi/lo split, 1 = plain; bf16: 3 = h/m products, 6 = h/m/l
     int collector;                // reuse the A operand through the collector buffer
     const float *shift;           // [D]
+    const float *scale;           // [D] power-of-two per-feature scale (f16 engine), else unused
+    int *overflow;                // f16 engine: set to 1 when a scaled value leaves fp16's range
+    const int *run_if;            // if non-NULL the kernel only runs when *run_if != 0 (rescue launch)
     double *partials;             // [n_pairs][2][col][row]  (C_tau', C_00'), column-major so a
                                   // warp (32 rows) touches 256 contiguous bytes per column
     double *sums;                 // [2][D]  (S_0', S_tau')  atomically accumulated
@@ -141,13 +144,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
     return d;
 }
 // (tf32 x tf32 | bf16 x bf16) -> f32, K-major A and B, M = 256 (pair), N = 256
-template <bool BF16>
+constexpr int UM_KIND_TF32 = 0, UM_KIND_BF16 = 1, UM_KIND_F16 = 2;
+template <int KIND>
 __device__ __forceinline__ uint32_t umma_idesc()
 {
+    constexpr uint32_t fmt = KIND == UM_KIND_TF32 ? 2u : KIND == UM_KIND_BF16 ? 1u : 0u;
     uint32_t d = 0;
     d |= 1u << 4;                     // D format F32
-    d |= (BF16 ? 1u : 2u) << 7;       // A format: BF16 = 1, TF32 = 2
-    d |= (BF16 ? 1u : 2u) << 10;      // B format
+    d |= fmt << 7;                    // A format: kind::tf32 TF32 = 2; kind::f16 BF16 = 1, F16 = 0
+    d |= fmt << 10;                   // B format
     d |= (uint32_t)(256 >> 3) << 17;  // N
     d |= (uint32_t)(256 >> 4) << 24;  // M
     return d;
@@ -190,6 +195,14 @@ __device__ __forceinline__ float bf16_rn(float x)
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
     return (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xFFFF0000u);
+}
+
+// two floats -> packed fp16 pair, round to nearest even (a in the low half = the earlier frame)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 
 #define UM_TMEM_LD32(v, taddr) asm volatile( \
@@ -261,10 +274,14 @@ __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, 
 }
 
 // ---------------------------------------------------------------------------------------
-template <bool BF16>
+template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 tica_umma_kernel(const UmmaParams P)
 {
+    constexpr bool BF16 = KIND != UM_KIND_TF32;      // 2-byte operands, K = 16 (kind::f16)
+    constexpr bool F16 = KIND == UM_KIND_F16;
+    // rescue launch (the f16 engine's fp16 range check tripped): uniform over the grid
+    if (P.run_if != nullptr && *reinterpret_cast<const volatile int *>(P.run_if) == 0) return;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1 KB-aligned operand ring, control block behind it
     unsigned char *ring = reinterpret_cast<unsigned char *>(
@@ -344,7 +361,7 @@ tica_umma_kernel(const UmmaParams P)
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA, one lane) =============
         if (cta_rank == 0 && lane == 0 && my_tiles > 0) {
-            const uint32_t idesc = umma_idesc<BF16>();
+            const uint32_t idesc = umma_idesc<KIND>();
             const uint32_t ring_addr = smem_u32(op_ring);
             const bool dbg_on = P.dbg != nullptr && pair == 0;
             long long d_wait_conv = 0, d_wait_acc = 0;
@@ -401,6 +418,8 @@ tica_umma_kernel(const UmmaParams P)
                     // bf16 components h, m, l of A (unlagged) and B (lagged), 8 KB each:
                     // x ~ h + m (+ l);  3 products: hh' + hm' + mh' (~2^-16 relative, unbiased);
                     // 6 products add mm' + hl' + lh' (~2^-24).  K = 16 frames per instruction.
+                    // fp16 engine: the same three products on components h, l of the SCALED
+                    // value (11-bit significands: ~2^-22), l sits in the m slot.
                     const uint32_t A0 = stage_addr, B0 = stage_addr + 3 * UM_BF_TILE_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < UM_KT / 16; ++ks) {
@@ -410,6 +429,17 @@ tica_umma_kernel(const UmmaParams P)
                                        dAl = umma_desc(A0 + 2 * UM_BF_TILE_BYTES + off);
                         const uint64_t dBh = umma_desc(B0 + off), dBm = umma_desc(B0 + UM_BF_TILE_BYTES + off),
                                        dBl = umma_desc(B0 + 2 * UM_BF_TILE_BYTES + off);
+                        if (P.passes == 3 && P.collector) {
+                            // A = h feeds four MMAs, A = m (l for fp16) two: 2 instead of 6 A-tile
+                            // fetches from shared memory per K step
+                            UMMA_KIND_PAIR("f16", ".collector::a::fill", tmem, dAh, dBh, idesc, acc);
+                            UMMA_KIND_PAIR("f16", ".collector::a::use", tmem, dAh, dBm, idesc, 1u);
+                            UMMA_KIND_PAIR("f16", ".collector::a::use", tmem + 256, dAh, dAh, idesc, acc);
+                            UMMA_KIND_PAIR("f16", ".collector::a::lastuse", tmem + 256, dAh, dAm, idesc, 1u);
+                            UMMA_KIND_PAIR("f16", ".collector::a::fill", tmem, dAm, dBh, idesc, 1u);
+                            UMMA_KIND_PAIR("f16", ".collector::a::lastuse", tmem + 256, dAm, dAh, idesc, 1u);
+                            continue;
+                        }
                         umma_bf16_pair(tmem, dAh, dBh, idesc, acc);                // C_tau
                         umma_bf16_pair(tmem, dAh, dBm, idesc, 1u);
                         umma_bf16_pair(tmem, dAm, dBh, idesc, 1u);
@@ -451,6 +481,8 @@ tica_umma_kernel(const UmmaParams P)
         const int f_local = 32 * fb + lane;              // feature inside the CTA (0..127)
         const int chunk = lane >> 2, within = (lane & 3) * 4;
         const float sh = P.shift[UM_F * cta_rank + f_local];
+        const float sc = F16 ? P.scale[UM_F * cta_rank + f_local] : 1.f;
+        float amax = 0.f;                                // largest scaled magnitude seen (fp16 range check)
         const bool split = P.passes == 3;
         double sumA = 0.0, sumB = 0.0;                   // column sums of feature 128*rank + f_local
         int stage = 0;
@@ -519,6 +551,38 @@ tica_umma_kernel(const UmmaParams P)
                             *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
                         }
                     }
+                } else if constexpr (F16) {
+                    // fp16 h/l split of the scaled value (x - shift) * 2^e: h = the value rounded
+                    // to 11 significant bits (two integer ops; exact in fp16's normal range),
+                    // l = fp16(value - h).  Below 2^-14 both roundings are absolute, <= 2^-25.
+                    unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
+                    unsigned char *l_buf = h_buf + UM_BF_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < UM_KT / 16; ++k) {
+                        const int kb = 2 * k + rb_par;          // block of 8 frames
+                        float h[8], l[8];
+                        float s8 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 8 * kb + i;
+                            const float v = *reinterpret_cast<const float *>(
+                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                            const float u = (r < valid) ? v - sh : 0.f;
+                            s8 += u;
+                            const float as = u * sc;
+                            amax = fmaxf(amax, fabsf(as));
+                            h[i] = tf32_rn(as);
+                            l[i] = as - h[i];                 // exact in fp32
+                        }
+                        if (op == 0) tsA += s8; else tsB += s8;
+                        uint4 hw, lw;
+                        hw.x = pack_f16(h[0], h[1]); hw.y = pack_f16(h[2], h[3]);
+                        hw.z = pack_f16(h[4], h[5]); hw.w = pack_f16(h[6], h[7]);
+                        lw.x = pack_f16(l[0], l[1]); lw.y = pack_f16(l[2], l[3]);
+                        lw.z = pack_f16(l[4], l[5]); lw.w = pack_f16(l[6], l[7]);
+                        *reinterpret_cast<uint4 *>(h_buf + kb * UM_LBO) = hw;
+                        *reinterpret_cast<uint4 *>(l_buf + kb * UM_LBO) = lw;
+                    }
                 } else {
                     // 16-byte chunk = 8 consecutive frames of this thread's feature
                     unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
@@ -580,6 +644,8 @@ tica_umma_kernel(const UmmaParams P)
             atomicAdd(&P.sums[f], sumA);
             atomicAdd(&P.sums[UM_D + f], sumB);
         }
+        // fp16 tops out at 65504: anything near it (or Inf) sends the whole call to the bf16 engine
+        if (F16 && !(amax < 60000.f)) atomicOr(P.overflow, 1);
     } else if (warp >= 4 + UM_CONV_WARPS) {
         // ================================ epilogue (128 threads, both CTAs) =============
         const int ew = warp - (4 + UM_CONV_WARPS);                       // == warp % 4: TMEM lane quarter
@@ -610,9 +676,13 @@ tica_umma_kernel(const UmmaParams P)
 }
 
 // ---------------------------------------------------------------------------------------
-// provisional per-feature mean of the first rows of the first sequence -> float32 shift
+// provisional per-feature mean of the first rows of the first sequence -> float32 shift, and
+// (fp16 engine) a power-of-two scale 2^-e that brings the largest centred magnitude m of those
+// rows into [1, 2): fp16 then has 2^15 of headroom above the sample and 11-bit components of
+// everything down to 2^-14 of it.  m is floored at |mean| / 256 so that a feature which is
+// (nearly) constant in the sample cannot be blown up into fp16's ceiling by a later excursion.
 __global__ void tica_shift_kernel(const float *__restrict__ X, long long n, long long ld, int D,
-                                  float *__restrict__ shift)
+                                  float *__restrict__ shift, float *__restrict__ scale)
 {
     const long long rows = n < 512 ? n : 512;
     // shift[] is padded to UM_D entries; features >= D do not exist (TMA zero-fills them)
@@ -620,8 +690,27 @@ __global__ void tica_shift_kernel(const float *__restrict__ X, long long n, long
         double s = 0.0;
         if (c < D)
             for (long long r = 0; r < rows; ++r) s += (double)X[r * ld + c];
-        shift[c] = (float)(s / (double)rows);
+        const float sh = (float)(s / (double)rows);
+        shift[c] = sh;
+        float m = 0.f;
+        if (c < D)
+            for (long long r = 0; r < rows; ++r) m = fmaxf(m, fabsf(X[r * ld + c] - sh));
+        m = fmaxf(m, fabsf(sh) * (1.f / 256.f));
+        int e = 0;
+        if (m > 0.f && m < INFINITY) e = ilogbf(m);
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        scale[c] = ldexpf(1.f, -e);
     }
+}
+
+// rescue path of the fp16 engine: when the range check tripped, forget what that launch wrote
+__global__ void tica_umma_rescue_clear_kernel(const int *__restrict__ flag, double *__restrict__ buf,
+                                              size_t n)
+{
+    if (*flag == 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        buf[i] = 0.0;
 }
 
 struct EdgeSeq {
@@ -709,6 +798,8 @@ __global__ void __launch_bounds__(256)
 tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
                           const double *__restrict__ sums, const double *__restrict__ E,
                           const double *__restrict__ es, const float *__restrict__ shift,
+                          const float *__restrict__ scale /* NULL: partials are unscaled */,
+                          const int *__restrict__ rescued /* != 0: the bf16 rescue wrote them */,
                           double n_pairs_total /* sum_s (n_s - lag) */, double n_obs, double n_seq,
                           int Dr, double *__restrict__ acc)
 {
@@ -724,6 +815,12 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
     for (int p = 0; p < n_pairs; ++p) {
         ctau += partials[(size_t)p * 2 * DD + tidx];
         c00 += partials[(size_t)p * 2 * DD + DD + tidx];
+    }
+    if (scale != nullptr && *rescued == 0) {
+        // fp16 engine: the tensor cores summed (s_i x'_i)(s_j x'_j); powers of two, exact to undo
+        const double inv = 1.0 / ((double)scale[i] * (double)scale[j]);
+        ctau *= inv;
+        c00 *= inv;
     }
     ctau += E[pidx];
     c00 += E[DD + pidx];
@@ -895,11 +992,13 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
     size_t woff = 0;
     const size_t w_shift = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
+    const size_t w_scale = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
+    const size_t w_flag = woff; woff = align_up(woff + sizeof(int), 256);       // zeroed with the rest
     const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * 2 * UM_D, 256);
     const size_t w_E = woff; woff = align_up(woff + sizeof(double) * 4 * DD, 256);
     const size_t w_es = woff; woff = align_up(woff + sizeof(double) * 3 * UM_D, 256);
     const size_t w_part = woff; woff += sizeof(double) * 2 * DD * n_pairs;
-    MSMB_CUDA(cudaMemsetAsync(wsb + w_sums, 0, woff - w_sums, st));
+    MSMB_CUDA(cudaMemsetAsync(wsb + w_flag, 0, woff - w_flag, st));
 
     std::vector<CUtensorMap> mA(n_seq), mB(n_seq);
     for (int s = 0; s < n_seq; ++s) { mA[s] = maps[2 * (size_t)s]; mB[s] = maps[2 * (size_t)s + 1]; }
@@ -911,7 +1010,9 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     MSMB_CUDA(cudaStreamSynchronize(st));    // host vectors are pageable: keep them alive until copied
 
     float *d_shift = reinterpret_cast<float *>(wsb + w_shift);
-    tica_shift_kernel<<<1, 256, 0, st>>>(seqs[0].base, seqs[0].n, ld, D, d_shift);
+    float *d_scale = reinterpret_cast<float *>(wsb + w_scale);
+    int *d_flag = reinterpret_cast<int *>(wsb + w_flag);
+    tica_shift_kernel<<<1, 256, 0, st>>>(seqs[0].base, seqs[0].n, ld, D, d_shift, d_scale);
     MSMB_LAUNCH_CHECK();
 
     UmmaParams P;
@@ -922,14 +1023,18 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.n_seq = n_seq;
     P.n_tiles = (int)tiles;
     P.n_pairs = n_pairs;
-    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16 (see lib.cu)
+    const bool f16 = passes == 23;                  // 23 = 3xF16 (see lib.cu)
+    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16: 2-byte operands, K = 16
     // bf16 MMAs cover 16 frames per accumulate step (tf32: 8), so twice the frames per slab
     // carry the same truncation bias
     P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", bf16 ? 2 * UM_SLAB_TILES_DEFAULT : UM_SLAB_TILES_DEFAULT);
     if (P.slab_tiles < 1) P.slab_tiles = 1;
-    P.passes = bf16 ? passes - 10 : passes;
+    P.passes = f16 ? 3 : bf16 ? passes - 10 : passes;
     P.collector = env_int("MSMB200_UMMA_COLLECTOR", 0);
     P.shift = d_shift;
+    P.scale = d_scale;
+    P.overflow = d_flag;
+    P.run_if = nullptr;
     P.partials = reinterpret_cast<double *>(wsb + w_part);
     P.sums = reinterpret_cast<double *>(wsb + w_sums);
     P.dbg = nullptr;
@@ -944,14 +1049,34 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + sizeof(UmmaSmem) + 1024;
         static bool attr_set = false;
         if (!attr_set) {
-            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<false>,
+            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_TF32>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<true>,
+            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_BF16>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_F16>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
-        if (bf16) tica_umma_kernel<true><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
-        else tica_umma_kernel<false><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+        if (f16) {
+            tica_umma_kernel<UM_KIND_F16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+            MSMB_LAUNCH_CHECK();
+            // Range rescue, all on the stream (no host round trip): if a scaled value left fp16's
+            // range the two launches below wipe the partials and redo the call with the 6xBF16
+            // engine (full fp32 exponent range); otherwise both exit at once.
+            tica_umma_rescue_clear_kernel<<<2, 256, 0, st>>>(
+                d_flag, reinterpret_cast<double *>(wsb + w_sums), (w_E - w_sums) / sizeof(double));
+            MSMB_LAUNCH_CHECK();
+            tica_umma_rescue_clear_kernel<<<4 * sm_count(), 256, 0, st>>>(
+                d_flag, P.partials, 2 * DD * (size_t)n_pairs);
+            MSMB_LAUNCH_CHECK();
+            UmmaParams Q = P;
+            Q.passes = 6;
+            Q.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", 2 * UM_SLAB_TILES_DEFAULT);
+            Q.run_if = d_flag;
+            Q.dbg = nullptr;
+            tica_umma_kernel<UM_KIND_BF16><<<2 * n_pairs, UM_THREADS, smem, st>>>(Q);
+        } else if (bf16) tica_umma_kernel<UM_KIND_BF16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+        else tica_umma_kernel<UM_KIND_TF32><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
         MSMB_LAUNCH_CHECK();
     }
     {
@@ -963,8 +1088,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     }
     tica_umma_finalize_kernel<<<(unsigned)(((size_t)D * D + 255) / 256), 256, 0, st>>>(
         P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(wsb + w_E),
-        reinterpret_cast<const double *>(wsb + w_es), d_shift, n_pairs_total, n_obs,
-        (double)n_seq, D, acc);
+        reinterpret_cast<const double *>(wsb + w_es), d_shift, f16 ? d_scale : nullptr, d_flag,
+        n_pairs_total, n_obs, (double)n_seq, D, acc);
     MSMB_LAUNCH_CHECK();
     if (d_dbg) {
         long long h[16];

@@ -58,11 +58,13 @@ class tICA(BaseEstimator, TransformerMixin):
         Scale the projection by the eigenvalues (kinetic map).
     commute_mapping : bool, default=False
         Scale the projection by regularised timescales (commute map).
-    engine : {'auto', 'simt_f64', 'umma_3xtf32', 'umma_tf32', 'umma_3xbf16', 'umma_6xbf16'}, default='auto'
+    engine : {'auto', 'simt_f64', 'umma_3xf16', 'umma_6xbf16', 'umma_3xbf16', 'umma_3xtf32', 'umma_tf32'}, default='auto'
         Which device kernel accumulates the covariance matrices.  'auto' uses the
-        tcgen05 tensor-core kernel with the error-compensated 6-product bf16 split
-        (~2^-24 per product) when the shape allows it and the float64 CUDA-core
-        kernel otherwise; 'umma_3xbf16' is the fastest (~2^-16 per product, unbiased).
+        tcgen05 tensor-core kernel with the error-compensated 3-product fp16 split
+        of the per-feature power-of-two scaled frames (~2^-22 per product; a value
+        outside fp16's range makes the call redo itself as 'umma_6xbf16', ~2^-24,
+        full float32 range) when the shape allows it and the float64 CUDA-core
+        kernel otherwise; 'umma_3xbf16' is ~2^-16 per product, unbiased.
 
     Attributes
     ----------

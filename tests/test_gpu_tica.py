@@ -205,6 +205,54 @@ def test_umma_bf16_engines(engine, mom_tol):
     np.testing.assert_allclose(b.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)
 
 
+def test_umma_f16_engine_matches_f64():
+    # fp16 h/l split of the power-of-two scaled frames: 3 products, ~2^-22 per element
+    lens = [4001, 130, 64, 11, 15, 777, 32, 2048]
+    seqs = [s[:n] for s, n in zip(ar1_numpy(len(lens), 4100, 256, seed=24), lens)]
+    a, b = _umma_vs_simt(seqs, 10, engine="umma_3xf16")
+    assert a.n_observations_ == b.n_observations_ and a.n_sequences_ == b.n_sequences_
+    _assert_moments_close(b, a, 5e-6)
+    np.testing.assert_allclose(b.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)
+    np.testing.assert_allclose(b.means_, a.means_, rtol=0, atol=1e-6)
+
+
+def test_umma_f16_engine_feature_scales():
+    # features spanning 1e-6 ... 1e6 (and an offset 1000x the spread): the per-feature scale
+    # keeps every one of them inside fp16's range with 11-bit components
+    rng = np.random.RandomState(3)
+    scales = (10.0 ** rng.uniform(-6, 6, size=256)).astype(np.float32)
+    offs = (scales * rng.uniform(-1000, 1000, size=256)).astype(np.float32)
+    offs[::3] = 0
+    seqs = [(s * scales + offs).astype(np.float32) for s in ar1_numpy(3, 3000, 256, seed=25)]
+    a, b = _umma_vs_simt(seqs, 10, engine="umma_3xf16")
+    # compare correlation-normalised moments: the features differ by 24 orders of magnitude
+    sd = np.sqrt(np.diag(a.covariance_))
+    np.testing.assert_allclose(b.covariance_ / np.outer(sd, sd), a.covariance_ / np.outer(sd, sd),
+                               rtol=0, atol=2e-5)
+    np.testing.assert_allclose(b.offset_correlation_ / np.outer(sd, sd),
+                               a.offset_correlation_ / np.outer(sd, sd), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(b.means_, a.means_, rtol=1e-6, atol=0)
+
+
+def test_umma_f16_engine_range_rescue():
+    # a later excursion 10^7 times the spread of the first 512 frames leaves fp16's range: the
+    # call must redo itself with the bf16 engine on the stream and still match float64
+    seqs = ar1_numpy(2, 4000, 256, seed=26)
+    seqs[1] = seqs[1].copy()
+    seqs[1][3000:3100, 5] += 3.0e7
+    seqs[1][3500, 200] = -8.0e6
+    a, b = _umma_vs_simt(seqs, 10, engine="umma_3xf16")
+    c = _umma_vs_simt(seqs, 10, engine="umma_6xbf16")[1]
+    assert a.n_observations_ == b.n_observations_
+    # the rescue IS the 6xBF16 engine: same accumulators (up to the order of the column-sum atomics)
+    np.testing.assert_allclose(b._outer_0_to_T_lagged, c._outer_0_to_T_lagged, rtol=1e-12)
+    np.testing.assert_allclose(b._outer_0_to_TminusTau, c._outer_0_to_TminusTau, rtol=1e-12)
+    _assert_moments_close(b, a, 5e-6)
+    # and the next call on the same estimator is clean again (flag is per call)
+    d = _umma_vs_simt(seqs[:1], 10, engine="umma_3xf16")
+    _assert_moments_close(d[1], d[0], 5e-6)
+
+
 @pytest.mark.parametrize("D", [64, 96, 128, 224])
 def test_umma_narrow_feature_counts(D):
     # D = 32k < 256 rides the 256-wide tensor-core tiles (TMA zero-fills the missing feature blocks)
