@@ -1,40 +1,42 @@
-// tica_umma.cu -- K1 on Blackwell tensor cores: TMA-fed tcgen05.mma (kind::tf32,
-// cta_group::2) with TMEM accumulators.  sm_100a only.
+// tica_umma.cu -- K1 on Blackwell tensor cores: TMA-fed tcgen05.mma (cta_group::2, kind::f16 or
+// kind::tf32) with TMEM accumulators.  sm_100a only.
 //
-// What it computes (per call, for D = 256 float32 features):
-//   C_tau' = sum_t x'_t x'_{t+lag}^T       C_00' = sum_t x'_t x'_t^T
-//   S_0'   = sum_t x'_t                    S_tau' = sum_t x'_{t+lag}
+// What it computes (per call, for D = 32k <= 256 float32 features):
+//   C_tau' = sum_t x'_t x'_{t+lag}^T       C_00' = sum_t x'_t x'_t^T        S_0' = sum_t x'_t
 // over the pair indices t of every sequence, where x' = fl32(x - shift) is the frame
 // re-centred by a provisional per-feature mean (covariances are shift invariant;
 // the raw moments of tica.py:417-422 are reconstructed exactly in float64 by
-// tica_umma_finalize).  The few pair indices that do not fill a 4-frame block and
-// the 2*lag head/tail frames that distinguish C_00 from C_tautau are handled in
-// float64 by tica_umma_edges.
+// tica_umma_finalize).  The 2*lag head/tail frames per sequence that distinguish C_00 from
+// C_tautau and S_0 from S_tau are handled in float64 by tica_umma_edges.
 //
 // Design:
 //  * A CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns a range of 32-frame tiles.
 //    CTA r holds features [128r, 128r+128): as the M-half of A (unlagged frames)
-//    and as the N-half of B (lagged frames) of one M=256 x N=256 x K=8 UMMA.
+//    and as the N-half of B (lagged frames) of one M=256 x N=256 UMMA.
 //  * TMEM per CTA: 128 lanes x 512 columns fp32 = C_tau rows (cols 0..255) and
 //    C_00 rows (cols 256..511) of this CTA's 128 features: all of TMEM.
-//  * Operands are K-major, no swizzle: [row-block of 4 frames][feature][4 frames],
-//    i.e. 16-byte chunks = 4 consecutive frames of one feature, core matrix =
-//    8 features x 4 frames (LBO = 2048 B between row-blocks, SBO = 128 B).
+//  * Operands are K-major, no swizzle: 16-byte chunks = 8 (2-byte kinds) or 4 (tf32) consecutive
+//    frames of one feature, core matrix = 8 features x 16 bytes (LBO = 2048 B between K chunks,
+//    SBO = 128 B between 8-feature groups).
 //  * TMA: one 3-D tensor map per sequence and operand, dims (32 feat, rows, D/32
 //    blocks), box (32, KT, 4), SWIZZLE_128B -> smem [block][frame][128 B]: full
-//    128-byte rows, so every 32-byte sector fetched is used (a first version with
-//    16-byte boxes was TMA-bound at ~4 useful B/cycle/SM, profiles/r1).  The converter
-//    warps read a 4-frame x 4-feature block per lane quad (the swizzle makes that
-//    bank-conflict free), transpose it with 4 shuffles and write the K-major hi/lo
-//    operand tiles.  The lagged operand has its own map whose base is shifted by lag
-//    rows, so any lag works and no operand needs an unaligned descriptor; rows past
-//    the last pair index are zero-filled by TMA.
-//  * Precision: x' = hi + lo with hi = tf32_rn(x'), lo = tf32_rn(x' - hi);
-//    products hi*hi + hi*lo + lo*hi (3 MMAs, ~2^-21 relative), fp32 accumulation in
-//    TMEM over a bounded slab of frames, then flushed into float64 partials.
-//  * Warp roles (512 threads): w0 TMA producer, w1 MMA issuer (leader CTA), w2 TMEM
-//    allocator, w4-11 converters (fp32 -> centred tf32 hi/lo, transpose, column sums),
-//    w12-15 epilogue (tcgen05.ld -> float64 read-modify-write of the pair's partials).
+//    128-byte rows, so every 32-byte sector fetched is used.  The lagged operand has its own
+//    map whose base is shifted by lag rows, so any lag works and no operand needs an unaligned
+//    descriptor; rows past the last pair index are zero-filled by TMA.
+//  * Engines (precision of the operand split; the products always accumulate in fp32 TMEM over a
+//    bounded slab of frames, then drain into float64 partials):
+//      3xF16  (default) x'*2^e = h + l in fp16 (per-feature power-of-two scale, 11-bit parts),
+//             products hh' + hl' + lh' (~2^-22); a value outside fp16's range is detected in the
+//             drain (Inf/NaN accumulators) and the call redoes itself as 6xBF16 on the stream;
+//      6xBF16 x' = h + m + l in bf16, six products (~2^-24, full fp32 range); 3xBF16 (~2^-16);
+//      3xTF32 / TF32: kind::tf32, K = 8.
+//  * Warp roles (640 threads): w0 TMA producer, w1 MMA issuer (leader CTA; warp-uniform loop,
+//    one elected lane issues), w2 TMEM allocator, w4-19 converters: a thread owns one feature and
+//    8 frames of a tile -- gathers them with conflict-free 4-byte shared loads (the transpose),
+//    centres/scales/splits them, stores K-major 16-byte chunks; the same 16 warps drain TMEM
+//    (tcgen05.ld -> red.global.add.f64 into the pair's partials) between slabs.
+//  * No FP64 instruction runs while the tensor pipe is busy: on B200 it stalls for hundreds of
+//    cycles (column sums are carried as float pairs and folded during the drain).
 #include "common.cuh"
 #include <cuda.h>
 #include <vector>
@@ -52,9 +54,10 @@ constexpr int UM_STAGE_BYTES = 4 * UM_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo (U
 constexpr int UM_BF_TILE_BYTES = UM_KT * UM_F * 2;  // bf16 component tile, 8 KB (6 of them fit a stage)
 constexpr int UM_LBO = UM_F * 16;               // 2048: next row-block
 constexpr int UM_SBO = 128;                     // next 8-feature group
-constexpr int UM_THREADS = 512;
-constexpr int UM_CONV_WARPS = 8;                // converter warps per CTA
-constexpr int UM_FLUSH_WARPS = 12;              // warps per CTA that drain TMEM (4 epilogue + 8 converter)
+constexpr int UM_CONV_WARPS = 16;               // converter warps per CTA (4 per scheduler: the
+                                                // conversion is latency bound with fewer)
+constexpr int UM_THREADS = 32 * (4 + UM_CONV_WARPS);   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4.. converters
+constexpr int UM_FLUSH_WARPS = UM_CONV_WARPS;   // the converters also drain TMEM (4 per lane quarter)
 constexpr int UM_SLAB_TILES_DEFAULT = 32;       // 1024 frames of fp32 TMEM accumulation per flush
 
 struct UmmaParams {
@@ -68,6 +71,10 @@ struct UmmaParams {
     int slab_tiles;
     int passes;                   // tf32: 3 = hi/lo split, 1 = plain; bf16: 3 = h/m products, 6 = h/m/l
     int collector;                // reuse the A operand through the collector buffer
+    int flush_red;                // drain with red.global.add.f64 instead of load + add + store
+    uint32_t h_add, h_mask;       // fp16 engine: integer rounding of the h component (significand width)
+    int dbg_mode;                 // MSMB200_UMMA_DBGMODE (timing experiments, wrong results): 1 = converters
+                                  // skip their loads/stores, 2 = flush skips its drain, 4 = one MMA per K step
     const float *shift;           // [D]
     const float *scale;           // [D] power-of-two per-feature scale (f16 engine), else unused
     int *overflow;                // f16 engine: set to 1 when a scaled value leaves fp16's range
@@ -157,29 +164,30 @@ __device__ __forceinline__ uint32_t umma_idesc()
     d |= (uint32_t)(256 >> 4) << 24;  // M
     return d;
 }
+// The MMA warp runs its loop warp-uniformly and predicates the tcgen05 instructions on ONE elected
+// lane (`mma_leader`, in scope at every use): under a divergent `if (lane == 0)` the compiler cannot
+// prove the descriptors uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall loop,
+// which serialised issue and execution (178 instead of 128 cycles per MMA, profiles/r1_k1_issue.txt).
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(pred));
+    return pred;
+}
 #define UMMA_KIND_PAIR(KIND, QUAL, tmem_d, da, db, idesc, accumulate) asm volatile( \
-    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" \
-    "tcgen05.mma.cta_group::2.kind::" KIND QUAL " [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" \
-    :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory")
+    "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t" \
+    "@q tcgen05.mma.cta_group::2.kind::" KIND QUAL " [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" \
+    :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(mma_leader) : "memory")
 #define UMMA_TF32_PAIR(QUAL, tmem_d, da, db, idesc, accumulate) \
     UMMA_KIND_PAIR("tf32", QUAL, tmem_d, da, db, idesc, accumulate)
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db,
-                                               uint32_t idesc, uint32_t accumulate)
-{
-    UMMA_KIND_PAIR("f16", "", tmem_d, da, db, idesc, accumulate);
-}
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db,
-                                               uint32_t idesc, uint32_t accumulate)
-{
-    UMMA_TF32_PAIR("", tmem_d, da, db, idesc, accumulate);
-}
+#define umma_bf16_pair(tmem_d, da, db, idesc, accumulate) UMMA_KIND_PAIR("f16", "", tmem_d, da, db, idesc, accumulate)
+#define umma_tf32_pair(tmem_d, da, db, idesc, accumulate) UMMA_TF32_PAIR("", tmem_d, da, db, idesc, accumulate)
 // arrive (when all prior MMAs of this thread have completed) on `bar` in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
-{
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
+#define umma_commit_pair(bar) asm volatile( \
+    "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t" \
+    "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" \
+    :: "r"(smem_u32(bar)), "h"((uint16_t)3), "r"(mma_leader) : "memory")
 // round-to-nearest (ties away) to tf32's 10-bit mantissa with two full-rate integer ops
 // (cvt.rna.tf32.f32 goes through the slow conversion pipe: 16k conversions per tile)
 __device__ __forceinline__ float tf32_rn(float x)
@@ -248,7 +256,7 @@ __device__ __forceinline__ void flush_prefetch(const UmmaParams &P, int pair, ui
 // dealt round-robin to the `nparts` warps that share a quarter.
 __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, int pair,
                                             uint32_t cta_rank, int quarter, int part, int nparts,
-                                            int lane)
+                                            int lane, uint32_t &absmax)
 {
     const int row = UM_F * cta_rank + quarter * 32 + lane;
     double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
@@ -259,16 +267,30 @@ __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, 
         // element (row, col) of matrix m lives at ((m*256 + col) * 256 + row); c0 runs over
         // [C_tau cols 0..255 | C_00 cols 0..255] = m*256 + col directly
         double *dst = pc + (size_t)c0 * UM_D;
-        double cur[16];
+        if (P.flush_red) {
+            // fire-and-forget reductions at L2: no read round trip, half the SM <-> L2 bytes
+            // (this warp is the only writer of these addresses, so the sums stay deterministic)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+            for (int j = 0; j < 32; ++j) {
+                absmax = max(absmax, v[j] & 0x7FFFFFFFu);      // Inf / NaN sort above every finite value
+                asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;"
+                             :: "l"(dst + (size_t)j * UM_D), "d"((double)__uint_as_float(v[j])) : "memory");
+            }
+            continue;
+        }
+        double cur[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cur[j] = __ldcg(dst + (size_t)(half * 16 + j) * UM_D);
-            if (half == 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int q = 0; q < 4; ++q) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                __stcg(dst + (size_t)(half * 16 + j) * UM_D,
-                       cur[j] + (double)__uint_as_float(v[half * 16 + j]));
+            for (int j = 0; j < 8; ++j) cur[j] = __ldcg(dst + (size_t)(q * 8 + j) * UM_D);
+            if (q == 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                absmax = max(absmax, v[q * 8 + j] & 0x7FFFFFFFu);
+                __stcg(dst + (size_t)(q * 8 + j) * UM_D,
+                       cur[j] + (double)__uint_as_float(v[q * 8 + j]));
+            }
         }
     }
 }
@@ -290,7 +312,8 @@ tica_umma_kernel(const UmmaParams P)
     unsigned char *op_ring = ring + UM_STAGES * UM_RAW_BYTES;         // [UM_STAGES][A_hi|A_lo|B_hi|B_lo]
     UmmaSmem *ctl = reinterpret_cast<UmmaSmem *>(op_ring + UM_STAGES * UM_STAGE_BYTES);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (see elect_one)
     uint32_t cta_rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
     const int pair = blockIdx.x >> 1;
@@ -360,7 +383,8 @@ tica_umma_kernel(const UmmaParams P)
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA, one lane) =============
-        if (cta_rank == 0 && lane == 0 && my_tiles > 0) {
+        if (cta_rank == 0 && my_tiles > 0) {
+            const uint32_t mma_leader = elect_one();
             const uint32_t idesc = umma_idesc<KIND>();
             const uint32_t ring_addr = smem_u32(op_ring);
             const bool dbg_on = P.dbg != nullptr && pair == 0;
@@ -429,6 +453,10 @@ tica_umma_kernel(const UmmaParams P)
                                        dAl = umma_desc(A0 + 2 * UM_BF_TILE_BYTES + off);
                         const uint64_t dBh = umma_desc(B0 + off), dBm = umma_desc(B0 + UM_BF_TILE_BYTES + off),
                                        dBl = umma_desc(B0 + 2 * UM_BF_TILE_BYTES + off);
+                        if (P.dbg_mode & 4) {
+                            umma_bf16_pair(tmem, dAh, dBh, idesc, acc);
+                            continue;
+                        }
                         if (P.passes == 3 && P.collector) {
                             // A = h feeds four MMAs, A = m (l for fp16) two: 2 instead of 6 A-tile
                             // fetches from shared memory per K step
@@ -460,7 +488,7 @@ tica_umma_kernel(const UmmaParams P)
                 if (slab_last) umma_commit_pair(&ctl->acc_full);
                 if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
             }
-            if (dbg_on) {
+            if (dbg_on && lane == 0) {
                 P.dbg[0] = clock64() - d_start;      // MMA thread: total issue-loop cycles
                 P.dbg[1] = d_wait_conv;              //   of which waiting for converted operands
                 P.dbg[2] = d_wait_acc;               //   of which waiting for the TMEM flush
@@ -470,39 +498,49 @@ tica_umma_kernel(const UmmaParams P)
     } else if (warp >= 4 && warp < 4 + UM_CONV_WARPS) {
         // ================================ converters (256 threads, both CTAs) ==========
         // Thread map: warp cw & 3 -> 32-feature block of this CTA, lane -> feature inside
-        // the block; warps 0-3 take the even 4-frame row-blocks of a tile, warps 4-7 the
-        // odd ones.  A thread gathers the 4 frames of ITS feature with four 4-byte
+        // the block; cw >> 2 -> which quarter (8 frames) of a tile.  A thread gathers the
+        // frames of ITS feature 4 (tf32) or 8 (2-byte kinds) at a time with 4-byte
         // shared loads (a warp reads one 128-byte swizzled row segment per load: all 32
         // banks, conflict free) and stores one 16-byte K-major chunk (a warp writes 512
         // contiguous bytes): the fp32 -> tf32 hi/lo conversion transposes for free.
         const int cw = warp - 4;
         const int fb = cw & 3;                           // feature block (32 features)
-        const int rb_par = cw >> 2;                      // row-block parity handled by this warp
+        const int kq = cw >> 2;                          // 8-frame quarter of the tile handled by this warp
         const int f_local = 32 * fb + lane;              // feature inside the CTA (0..127)
         const int chunk = lane >> 2, within = (lane & 3) * 4;
         const float sh = P.shift[UM_F * cta_rank + f_local];
         const float sc = F16 ? P.scale[UM_F * cta_rank + f_local] : 1.f;
-        float amax = 0.f;                                // largest scaled magnitude seen (fp16 range check)
+        const float nsh = -sh * sc;                      // exact (power-of-two scale)
+        const uint32_t h_add = P.h_add, h_mask = P.h_mask;
         const bool split = P.passes == 3;
-        double sumA = 0.0, sumB = 0.0;                   // column sums of feature 128*rank + f_local
+        double sumA = 0.0;                               // column sum (unlagged rows) of feature 128*rank + f_local,
+                                                         // in units of 1/sc; the lagged sum follows from it and the
+                                                         // head/tail rows (tica_umma_edges_kernel)
+        float sAh = 0.f, sAl = 0.f;                      //   its float-pair front end (see below)
         int stage = 0;
         uint32_t phase = 0;
         const bool dbg_on = P.dbg != nullptr && pair == 0 && tid == 128 && cta_rank == 0;
-        long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0;
-        // the converters are idle whenever the accumulators are being drained (the UMMA pipe
-        // stalls, so no operand stage is released): they help, 2 of the 3 warps per TMEM quarter
+        long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0, d_flush = 0;
+        // the converters have nothing to convert while the accumulators are being drained (the UMMA
+        // pipe stalls, so no operand stage is released): they do the draining, 4 warps per TMEM quarter
         int next_flush = 0;
         uint32_t acc_phase = 0;
+        uint32_t absmax = 0;                             // largest |accumulator| bit pattern drained so far
         auto help_flush = [&]() {
-            flush_prefetch(P, pair, cta_rank, cw & 3, 1 + (cw >> 2), 3, lane);
+            const long long f0 = dbg_on ? clock64() : 0;
+            if (!P.flush_red) flush_prefetch(P, pair, cta_rank, cw & 3, cw >> 2, 4, lane);
             mbar_wait(&ctl->acc_full, acc_phase);
             acc_phase ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
-            flush_share(P, tmem, pair, cta_rank, cw & 3, 1 + (cw >> 2), 3, lane);
+            sumA += (double)sAh + (double)sAl;           // the tensor pipe is idle here: FP64 is cheap
+            sAh = sAl = 0.f;
+            if (!(P.dbg_mode & 2))
+                flush_share(P, tmem, pair, cta_rank, cw & 3, cw >> 2, 4, lane, absmax);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0 && next_flush + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
             ++next_flush;
+            if (dbg_on) d_flush += clock64() - f0;
         };
         for (int t = 0; t < my_tiles; ++t) {
             // slab j ends with tile min(first_len + j*slab_tiles, my_tiles) - 1; by the time this warp is
@@ -521,114 +559,126 @@ tica_umma_kernel(const UmmaParams P)
             const int valid = ctl->valid_rows[stage];
             const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
             unsigned char *st = op_ring + stage * UM_STAGE_BYTES;
-            float tsA = 0.f, tsB = 0.f;
+            float tsA = 0.f;
+            // full tiles (all but the last of a sequence) skip the per-value row test
+            auto convert_tile = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-            for (int op = 0; op < 2; ++op) {
-                const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
-                if constexpr (!BF16) {
-                    unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
-                    unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
+                for (int op = 0; op < 2; ++op) {
+                    const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
+                    if constexpr (!BF16) {
+                        unsigned char *hi_buf = st + op * 2 * UM_TILE_BYTES + f_local * 16;
+                        unsigned char *lo_buf = hi_buf + UM_TILE_BYTES;
 #pragma unroll
-                    for (int k = 0; k < UM_RB / 2; ++k) {
-                        const int rb = 2 * k + rb_par;
-                        float a[4];
+                        for (int k = 0; k < 2; ++k) {
+                            const int rb = 2 * kq + k;
+                            float a[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = 4 * rb + i;          // frame inside the tile
-                            const float v = *reinterpret_cast<const float *>(
-                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            a[i] = (r < valid) ? v - sh : 0.f;
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = 4 * rb + i;          // frame inside the tile
+                                const float v = *reinterpret_cast<const float *>(
+                                    raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                a[i] = (FULL || r < valid) ? v - sh : 0.f;
+                            }
+                            const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
+                            if (op == 0) tsA += s4;
+                            float4 hv;
+                            hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
+                            *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
+                            if (split) {
+                                float4 l;
+                                l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
+                                l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
+                                *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
+                            }
                         }
-                        const float s4 = (a[0] + a[1]) + (a[2] + a[3]);
-                        if (op == 0) tsA += s4; else tsB += s4;
-                        float4 hv;
-                        hv.x = tf32_rn(a[0]); hv.y = tf32_rn(a[1]); hv.z = tf32_rn(a[2]); hv.w = tf32_rn(a[3]);
-                        *reinterpret_cast<float4 *>(hi_buf + rb * UM_LBO) = hv;
-                        if (split) {
-                            float4 l;
-                            l.x = tf32_rn(a[0] - hv.x); l.y = tf32_rn(a[1] - hv.y);
-                            l.z = tf32_rn(a[2] - hv.z); l.w = tf32_rn(a[3] - hv.w);
-                            *reinterpret_cast<float4 *>(lo_buf + rb * UM_LBO) = l;
-                        }
-                    }
-                } else if constexpr (F16) {
-                    // fp16 h/l split of the scaled value (x - shift) * 2^e: h = the value rounded
-                    // to 11 significant bits (two integer ops; exact in fp16's normal range),
-                    // l = fp16(value - h).  Below 2^-14 both roundings are absolute, <= 2^-25.
-                    unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
-                    unsigned char *l_buf = h_buf + UM_BF_TILE_BYTES;
+                    } else if constexpr (F16) {
+                        // fp16 h/l split of the scaled value (x - shift) * 2^e: h = the value rounded
+                        // to 11 significant bits (two integer ops; exact in fp16's normal range),
+                        // l = fp16(value - h).  Below 2^-14 both roundings are absolute, <= 2^-25.
+                        unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
+                        unsigned char *l_buf = h_buf + UM_BF_TILE_BYTES;
+                        {
+                            const int kb = kq;                      // block of 8 frames
+                            float h[8], l[8];
+                            float s8 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < UM_KT / 16; ++k) {
-                        const int kb = 2 * k + rb_par;          // block of 8 frames
-                        float h[8], l[8];
-                        float s8 = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 8 * kb + i;
-                            const float v = *reinterpret_cast<const float *>(
-                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            const float u = (r < valid) ? v - sh : 0.f;
-                            s8 += u;
-                            const float as = u * sc;
-                            amax = fmaxf(amax, fabsf(as));
-                            h[i] = tf32_rn(as);
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = 8 * kb + i;
+                                const float v = *reinterpret_cast<const float *>(
+                                    raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                // (v - sh) * sc in one rounding: the scale is a power of two, so this is
+                            // exactly sc * fl32(v - sh), the x' of the float64 edge kernel
+                            const float as = (FULL || r < valid) ? fmaf(v, sc, nsh) : 0.f;
+                            s8 += as;
+                            h[i] = __uint_as_float((__float_as_uint(as) + h_add) & h_mask);
                             l[i] = as - h[i];                 // exact in fp32
                         }
-                        if (op == 0) tsA += s8; else tsB += s8;
+                        if (op == 0) tsA += s8;
                         uint4 hw, lw;
-                        hw.x = pack_f16(h[0], h[1]); hw.y = pack_f16(h[2], h[3]);
-                        hw.z = pack_f16(h[4], h[5]); hw.w = pack_f16(h[6], h[7]);
-                        lw.x = pack_f16(l[0], l[1]); lw.y = pack_f16(l[2], l[3]);
-                        lw.z = pack_f16(l[4], l[5]); lw.w = pack_f16(l[6], l[7]);
-                        *reinterpret_cast<uint4 *>(h_buf + kb * UM_LBO) = hw;
-                        *reinterpret_cast<uint4 *>(l_buf + kb * UM_LBO) = lw;
-                    }
-                } else {
-                    // 16-byte chunk = 8 consecutive frames of this thread's feature
-                    unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
-                    unsigned char *m_buf = h_buf + UM_BF_TILE_BYTES;
-                    unsigned char *l_buf = h_buf + 2 * UM_BF_TILE_BYTES;
-                    const bool six = P.passes == 6;
-#pragma unroll
-                    for (int k = 0; k < UM_KT / 16; ++k) {
-                        const int kb = 2 * k + rb_par;          // block of 8 frames
-                        float a[8], h[8], m[8];
-                        float s8 = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 8 * kb + i;
-                            const float v = *reinterpret_cast<const float *>(
-                                raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                            a[i] = (r < valid) ? v - sh : 0.f;
-                            s8 += a[i];
-                            h[i] = bf16_rn(a[i]);
-                            m[i] = bf16_rn(a[i] - h[i]);      // a - h is exact in fp32
-                        }
-                        if (op == 0) tsA += s8; else tsB += s8;
-                        uint4 hw, mw;
-                        hw.x = pack_bf16(h[0], h[1]); hw.y = pack_bf16(h[2], h[3]);
-                        hw.z = pack_bf16(h[4], h[5]); hw.w = pack_bf16(h[6], h[7]);
-                        mw.x = pack_bf16(m[0], m[1]); mw.y = pack_bf16(m[2], m[3]);
-                        mw.z = pack_bf16(m[4], m[5]); mw.w = pack_bf16(m[6], m[7]);
-                        *reinterpret_cast<uint4 *>(h_buf + kb * UM_LBO) = hw;
-                        *reinterpret_cast<uint4 *>(m_buf + kb * UM_LBO) = mw;
-                        if (six) {
-                            float l[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) l[i] = bf16_rn((a[i] - h[i]) - m[i]);
-                            uint4 lw;
-                            lw.x = pack_bf16(l[0], l[1]); lw.y = pack_bf16(l[2], l[3]);
-                            lw.z = pack_bf16(l[4], l[5]); lw.w = pack_bf16(l[6], l[7]);
+                            hw.x = pack_f16(h[0], h[1]); hw.y = pack_f16(h[2], h[3]);
+                            hw.z = pack_f16(h[4], h[5]); hw.w = pack_f16(h[6], h[7]);
+                            lw.x = pack_f16(l[0], l[1]); lw.y = pack_f16(l[2], l[3]);
+                            lw.z = pack_f16(l[4], l[5]); lw.w = pack_f16(l[6], l[7]);
+                            *reinterpret_cast<uint4 *>(h_buf + kb * UM_LBO) = hw;
                             *reinterpret_cast<uint4 *>(l_buf + kb * UM_LBO) = lw;
+                        }
+                    } else {
+                        // 16-byte chunk = 8 consecutive frames of this thread's feature
+                        unsigned char *h_buf = st + op * 3 * UM_BF_TILE_BYTES + f_local * 16;
+                        unsigned char *m_buf = h_buf + UM_BF_TILE_BYTES;
+                        unsigned char *l_buf = h_buf + 2 * UM_BF_TILE_BYTES;
+                        const bool six = P.passes == 6;
+                        {
+                            const int kb = kq;                      // block of 8 frames
+                            float a[8], h[8], m[8];
+                            float s8 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int r = 8 * kb + i;
+                                const float v = *reinterpret_cast<const float *>(
+                                    raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                                a[i] = (FULL || r < valid) ? v - sh : 0.f;
+                                s8 += a[i];
+                                h[i] = bf16_rn(a[i]);
+                                m[i] = bf16_rn(a[i] - h[i]);      // a - h is exact in fp32
+                            }
+                            if (op == 0) tsA += s8;
+                            uint4 hw, mw;
+                            hw.x = pack_bf16(h[0], h[1]); hw.y = pack_bf16(h[2], h[3]);
+                            hw.z = pack_bf16(h[4], h[5]); hw.w = pack_bf16(h[6], h[7]);
+                            mw.x = pack_bf16(m[0], m[1]); mw.y = pack_bf16(m[2], m[3]);
+                            mw.z = pack_bf16(m[4], m[5]); mw.w = pack_bf16(m[6], m[7]);
+                            *reinterpret_cast<uint4 *>(h_buf + kb * UM_LBO) = hw;
+                            *reinterpret_cast<uint4 *>(m_buf + kb * UM_LBO) = mw;
+                            if (six) {
+                                float l[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) l[i] = bf16_rn((a[i] - h[i]) - m[i]);
+                                uint4 lw;
+                                lw.x = pack_bf16(l[0], l[1]); lw.y = pack_bf16(l[2], l[3]);
+                                lw.z = pack_bf16(l[4], l[5]); lw.w = pack_bf16(l[6], l[7]);
+                                *reinterpret_cast<uint4 *>(l_buf + kb * UM_LBO) = lw;
+                            }
                         }
                     }
                 }
+            };
+            if (P.dbg_mode & 1) { /* timing experiment: no conversion traffic */ }
+            else if (valid == UM_KT) convert_tile(std::true_type());
+            else convert_tile(std::false_type());
+            // column sums: error-free float pair (TwoSum) per tile, folded into the doubles only while
+            // the accumulators drain -- an FP64 instruction issued while the tensor pipe is busy
+            // stalls for hundreds of cycles on B200 (stall_math on this DADD was the top stall of
+            // the converter warps, profiles/r1_k1_issue.txt)
+            {
+                const float t = sAh + tsA, bp = t - sAh;
+                sAl += (sAh - (t - bp)) + (tsA - bp);
+                sAh = t;
             }
-            sumA += (double)tsA;
-            sumB += (double)tsB;
             long long q3 = dbg_on ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> UMMA (async proxy)
-            asm volatile("bar.sync 1, 256;" ::: "memory");                 // all 8 converter warps of this CTA
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * UM_CONV_WARPS) : "memory");   // all converter warps of this CTA
             if (tid == 128) {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
                              :: "r"(smem_u32(&ctl->raw_empty[stage])) : "memory");
@@ -638,33 +688,17 @@ tica_umma_kernel(const UmmaParams P)
             if (++stage == UM_STAGES) { stage = 0; phase ^= 1; }
         }
         while (next_flush < n_slabs) help_flush();
-        if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync; }
+        if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync;
+                      P.dbg[8] = d_flush; P.dbg[9] = n_slabs; }
         if (my_tiles > 0) {
             const int f = UM_F * cta_rank + f_local;
-            atomicAdd(&P.sums[f], sumA);
-            atomicAdd(&P.sums[UM_D + f], sumB);
+            sumA += (double)sAh + (double)sAl;
+            atomicAdd(&P.sums[f], sumA / (double)sc);
         }
-        // fp16 tops out at 65504: anything near it (or Inf) sends the whole call to the bf16 engine
-        if (F16 && !(amax < 60000.f)) atomicOr(P.overflow, 1);
-    } else if (warp >= 4 + UM_CONV_WARPS) {
-        // ================================ epilogue (128 threads, both CTAs) =============
-        const int ew = warp - (4 + UM_CONV_WARPS);                       // == warp % 4: TMEM lane quarter
-        uint32_t acc_phase = 0;
-        const bool dbg_on = P.dbg != nullptr && pair == 0 && cta_rank == 0 && ew == 0 && lane == 0;
-        long long d_flush = 0;
-        for (int slab = 0; slab < n_slabs; ++slab) {
-            flush_prefetch(P, pair, cta_rank, ew, 0, 3, lane);
-            mbar_wait(&ctl->acc_full, acc_phase);
-            const long long f0 = dbg_on ? clock64() : 0;
-            acc_phase ^= 1;
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            flush_share(P, tmem, pair, cta_rank, ew, 0, 3, lane);
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0 && slab + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
-            if (dbg_on) d_flush += clock64() - f0;
-        }
-        if (dbg_on) { P.dbg[8] = d_flush; P.dbg[9] = n_slabs; }
+        // fp16 tops out at 65504: a scaled value beyond it became Inf, and Inf (or the NaN of
+        // Inf * 0) is then in the accumulators of its feature -- the whole call is redone by the
+        // bf16 engine (rescue launch).  Non-finite input takes the same, harmless, detour.
+        if (F16 && absmax >= 0x7F800000u) atomicOr(P.overflow, 1);
     }
 
     // teardown: nobody may still be using the peer's barriers / TMEM
@@ -723,7 +757,8 @@ struct EdgeSeq {
 //   E[1] += the same t of x'_t x'_t^T
 //   E[2] += sum_{t < lag} x'_t x'_t^T            (head: in C_00, not in C_tautau)
 //   E[3] += sum_{t >= n-lag} x'_t x'_t^T         (tail: in C_tautau, not in C_00)
-//   es[0..2] (D each): remainder sums of x'_t, of x'_{t+lag}, and the tail-row sum
+//   es[0..2] (D each): remainder sum of x'_t; (that + tail rows - head rows) = what turns the
+//   unlagged column sum of the tensor-core part into the lagged one; the tail-row sum
 // grid (n_blocks, D/16): block (b, it) accumulates rows 16*it..16*it+15 of the outputs
 // over sequences b, b + n_blocks, ...
 __global__ void __launch_bounds__(256)
@@ -740,7 +775,7 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int u = 0; u < 16; ++u) acc[m][u] = 0.0;
-    double s0 = 0.0, st = 0.0, stail = 0.0;    // column `tid` sums (only blockIdx.y == 0 publishes)
+    double s0 = 0.0, shead = 0.0, stail = 0.0; // column `tid` sums (only blockIdx.y == 0 publishes)
 
     for (int s = blockIdx.x; s < n_seq; s += gridDim.x) {
         const float *X = seqs[s].base;
@@ -770,10 +805,10 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
                     acc[1][u] = fma(xi, xj, acc[1][u]);
                 }
                 s0 += xj;
-                st += yj;
             } else if (kind == 2) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) acc[2][u] = fma(sx[i0 + u], xj, acc[2][u]);
+                shead += xj;
             } else {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) acc[3][u] = fma(sx[i0 + u], xj, acc[3][u]);
@@ -788,7 +823,7 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
             if (tid < Dr) atomicAdd(&E[(size_t)m * D * D + (size_t)(i0 + u) * D + tid], acc[m][u]);
     if (blockIdx.y == 0 && tid < Dr) {
         atomicAdd(&es[tid], s0);
-        atomicAdd(&es[D + tid], st);
+        atomicAdd(&es[D + tid], s0 + stail - shead);
         atomicAdd(&es[2 * D + tid], stail);
     }
 }
@@ -827,7 +862,8 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
     const double ctt = c00 - E[2 * DD + pidx] + E[3 * DD + pidx];
     const double si = (double)shift[i], sj = (double)shift[j];
     const double S0i = sums[i] + es[i], S0j = sums[j] + es[j];
-    const double Sti = sums[D + i] + es[D + i], Stj = sums[D + j] + es[D + j];
+    // sum over the pair rows of x'_{t+lag} = the same sum of x'_t, minus the head rows, plus the tail rows
+    const double Sti = sums[i] + es[D + i], Stj = sums[j] + es[D + j];
     const double Np = n_pairs_total;
     acc[idx] += ctau + S0i * sj + si * Stj + Np * si * sj;
     acc[RR + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
@@ -1027,10 +1063,21 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16: 2-byte operands, K = 16
     // bf16 MMAs cover 16 frames per accumulate step (tf32: 8), so twice the frames per slab
     // carry the same truncation bias
-    P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", bf16 ? 2 * UM_SLAB_TILES_DEFAULT : UM_SLAB_TILES_DEFAULT);
+    // (the fp16 engine's eigenvalue error grows ~3e-6 per 1024 frames of slab, measured: it stays at 1024)
+    P.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES",
+                           (bf16 && !f16) ? 2 * UM_SLAB_TILES_DEFAULT : UM_SLAB_TILES_DEFAULT);
     if (P.slab_tiles < 1) P.slab_tiles = 1;
     P.passes = f16 ? 3 : bf16 ? passes - 10 : passes;
-    P.collector = env_int("MSMB200_UMMA_COLLECTOR", 0);
+    P.collector = env_int("MSMB200_UMMA_COLLECTOR", 1);
+    P.flush_red = env_int("MSMB200_UMMA_FLUSH_RED", 1);
+    P.dbg_mode = env_int("MSMB200_UMMA_DBGMODE", 0);
+    {
+        int hb = env_int("MSMB200_UMMA_HBITS", 11);      // significant bits kept in h (11 = all of fp16)
+        if (hb < 4) hb = 4;
+        if (hb > 11) hb = 11;
+        P.h_add = 1u << (23 - hb);
+        P.h_mask = ~((1u << (24 - hb)) - 1u);
+    }
     P.shift = d_shift;
     P.scale = d_scale;
     P.overflow = d_flag;
