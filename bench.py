@@ -12,8 +12,10 @@ the hot path over all frames:
   1. tICA(lag_time=10).fit  -> the covariance accumulation K1 over every sequence
      (tica.py:401-424; the eigensolve is lazy in the reference too and is not part
      of fit), plus the all-reduce of the packed accumulator when N > 1;
-  2. KCenters(n_clusters=k).fit -> k fused distance/assign passes K2 over every
-     frame (kcenters.py:91-97), labels + distances + centre ids produced.
+  2. KCenters(n_clusters=k).fit -> the reference's k centres, labels and distances
+     (kcenters.py:79-102).  The reference reads every frame once per centre; the
+     look-ahead path (csrc/kcenters_lookahead.cu) certifies several centres per read
+     (`roofline.launches_per_step` fused passes per fit; --no-lookahead = k passes).
 
 `value` = total frames / step time with the frames already resident in HBM
 (CUDA events, max over ranks).  `e2e` = the same two estimator calls through the
@@ -53,6 +55,8 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lookahead", action="store_true",
+                    help="KCenters: one pass per centre (the reference's schedule) instead of look-ahead")
     return ap.parse_args()
 
 
@@ -257,7 +261,9 @@ def run_ours(args):
         if record:
             ev[1].record()
         ids, distances, labels, ring = par.kcenters_fit_gpu(X, row_offset, k, "euclidean",
-                                                            seed_global=12345 % n_total)
+                                                            seed_global=12345 % n_total,
+                                                            lookahead=not args.no_lookahead,
+                                                            stats=state)
         if record:
             ev[2].record()
         state["ids"], state["labels"], state["distances"] = ids, labels, distances
@@ -280,11 +286,17 @@ def run_ours(args):
     if profiling:
         torch.cuda.profiler.start()
     t_start.record()
+    state["time_passes"] = True          # CUDA events around every fused K2 launch (look-ahead path)
+    pass_ms, pass_centres = [], []
     for _ in range(args.steps):
+        state["pass_events"] = []
         step(True)
         ev[2].synchronize()
         phase_ms["tica"].append(ev[0].elapsed_time(ev[1]))
         phase_ms["kcenters"].append(ev[1].elapsed_time(ev[2]))
+        for (nc, e0, e1) in state["pass_events"]:
+            pass_ms.append(e0.elapsed_time(e1))
+            pass_centres.append(nc)
     t_stop.record()
     barrier()
     if profiling:
@@ -383,7 +395,11 @@ def run_ours(args):
         engine_used = args.engine
     tica_s = float(tica_ms.item()) / 1e3
     kc_s = float(kc_ms.item()) / 1e3
-    pass_s = kc_s / k
+    n_passes = int(state.get("passes", k))                # reads of the frames per KCenters.fit
+    if pass_ms:                                            # look-ahead: per-launch CUDA events
+        pass_s = float(np.mean(pass_ms)) / 1e3
+    else:                                                  # one pass per centre, launches back to back
+        pass_s = kc_s / k
     bytes_per_pass = (n_total / ws) * (4 * D + 8)          # per GPU: frame + f64 running min
     hbm_ach = bytes_per_pass / pass_s / 1e9
     flops_tica = 4.0 * D * D * (n_total / ws)              # algorithmic: two rank-1 DxD updates / frame
@@ -393,11 +409,14 @@ def run_ours(args):
     issued = {"auto": 3, "umma_3xf16": 3, "umma_6xbf16": 6, "umma_3xbf16": 3, "umma_3xtf32": 3,
               "umma_tf32": 1}.get(args.engine, 1)
     tica_ach = flops_tica / tica_s / 1e12
-    roof_k2 = {"kernel": "kcenters_pass_kernel", "bound": "hbm", "achieved": hbm_ach,
+    roof_k2 = {"kernel": "kcenters_multi_pass_kernel" if pass_ms else "kcenters_pass_fast_kernel",
+               "bound": "hbm", "achieved": hbm_ach,
                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                "traffic": None, "peak_source": peaks["source"],
                "algorithmic_bytes_per_launch": bytes_per_pass, "ms_per_launch": pass_s * 1e3,
-               "share_of_step": kc_s / (ms_per_step / 1e3)}
+               "launches_per_step": n_passes,
+               "centres_per_launch": sorted(set(pass_centres)) if pass_centres else [1],
+               "share_of_step": (pass_s * n_passes) / (ms_per_step / 1e3)}
     roof_k1 = {"kernel": "tica_accumulate(%s)" % args.engine, "bound": "tensor", "achieved": tica_ach,
                "peak": tf32_peak, "unit": "TFLOP/s", "frac": tica_ach / tf32_peak, "traffic": None,
                "peak_source": peaks["source"] + ("; sustained bf16 (kind::f16 MMAs run at the same rate)" if is_bf16 else
@@ -421,7 +440,9 @@ def run_ours(args):
         "data": "synthetic", "config": workload_config(args, ws),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": dominant, "roofline_all": [roof_k1, roof_k2],
-        "phases_ms": {"tica_fit": tica_s * 1e3, "kcenters_fit": kc_s * 1e3},
+        "phases_ms": {"tica_fit": tica_s * 1e3, "kcenters_fit": kc_s * 1e3,
+                      "kcenters_launches": [[int(c), round(float(m), 3)] for c, m in
+                                            zip(pass_centres[-n_passes:], pass_ms[-n_passes:])] if pass_ms else None},
         "tica_engine": args.engine,
         "check": {"eigenvalues": eig, "kcenters_ids": [int(i) for i in state["ids"].cpu().numpy()]},
     }

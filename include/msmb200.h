@@ -150,6 +150,39 @@ int msmb200_candidate_from_row(const void *X, int64_t row, int d, int64_t ld,
                                int dtype, int64_t row_offset,
                                msmb200_candidate *out, void *stream);
 
+/* ------------------------------------------------------------------------ *
+ *  K2b  k-centers with look-ahead (csrc/kcenters_lookahead.cu)
+ *  Same results as k calls of msmb200_kcenters_pass (kcenters.py:91-97), in
+ *  (number of certified chains + 1) reads of the frames instead of k:
+ *    multi_pass  applies the J pending centres (labels label0 .. label0+J-1) in
+ *                ONE streaming read -- float32 filter, reference arithmetic for
+ *                every (frame, centre) pair that could lower the frame's minimum
+ *                -- and records each lane's largest / second largest minimum;
+ *    select      turns those into this shard's candidate set: up to t_cap
+ *                frames (value, global row, the row itself) and the bound tau on
+ *                every frame that is NOT a candidate;
+ *    chain       replays the reference's arg-max / update loop on the candidate
+ *                sets of all shards (all-gathered by the caller) and emits the
+ *                centres it can certify (value > tau; the first pick is the true
+ *                arg-max and always certified): the next multi_pass' input.
+ *  float32, euclidean / sqeuclidean, 16-byte aligned rows (..._supported()).
+ *  Buffers are opaque DEVICE blobs sized by the *_bytes() helpers; a centres
+ *  blob is {int32 n; int32 cap; 24 bytes pad; int64 ids[cap]; float rows[cap][d]}.
+ * ------------------------------------------------------------------------ */
+int msmb200_kcenters_lookahead_supported(int d, int64_t ld, int dtype, int metric);
+size_t msmb200_kcenters_lane_bytes(int device);
+size_t msmb200_kcenters_set_bytes(int d, int t_cap);
+size_t msmb200_kcenters_centers_bytes(int d, int j_cap);
+int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int64_t ld, int dtype,
+                                int metric, const void *centers, int n_centers, int j_cap,
+                                int32_t label0, int first, double *distances,
+                                int32_t *labels, int64_t row_offset, void *lane_buf,
+                                size_t lane_bytes, void *stream);
+int msmb200_kcenters_select(const void *X, int64_t n, int d, int64_t ld, int64_t row_offset,
+                            const void *lane_buf, int t_cap, void *set_out, void *stream);
+int msmb200_kcenters_chain(void *sets, int n_sets, size_t set_stride, int d, int metric,
+                           int k_remaining, int j_cap, void *centers_out, void *stream);
+
 /* ======================================================================== *
  *  K3  assign_nearest                                                      *
  *  replaces libdistance.assign_nearest (libdistance.pyx:82-131 ->          *

@@ -97,13 +97,21 @@ class KCentersState(object):
                   self.row_elems, self.dtype, dev.ptr(out_cand), dev.stream_ptr())
 
 
-def kcenters_fit(data, n_clusters, metric, seed_index, traces=None):
-    """Single-GPU Gonzalez k-centers (kcenters.py:79-102): k passes enqueued back
-    to back, the arg-max that names the next centre never leaves the device.
+def kcenters_fit(data, n_clusters, metric, seed_index, traces=None, lookahead=True, stats=None):
+    """Single-GPU Gonzalez k-centers (kcenters.py:79-102).  float32 (sq)euclidean input takes
+    the look-ahead path (kcenters_fit_lookahead: several centres per read of the frames);
+    everything else runs k passes enqueued back to back, the arg-max that names the next
+    centre never leaving the device.  Both give the reference's centres and labels.
 
     Returns (cluster_ids int64[k] tensor, distances f64[n], labels i32[n])."""
+    if traces is None and lookahead and lookahead_supported(data, metric):
+        ids, _, distances, labels = kcenters_fit_lookahead(data, n_clusters, metric, seed_index,
+                                                           stats=stats)
+        return ids, distances, labels
     st = KCentersState(data, metric, traces=traces)
     k = int(n_clusters)
+    if stats is not None:
+        stats["passes"] = k
     # ring of k candidate slots: slot i holds centre i (its index is cluster_ids_[i])
     ring = torch.zeros((k + 1, st.cand_bytes), dtype=torch.uint8, device="cuda")
     st.seed(ring[0], int(seed_index))
@@ -111,6 +119,134 @@ def kcenters_fit(data, n_clusters, metric, seed_index, traces=None):
         st.run_pass(ring[i], i, out_cand=ring[i + 1])
     ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
     return ids, st.distances, st.labels
+
+
+# ------------------------------------------------------------------ K2b (look-ahead)
+LOOKAHEAD_T_CAP = 512     # candidates kept per shard and pass
+LOOKAHEAD_J_CAP = 16      # centres applied by one fused pass at most
+CENTERS_HEADER = 32       # sizeof(CentersHeader)
+
+
+def lookahead_supported(data, metric):
+    """True when the fused look-ahead kernels take this input (float32, euclidean or
+    sqeuclidean, 16-byte aligned rows); otherwise KCenters runs one pass per centre."""
+    if metric not in ("euclidean", "sqeuclidean") or data.dtype != torch.float32 or data.dim() != 2:
+        return False
+    if data.data_ptr() % 16 or not data.is_contiguous():
+        return False
+    d = int(data.shape[1])
+    return bool(_lib.load().msmb200_kcenters_lookahead_supported(d, d, _lib.F32, _lib.metric_id(metric)))
+
+
+class LookaheadState(object):
+    """Per-shard buffers of the look-ahead k-centers (csrc/kcenters_lookahead.cu)."""
+
+    def __init__(self, data, metric, row_offset=0, t_cap=LOOKAHEAD_T_CAP, j_cap=LOOKAHEAD_J_CAP):
+        _lib.require_gpu()
+        lib = _lib.load()
+        self.data = data
+        self.metric = _lib.metric_id(metric)
+        self.n, self.d = int(data.shape[0]), int(data.shape[1])
+        self.row_offset = int(row_offset)
+        self.t_cap, self.j_cap = int(t_cap), int(j_cap)
+        self.distances = torch.full((self.n,), float("inf"), dtype=torch.float64, device="cuda")
+        self.labels = torch.zeros((self.n,), dtype=torch.int32, device="cuda")
+        self.lane = torch.zeros(int(lib.msmb200_kcenters_lane_bytes(0)), dtype=torch.uint8, device="cuda")
+        self.set_bytes = int(lib.msmb200_kcenters_set_bytes(self.d, self.t_cap))
+        self.centers_bytes = int(lib.msmb200_kcenters_centers_bytes(self.d, self.j_cap))
+        self.cset = torch.zeros(self.set_bytes, dtype=torch.uint8, device="cuda")
+        self.centers = torch.zeros(self.centers_bytes, dtype=torch.uint8, device="cuda")
+
+    # views into a centres blob
+    def centers_ids(self, blob=None):
+        b = self.centers if blob is None else blob
+        return b[CENTERS_HEADER:CENTERS_HEADER + 8 * self.j_cap].view(torch.int64)
+
+    def centers_rows(self, blob=None):
+        b = self.centers if blob is None else blob
+        off = CENTERS_HEADER + 8 * self.j_cap
+        return b[off:off + 4 * self.j_cap * self.d].view(torch.float32).reshape(self.j_cap, self.d)
+
+    def seed(self, global_row):
+        """The seed centre (kcenters.py:84) as the first pending centre; on a rank that does not
+        hold the row the blob is zeroed (the caller broadcasts the owner's)."""
+        self.centers.zero_()
+        local = int(global_row) - self.row_offset
+        if 0 <= local < self.n:
+            self.centers[:8].view(torch.int32)[0] = 1
+            self.centers[:8].view(torch.int32)[1] = self.j_cap
+            self.centers_ids()[0] = int(global_row)
+            self.centers_rows()[0].copy_(self.data[local])
+            return True
+        return False
+
+    def multi_pass(self, n_centers, label0, first):
+        if self.n == 0:
+            return
+        _lib.call("msmb200_kcenters_multi_pass", dev.ptr(self.data), self.n, self.d, self.d,
+                  _lib.F32, self.metric, dev.ptr(self.centers), int(n_centers), self.j_cap,
+                  int(label0), 1 if first else 0, dev.ptr(self.distances), dev.ptr(self.labels),
+                  self.row_offset, dev.ptr(self.lane), self.lane.numel(), dev.stream_ptr())
+
+    def select(self):
+        if self.n == 0:
+            self.cset.zero_()
+            self.cset[8:16].view(torch.float64)[0] = float("-inf")
+            return self.cset
+        _lib.call("msmb200_kcenters_select", dev.ptr(self.data), self.n, self.d, self.d,
+                  self.row_offset, dev.ptr(self.lane), self.t_cap, dev.ptr(self.cset),
+                  dev.stream_ptr())
+        return self.cset
+
+    def chain(self, sets, n_sets, k_remaining):
+        _lib.call("msmb200_kcenters_chain", dev.ptr(sets), int(n_sets), self.set_bytes, self.d,
+                  self.metric, int(k_remaining), self.j_cap, dev.ptr(self.centers), dev.stream_ptr())
+        return int(self.centers[:4].view(torch.int32).item())     # the one host sync per chain
+
+
+def kcenters_fit_lookahead(data, n_clusters, metric, seed_index, gather_sets=None, bcast=None,
+                           row_offset=0, stats=None, state=None):
+    """Gonzalez k-centers with look-ahead: the reference's centres, labels and distances
+    (kcenters.py:79-102) in (number of chains + 1) reads of the frames instead of k.
+
+    gather_sets(set_blob) -> (all_sets, n_sets) and bcast(blob) make it rank-collective
+    (parallel.kcenters_fit_gpu); single GPU by default.  `state` is the per-shard engine
+    (default: the CUDA LookaheadState; the gloo protocol tests pass a host mirror with the
+    same five methods).
+
+    Returns (cluster_ids int64[k] (global rows), centre rows (k, d), distances f64[n],
+    labels i32[n]) as tensors on the state's device."""
+    st = LookaheadState(data, metric, row_offset=row_offset) if state is None else state
+    k = int(n_clusters)
+    ids, rows = [], []
+    st.seed(seed_index)
+    if bcast is not None:
+        bcast(st.centers)
+    done, n_pending, passes = 0, 1, 0
+    while True:
+        timed = stats is not None and stats.get("time_passes") and torch.cuda.is_available()
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        st.multi_pass(n_pending, done, first=(done == 0))
+        if timed:
+            e1.record()
+            stats.setdefault("pass_events", []).append((n_pending, e0, e1))
+        passes += 1
+        ids.append(st.centers_ids()[:n_pending].clone())
+        rows.append(st.centers_rows()[:n_pending].clone())
+        done += n_pending
+        if done >= k:
+            break
+        sets, n_sets = st.select(), 1
+        if gather_sets is not None:
+            sets, n_sets = gather_sets(sets)
+        n_pending = st.chain(sets, n_sets, k - done)
+        if n_pending < 1:
+            raise _lib.Msmb200Error("k-centers look-ahead found no next centre (empty input?)")
+    if stats is not None:
+        stats["passes"] = passes
+    return torch.cat(ids), torch.cat(rows), st.distances, st.labels
 
 
 def regular_spatial_fit(data, d_min, metric, traces=None):

@@ -41,6 +41,15 @@ SIGNATURES = {
     "msmb200_kcenters_pass": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_i32,
                                       c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "msmb200_candidate_select": (c_int, [c_vp, c_int, c_sz, c_int, c_int, c_vp, c_vp]),
+    "msmb200_kcenters_lookahead_supported": (c_int, [c_int, c_i64, c_int, c_int]),
+    "msmb200_kcenters_lane_bytes": (c_sz, [c_int]),
+    "msmb200_kcenters_set_bytes": (c_sz, [c_int, c_int]),
+    "msmb200_kcenters_centers_bytes": (c_sz, [c_int, c_int]),
+    "msmb200_kcenters_multi_pass": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_int, c_vp, c_int,
+                                            c_int, c_i32, c_int, c_vp, c_vp, c_i64, c_vp, c_sz,
+                                            c_vp]),
+    "msmb200_kcenters_select": (c_int, [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_vp, c_vp]),
+    "msmb200_kcenters_chain": (c_int, [c_vp, c_int, c_sz, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "msmb200_candidate_from_row": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_i64, c_vp, c_vp]),
     "msmb200_assign_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
     "msmb200_assign_nearest": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_int, c_int,

@@ -7,12 +7,15 @@ The hot path shards by frames:
   ``all_reduce(SUM)`` of 3*D*D + 3*D + 2 doubles (1.58 MB at D = 256) merges them.
   The sufficient statistics are additive (tica.py:414-422 are all ``+=``), and
   n_observations / n_sequences ride in the same buffer.
-* KCenters: the concatenated frames are sharded contiguously; every pass each
-  rank writes its farthest frame {value, global index, row} into a candidate
-  slot, ONE ``all_gather`` of those slots (16 B + one row per rank) follows, and
+* KCenters: the concatenated frames are sharded contiguously.  Look-ahead path
+  (float32, (sq)euclidean): after each fused pass every rank all-gathers its
+  candidate set (<= 512 frames + the bound tau on everything else, ~0.5 MB) and
+  runs the same deterministic chain kernel on the union, so all ranks know the next
+  J centres without a broadcast: ONE ``all_gather`` per chain, not per centre.
+  Other metrics: every pass each rank writes its farthest frame {value, global
+  index, row} into a candidate slot, ONE ``all_gather`` of those slots follows, and
   every rank deterministically selects (max value, then lowest global index ==
-  np.argmax's first maximum, kcenters.py:97), so the next centre is known
-  everywhere without a broadcast.
+  np.argmax's first maximum, kcenters.py:97).
 * assign_nearest: centres are broadcast once; labels stay with their shard.
 
 The collectives are tiny and latency-bound, so they are plain NCCL calls on
@@ -127,13 +130,43 @@ def broadcast_centers(centers, src=0, group=None):
 
 
 def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, traces=None,
-                     group=None):
+                     group=None, lookahead=True, stats=None):
     """KCenters over frame shards: `data_local` is this rank's contiguous slice of
     the concatenated frames, starting at global row `row_offset`.
 
     Returns (cluster_ids int64[k] (global indices, device), distances f64[n_local],
     labels i32[n_local], centres ring (k+1, cand_bytes) uint8)."""
     from . import _kernels as K
+    rank, ws = world()
+    # every rank must take the same path: the shape test is a function of (d, dtype, metric) and of
+    # the local base address alignment, which FrameStore / torch allocations always satisfy
+    if traces is None and lookahead and K.lookahead_supported(data_local, metric):
+        gathered = {}
+
+        def gather_sets(local_set):
+            if ws == 1:
+                return local_set, 1
+            if "buf" not in gathered:
+                gathered["buf"] = torch.empty(ws * local_set.numel(), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(gathered["buf"], local_set, group=group)
+            return gathered["buf"], ws
+
+        def bcast(blob):
+            # only the rank that holds the seed row wrote a non-zero blob
+            if ws > 1:
+                dist.all_reduce(blob, op=dist.ReduceOp.SUM, group=group)
+
+        ids, rows, distances, labels = K.kcenters_fit_lookahead(
+            data_local, n_clusters, metric, seed_global, gather_sets=gather_sets, bcast=bcast,
+            row_offset=row_offset, stats=stats)
+        k = int(n_clusters)
+        cand_bytes = CAND_HEADER + 4 * int(data_local.shape[1])
+        ring = torch.zeros((k + 1, cand_bytes), dtype=torch.uint8, device="cuda")
+        ring[:k, 8:16] = ids.view(torch.uint8).reshape(k, 8)
+        ring[:k, CAND_HEADER:] = rows.contiguous().view(torch.uint8).reshape(k, -1)
+        return ids, distances, labels, ring
+    if stats is not None:
+        stats["passes"] = int(n_clusters)
     st = K.KCentersState(data_local, metric, traces=traces, row_offset=row_offset)
 
     def alloc(nbytes):
