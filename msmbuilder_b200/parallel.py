@@ -122,6 +122,35 @@ def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn
     return ring
 
 
+def lookahead_collectives(group=None):
+    """The two collectives of the look-ahead k-centers (_kernels.kcenters_fit_lookahead):
+
+    gather_sets(local_set) -> (all_sets, world_size)   ONE all-gather per chain of every rank's
+                                                       candidate set (uint8 blob, same size everywhere)
+    bcast(blob)                                        the seed centre: only the rank that holds
+                                                       the seed row wrote a non-zero blob, so a SUM
+                                                       all-reduce of the bytes hands it to everyone
+
+    Works on whatever device the blobs live on (NCCL: cuda, gloo: cpu)."""
+    _, ws = world()
+    gathered = {}
+
+    def gather_sets(local_set):
+        if ws == 1:
+            return local_set, 1
+        if "buf" not in gathered:
+            gathered["buf"] = torch.empty(ws * local_set.numel(), dtype=local_set.dtype,
+                                          device=local_set.device)
+        dist.all_gather_into_tensor(gathered["buf"], local_set, group=group)
+        return gathered["buf"], ws
+
+    def bcast(blob):
+        if ws > 1:
+            dist.all_reduce(blob, op=dist.ReduceOp.SUM, group=group)
+
+    return gather_sets, bcast
+
+
 def broadcast_centers(centers, src=0, group=None):
     _, ws = world()
     if ws > 1:
@@ -141,21 +170,7 @@ def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, tr
     # every rank must take the same path: the shape test is a function of (d, dtype, metric) and of
     # the local base address alignment, which FrameStore / torch allocations always satisfy
     if traces is None and lookahead and K.lookahead_supported(data_local, metric):
-        gathered = {}
-
-        def gather_sets(local_set):
-            if ws == 1:
-                return local_set, 1
-            if "buf" not in gathered:
-                gathered["buf"] = torch.empty(ws * local_set.numel(), dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(gathered["buf"], local_set, group=group)
-            return gathered["buf"], ws
-
-        def bcast(blob):
-            # only the rank that holds the seed row wrote a non-zero blob
-            if ws > 1:
-                dist.all_reduce(blob, op=dist.ReduceOp.SUM, group=group)
-
+        gather_sets, bcast = lookahead_collectives(group=group)
         ids, rows, distances, labels = K.kcenters_fit_lookahead(
             data_local, n_clusters, metric, seed_global, gather_sets=gather_sets, bcast=bcast,
             row_offset=row_offset, stats=stats)

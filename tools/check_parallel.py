@@ -48,9 +48,23 @@ def main():
         np.testing.assert_array_equal(kc.distances_[0], ref.distances_[0][a:b])
         np.testing.assert_array_equal(kc.cluster_centers_, ref.cluster_centers_)
         assert abs(kc.inertia_ - ref.inertia_) <= 1e-10 * ref.inertia_
+    # --- look-ahead KCenters across ranks (candidate sets all-gathered once per chain) against the
+    #     one-pass-per-centre schedule on one GPU, on data where the chain certifies little
+    from msmbuilder_b200 import _kernels as K
+    rs = np.random.RandomState(11)
+    cen = rs.randn(5, 64) * 8
+    Y = (cen[rs.randint(0, 5, 30000)] + 0.1 * rs.randn(30000, 64)).astype(np.float32)
+    (a, b) = par.shard_rows(len(Y), ws)[rank]
+    stats = {}
+    ids, distances, labels, ring = par.kcenters_fit_gpu(torch.from_numpy(Y[a:b]).cuda(), a, 40, "euclidean",
+                                                        seed_global=777, stats=stats)
+    rid, rdist, rlab = K.kcenters_fit(torch.from_numpy(Y).cuda(), 40, "euclidean", 777, lookahead=False)
+    assert torch.equal(ids, rid), (ids, rid)
+    assert torch.equal(labels, rlab[a:b]) and torch.equal(distances, rdist[a:b])
+    assert stats["passes"] <= 40
     dist.barrier()
     if rank == 0:
-        print("PARALLEL_OK world_size=%d" % ws)
+        print("PARALLEL_OK world_size=%d (look-ahead passes for k=40: %d)" % (ws, stats["passes"]))
     dist.destroy_process_group()
 
 
