@@ -129,6 +129,24 @@ def device_sequences(sequences):
     return store.split(store.data)
 
 
+def to_host(t, dtype=None):
+    """Device tensor -> NumPy array through PINNED host memory (torch's caching host allocator
+    keeps the blocks, so repeated calls pay no cudaHostAlloc): a pageable ``.cpu()`` of the
+    labels / distances of a few million frames runs at ~2 GB/s and was 20 % of an end-to-end
+    KCenters.fit; this runs at PCIe rate.  `dtype`: convert ON THE DEVICE first (e.g. the
+    int32 labels to the reference's intp) instead of a second pass over the host copy.
+    The returned array owns its (pinned) storage."""
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    t = t.contiguous()
+    if t.numel() * t.element_size() < (1 << 20) or not t.is_cuda:
+        return t.cpu().numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy()
+
+
 class Workspace(object):
     """Grow-only device scratch buffer keyed by purpose."""
 

@@ -123,7 +123,8 @@ def kcenters_fit(data, n_clusters, metric, seed_index, traces=None, lookahead=Tr
 
 # ------------------------------------------------------------------ K2b (look-ahead)
 LOOKAHEAD_T_CAP = 512     # candidates kept per shard and pass
-LOOKAHEAD_J_CAP = 16      # centres applied by one fused pass at most
+LOOKAHEAD_J_CAP = 16      # centres applied by one fused pass at most (fewer for wide frames: they
+                          # share 17 KB of shared memory next to the cp.async frame ring)
 CENTERS_HEADER = 32       # sizeof(CentersHeader)
 
 
@@ -141,8 +142,10 @@ def lookahead_supported(data, metric):
 class LookaheadState(object):
     """Per-shard buffers of the look-ahead k-centers (csrc/kcenters_lookahead.cu)."""
 
-    def __init__(self, data, metric, row_offset=0, t_cap=LOOKAHEAD_T_CAP, j_cap=LOOKAHEAD_J_CAP):
+    def __init__(self, data, metric, row_offset=0, t_cap=LOOKAHEAD_T_CAP, j_cap=None):
         _lib.require_gpu()
+        if j_cap is None:
+            j_cap = max(1, min(LOOKAHEAD_J_CAP, (17 * 1024) // (4 * int(data.shape[1]))))
         lib = _lib.load()
         self.data = data
         self.metric = _lib.metric_id(metric)

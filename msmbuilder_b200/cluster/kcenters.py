@@ -83,8 +83,10 @@ class _KCenters(ClusterMixin, TransformerMixin):
                                                 traces=traces)
         cluster_ids = ids.cpu().numpy()
         self.cluster_ids_ = [int(c) for c in cluster_ids]
-        self.labels_ = labels.cpu().numpy().astype(int)
-        self.distances_ = distances.cpu().numpy()
+        from .. import _device as dev
+        import torch
+        self.labels_ = dev.to_host(labels, torch.int64)       # == .astype(int) of the reference dtype
+        self.distances_ = dev.to_host(distances)
         centers = data[ids]
         self.cluster_centers_ = centers.cpu().numpy()
         # float64 sum on the device, fixed tree order (reference: np.sum on the host)
@@ -104,7 +106,8 @@ class _KCenters(ClusterMixin, TransformerMixin):
             if cent.dtype != data.dtype:
                 raise TypeError('X and y must be both float32 or float64')
             labels, _, _ = K.assign_nearest(data, cent, self.metric)
-        return labels.cpu().numpy().astype(np.intp)
+        from .. import _device as dev
+        return dev.to_host(labels, torch.int64)
 
     def fit_predict(self, X, y=None):
         return self.fit(X, y).labels_

@@ -20,6 +20,12 @@ from .base import MultiSequenceClusterMixin
 from .kcenters import _prepare
 from ..base import BaseEstimator
 
+
+def _to_host_intp(labels):
+    import torch
+    from .._device import to_host
+    return to_host(labels, torch.int64)
+
 __all__ = ['KMedoids']
 
 
@@ -94,7 +100,7 @@ class _KMedoids(ClusterMixin, TransformerMixin):
             if cent.dtype != data.dtype:
                 raise TypeError('X and y must be both float32 or float64')
             labels, _, _ = K.assign_nearest(data, cent, self.metric)
-        return labels.cpu().numpy().astype(np.intp)
+        return _to_host_intp(labels)
 
     def fit_predict(self, X, y=None):
         return self.fit(X, y).labels_

@@ -23,6 +23,12 @@ from .kcenters import _prepare
 from ..base import BaseEstimator
 from .. import _lib
 
+
+def _to_host_intp(labels):
+    import torch
+    from .._device import to_host
+    return to_host(labels, torch.int64)
+
 __all__ = ['MiniBatchKMedoids']
 
 
@@ -121,7 +127,7 @@ class _MiniBatchKMedoids(ClusterMixin, TransformerMixin):
             labels, _, inertia = K.rmsd_assign_nearest(data, traces, centers, traces[idx].contiguous())
         else:
             labels, _, inertia = K.assign_nearest(data, centers, self.metric)
-        self.labels_ = labels.cpu().numpy().astype(np.intp)
+        self.labels_ = _to_host_intp(labels)
         self.inertia_ = float(inertia)
         return self
 
@@ -138,7 +144,7 @@ class _MiniBatchKMedoids(ClusterMixin, TransformerMixin):
             if cent.dtype != data.dtype:
                 raise TypeError('X and y must be both float32 or float64')
             labels, _, _ = K.assign_nearest(data, cent, self.metric)
-        return labels.cpu().numpy().astype(np.intp)
+        return _to_host_intp(labels)
 
     def fit_predict(self, X, y=None):
         return self.fit(X, y).labels_

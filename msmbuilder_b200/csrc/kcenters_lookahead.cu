@@ -33,6 +33,7 @@
 namespace msmb {
 
 static constexpr int kThreads = 256;
+static constexpr int kStages = 3;            // per-warp frame ring of the fused passes (4 KB per stage)
 static constexpr long long kNoRow = 0x7fffffffffffffffLL;
 
 struct LaneCand {           // one per (group, frame slot) of the fused pass
@@ -120,13 +121,14 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
 {
     typedef Metric<METRIC, float> M;
     constexpr int V = R * JB;                        // float32 sums per group and chunk
+    constexpr int STAGES = kStages;                  // cp.async ring depth of the fused passes
     extern __shared__ float4 s_c[];                  // [J rounded up to JB][d / 4], NEGATED
     const int d4 = d >> 2;
     {
         // stored negated: x + (-c) is x - c bit for bit, and the float32 filter can then use the
         // packed f32x2 add / fma of sm_100 (two elements per instruction); the padding centres of
         // the last chunk are copies of the last real one and never looked at
-        const int Jpad = (J + JB - 1) / JB * JB;
+        const int Jpad = (J + JB - 1) / JB * JB;      // (recomputed below: this block is a scope)
         const float4 *c4 = reinterpret_cast<const float4 *>(centers);
         for (int i = threadIdx.x; i < Jpad * d4; i += blockDim.x) {
             const int jc = i / d4;
@@ -169,6 +171,42 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
 
     const long long stride_j = NG * ld4;
     const float4 *pfull = X4 + gid * ld4 + lane_in_group;
+
+    // Fused passes are compute heavy (J float32 distances per frame): the frames of the next
+    // STAGES - 1 iterations are already on their way into a per-warp shared-memory ring
+    // (cp.async.cg, 16 bytes per lane and request, each lane reads back only what it wrote), so
+    // HBM latency overlaps the arithmetic without holding the data in registers.
+    const int Jpad = (J + JB - 1) / JB * JB;
+    float4 *my_ring = s_c + (size_t)Jpad * d4 + (size_t)(threadIdx.x >> 5) * (STAGES * R * ITERS * 32) +
+                      (threadIdx.x & 31);
+    int stage_c = 0, stage_p = 0;                    // ring slot being consumed / produced
+    long long it_p = 0;                              // next iteration to prefetch
+    const float4 *ppre = pfull;
+    auto prefetch = [&]() {
+        if ((it_p * R) * NG + warp_gid0 < n) {       // warp uniform: this iteration exists
+            const bool full = (it_p * R + R - 1) * NG + warp_gid0 + (32 / G) <= n;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const long long row = (it_p * R + j) * NG + gid;
+                const float4 *p = full ? ppre + j * stride_j
+                                       : X4 + (row < n ? row : n - 1) * ld4 + lane_in_group;
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(
+                        my_ring + (stage_p * (R * ITERS) + j * ITERS + i) * 32);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(p + i * G) : "memory");
+                }
+            }
+            ppre += R * stride_j;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty: keeps the count uniform)
+        ++it_p;
+        if (++stage_p == STAGES) stage_p = 0;
+    };
+    if (!FIRST) {
+#pragma unroll 1
+        for (int s = 0; s < STAGES - 1; ++s) prefetch();
+    }
     auto iteration = [&](long long it, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         long long rr[R];
@@ -176,10 +214,16 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             rr[j] = (it * R + j) * NG + gid;
-            const long long rc = (FULL || rr[j] < n) ? rr[j] : n - 1;
-            const float4 *p = FULL ? pfull + j * stride_j : X4 + rc * ld4 + lane_in_group;
+            if (FIRST) {
+                const long long rc = (FULL || rr[j] < n) ? rr[j] : n - 1;
+                const float4 *p = FULL ? pfull + j * stride_j : X4 + rc * ld4 + lane_in_group;
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i) x[j][i] = ldg_stream(p + i * G);
+                for (int i = 0; i < ITERS; ++i) x[j][i] = ldg_stream(p + i * G);
+            } else {
+                // staged by cp.async STAGES - 1 iterations ago (lane-private slots: no barrier)
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i) x[j][i] = my_ring[(stage_c * (R * ITERS) + j * ITERS + i) * 32];
+            }
         }
         long long myrow = -1;
 #pragma unroll
@@ -277,13 +321,28 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
             }
         }
     };
+    auto stage_in = [&]() {          // make iteration `it`'s frames visible, keep STAGES - 1 in flight
+        if (!FIRST) {
+            prefetch();
+            asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 1) : "memory");
+        }
+    };
+    auto stage_out = [&]() {
+        if (!FIRST && ++stage_c == STAGES) stage_c = 0;
+    };
     long long it = 0;
     for (; (it * R + R - 1) * NG + warp_gid0 + (32 / G) <= n; ++it) {
+        stage_in();
         iteration(it, std::true_type());
+        stage_out();
         pfull += R * stride_j;
     }
-    for (; (it * R) * NG + warp_gid0 < n; ++it)
+    for (; (it * R) * NG + warp_gid0 < n; ++it) {
+        stage_in();
         iteration(it, std::false_type());
+        stage_out();
+    }
+    if (!FIRST) asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     if (owner) {
         LaneCand *out = reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader));
@@ -587,9 +646,10 @@ extern "C" int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int6
 #define MSMB_MULTI(METRIC, I, RR, F, JBV)                                                         \
     do {                                                                                          \
         auto kern = kcenters_multi_pass_kernel<METRIC, I, RR, F, JBV>;                            \
-        const size_t smem = (size_t)((n_centers + JBV - 1) / JBV * JBV) * d * sizeof(float);      \
-        MSMB_REQUIRE(smem <= 200 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
-                     "shared memory", n_centers, d);                                              \
+        const size_t smem = (size_t)((n_centers + JBV - 1) / JBV * JBV) * d * sizeof(float) +     \
+            ((F) ? 0 : (size_t)(kThreads / 32) * kStages * RR * I * 32 * sizeof(float4));         \
+        MSMB_REQUIRE(smem <= 113 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
+                     "the shared memory of two resident blocks", n_centers, d);                   \
         if (smem > 48 * 1024)                                                                     \
             MSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                            (int)smem));                                           \

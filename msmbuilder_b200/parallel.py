@@ -253,8 +253,9 @@ def kcenters_fit_sharded(est, local_sequences, row_offset, n_total, group=None):
     es = data.element_size()
     cent = ring[:k, CAND_HEADER:CAND_HEADER + row_elems * es].contiguous().view(data.dtype)
     est.cluster_centers_ = cent.reshape((k,) + tuple(data.shape[1:])).cpu().numpy()
-    est.labels_ = store.split(labels.cpu().numpy().astype(int))
-    est.distances_ = store.split(distances.cpu().numpy())
+    from ._device import to_host
+    est.labels_ = store.split(to_host(labels, torch.int64))
+    est.distances_ = store.split(to_host(distances))
     local_sum = distances.sum().reshape(1)
     _, ws = world()
     if ws > 1:
