@@ -152,13 +152,10 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
     const int vsel = FIRST ? 0 : lane_in_group / (G / V);
     const int jjsel = FIRST ? 0 : vsel - fsel * JB;
     const bool owner = (lane_in_group & (lanes_per_f - 1)) == 0;
-    // lanes of this warp that hold value index q of their group
-    auto slot_mask = [&](int q) -> unsigned {
-        const int w = G / V;
-        unsigned m = ((w >= 32) ? 0xffffffffu : ((1u << w) - 1u)) << (q * w);
-        for (int g = G; g < 32; g <<= 1) m |= m << g;
-        return m;
-    };
+    // lanes per reduction slot (a power of two) as a shift and as a mask of that many low bits
+    int slot_shift = 0;
+    while ((1 << slot_shift) < G / V) ++slot_shift;
+    const unsigned slot_lanes = (G / V >= 32) ? 0xffffffffu : ((1u << (G / V)) - 1u);
 
     double v1 = -INFINITY, v2 = -INFINITY;
     long long i1 = kNoRow;
@@ -180,14 +177,14 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
     float4 *my_ring = s_c + (size_t)Jpad * d4 + (size_t)(threadIdx.x >> 5) * (STAGES * R * ITERS * 32) +
                       (threadIdx.x & 31);
     int stage_c = 0, stage_p = 0;                    // ring slot being consumed / produced
-    long long it_p = 0;                              // next iteration to prefetch
     const float4 *ppre = pfull;
+    long long prow = 0;                              // it_p * R * NG
     auto prefetch = [&]() {
-        if ((it_p * R) * NG + warp_gid0 < n) {       // warp uniform: this iteration exists
-            const bool full = (it_p * R + R - 1) * NG + warp_gid0 + (32 / G) <= n;
+        if (prow + warp_gid0 < n) {                  // warp uniform: this iteration exists
+            const bool full = prow + (long long)(R - 1) * NG + warp_gid0 + (32 / G) <= n;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                const long long row = (it_p * R + j) * NG + gid;
+                const long long row = prow + j * NG + gid;
                 const float4 *p = full ? ppre + j * stride_j
                                        : X4 + (row < n ? row : n - 1) * ld4 + lane_in_group;
 #pragma unroll
@@ -200,12 +197,19 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
             ppre += R * stride_j;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty: keeps the count uniform)
-        ++it_p;
+        prow += (long long)R * NG;
         if (++stage_p == STAGES) stage_p = 0;
     };
     if (!FIRST) {
 #pragma unroll 1
         for (int s = 0; s < STAGES - 1; ++s) prefetch();
+    }
+    long long rbase = gid;                           // it * R * NG + gid, advanced per iteration
+    const long long next_off = (long long)(R + fsel) * NG;
+    double cur_pre = INFINITY;                       // running minimum of the NEXT iteration's frame
+    if (!FIRST) {
+        const long long r0 = (long long)fsel * NG + gid;
+        if (r0 < n) cur_pre = __ldcg(dist + r0);
     }
     auto iteration = [&](long long it, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
@@ -213,7 +217,7 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
         float4 x[R][ITERS];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            rr[j] = (it * R + j) * NG + gid;
+            rr[j] = rbase + j * NG;                  // == (it * R + j) * NG + gid
             if (FIRST) {
                 const long long rc = (FULL || rr[j] < n) ? rr[j] : n - 1;
                 const float4 *p = FULL ? pfull + j * stride_j : X4 + rc * ld4 + lane_in_group;
@@ -253,7 +257,14 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
                 lab = label0;
             }
         } else {
-            if (myrow >= 0) cur = __ldcg(dist + myrow);
+            // this frame's running minimum was requested one iteration ago (its load latency
+            // would otherwise sit in front of every iteration: 30 % of the stall samples), the
+            // next one is requested now
+            if (myrow >= 0) cur = cur_pre;
+            {
+                const long long rn = rbase + next_off;       // == ((it + 1) * R + fsel) * NG + gid
+                cur_pre = rn < n ? __ldcg(dist + rn) : INFINITY;
+            }
             // float upper bound of what the float32 sums are compared with
             float bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? cur * cur : cur);
             for (int j0 = 0; j0 < J; j0 += JB) {
@@ -281,27 +292,37 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
                 const bool need = myrow >= 0 && (j0 + jjsel) < J && !(tot * one_minus_eps >= bound);
                 const unsigned need_mask = __ballot_sync(0xffffffffu, need);
                 if (need_mask == 0) continue;
-                for (int jj = 0; jj < JB; ++jj) {
+                // needed slots of ANY group of the warp, lowest first: slot order is (frame, centre),
+                // so every frame meets its centres in ascending order (ties keep the first, like
+                // the reference's strict '<' over k sequential passes)
+                unsigned m = need_mask;
+                for (int g = G; g < 32; g <<= 1) m |= m >> g;
+                if (G < 32) m &= (1u << G) - 1u;
+                while (m) {
+                    const int q = (__ffs(m) - 1) >> slot_shift;
+                    m &= ~(slot_lanes << (q << slot_shift));
+                    const int f = q / JB, jj = q - f * JB;
+                    const float4 *cn = s_c + (j0 + jj) * d4 + lane_in_group;
+                    double a = 0.0, b = 0.0;
 #pragma unroll
-                    for (int f = 0; f < R; ++f) {
-                        if (!(need_mask & slot_mask(f * JB + jj))) continue;     // warp uniform
-                        double a = 0.0, b = 0.0;
+                    for (int ff = 0; ff < R; ++ff) {
+                        if (ff != f) continue;                  // warp uniform; x[] stays in registers
 #pragma unroll
                         for (int i = 0; i < ITERS; ++i) {
-                            const float4 c = s_c[(j0 + jj) * d4 + lane_in_group + i * G];
-                            M::acc(a, b, x[f][i].x, -c.x);
-                            M::acc(a, b, x[f][i].y, -c.y);
-                            M::acc(a, b, x[f][i].z, -c.z);
-                            M::acc(a, b, x[f][i].w, -c.w);
+                            const float4 c = cn[i * G];
+                            M::acc(a, b, x[ff][i].x, -c.x);
+                            M::acc(a, b, x[ff][i].y, -c.y);
+                            M::acc(a, b, x[ff][i].z, -c.z);
+                            M::acc(a, b, x[ff][i].w, -c.w);
                         }
-                        a = group_combine<false>(a, G);
-                        if (fsel == f && myrow >= 0) {
-                            const double dv = M::fin(a, 0.0, d);
-                            if (dv < cur) {                     // strict: kcenters.py:93
-                                cur = dv;
-                                lab = label0 + j0 + jj;
-                                bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? a : dv);
-                            }
+                    }
+                    a = group_combine<false>(a, G);
+                    if (fsel == f && myrow >= 0) {
+                        const double dv = M::fin(a, 0.0, d);
+                        if (dv < cur) {                         // strict: kcenters.py:93
+                            cur = dv;
+                            lab = label0 + j0 + jj;
+                            bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? a : dv);
                         }
                     }
                 }
@@ -331,16 +352,21 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
         if (!FIRST && ++stage_c == STAGES) stage_c = 0;
     };
     long long it = 0;
-    for (; (it * R + R - 1) * NG + warp_gid0 + (32 / G) <= n; ++it) {
+    const long long full_span = (long long)(R - 1) * NG + warp_gid0 + (32 / G);   // + it * R * NG <= n: full
+    const long long step_rows = (long long)R * NG;
+    long long wrow = 0;                              // it * R * NG
+    for (; wrow + full_span <= n; ++it, wrow += step_rows) {
         stage_in();
         iteration(it, std::true_type());
         stage_out();
         pfull += R * stride_j;
+        rbase += step_rows;
     }
-    for (; (it * R) * NG + warp_gid0 < n; ++it) {
+    for (; wrow + warp_gid0 < n; ++it, wrow += step_rows) {
         stage_in();
         iteration(it, std::false_type());
         stage_out();
+        rbase += step_rows;
     }
     if (!FIRST) asm volatile("cp.async.wait_group 0;" ::: "memory");
 
