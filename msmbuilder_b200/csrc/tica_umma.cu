@@ -71,7 +71,11 @@ struct UmmaParams {
     int slab_tiles;
     int passes;                   // tf32: 3 = hi/lo split, 1 = plain; bf16: 3 = h/m products, 6 = h/m/l
     int collector;                // reuse the A operand through the collector buffer
-    int flush_red;                // drain with red.global.add.f64 instead of load + add + store
+    int flush_red;                // 2: red.f32 into float32 second-level partials, folded into the float64 ones
+                                  // every `fold_every` slabs; 1: red.f64 straight into the float64 partials;
+                                  // 0: load + add + store
+    float *partials32;            // [n_pairs][2][col][row] float32 second level (flush_red == 2)
+    int fold_every;
     uint32_t h_add, h_mask;       // fp16 engine: integer rounding of the h component (significand width)
     int dbg_mode;                 // MSMB200_UMMA_DBGMODE (timing experiments, wrong results): 1 = converters
                                   // skip their loads/stores, 2 = flush skips its drain, 4 = one MMA per K step
@@ -256,10 +260,11 @@ __device__ __forceinline__ void flush_prefetch(const UmmaParams &P, int pair, ui
 // dealt round-robin to the `nparts` warps that share a quarter.
 __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, int pair,
                                             uint32_t cta_rank, int quarter, int part, int nparts,
-                                            int lane, uint32_t &absmax)
+                                            int lane, uint32_t &absmax, bool fold)
 {
     const int row = UM_F * cta_rank + quarter * 32 + lane;
     double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
+    float *pc32 = P.partials32 + (size_t)pair * 2 * UM_D * UM_D + row;
 #pragma unroll 1
     for (int c0 = 32 * part; c0 < 512; c0 += 32 * nparts) {
         uint32_t v[32];
@@ -267,13 +272,28 @@ __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, 
         // element (row, col) of matrix m lives at ((m*256 + col) * 256 + row); c0 runs over
         // [C_tau cols 0..255 | C_00 cols 0..255] = m*256 + col directly
         double *dst = pc + (size_t)c0 * UM_D;
+        if (P.flush_red == 2) {
+            // float32 second level: half the atomic sectors of the float64 reduction, and the
+            // 38 MB of all pairs stay L2 resident between drains (the 77 MB of float64 partials did
+            // not: 47 GB of DRAM writes per 50M frames).  <= fold_every slabs are summed here with
+            // round-to-nearest float adds (unbiased, ~1e-7) before they move on to float64.
+            float *d32 = pc32 + (size_t)c0 * UM_D;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                absmax = max(absmax, v[j] & 0x7FFFFFFFu);      // Inf / NaN sort above every finite value
+                asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;"
+                             :: "l"(d32 + (size_t)j * UM_D), "f"(__uint_as_float(v[j])) : "memory");
+            }
+            continue;
+        }
         if (P.flush_red) {
             // fire-and-forget reductions at L2: no read round trip, half the SM <-> L2 bytes
             // (this warp is the only writer of these addresses, so the sums stay deterministic)
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                absmax = max(absmax, v[j] & 0x7FFFFFFFu);      // Inf / NaN sort above every finite value
+                absmax = max(absmax, v[j] & 0x7FFFFFFFu);
                 asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;"
                              :: "l"(dst + (size_t)j * UM_D), "d"((double)__uint_as_float(v[j])) : "memory");
             }
@@ -290,6 +310,32 @@ __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, 
                 absmax = max(absmax, v[q * 8 + j] & 0x7FFFFFFFu);
                 __stcg(dst + (size_t)(q * 8 + j) * UM_D,
                        cur[j] + (double)__uint_as_float(v[q * 8 + j]));
+            }
+        }
+    }
+    if (P.flush_red == 2 && fold) {
+        // move this warp's share of the float32 level into the float64 partials and clear it.  The
+        // warp is the only one that ever touches these addresses; its own reductions above are
+        // ordered before these loads (same thread, same address, gpu scope).
+#pragma unroll 1
+        for (int c0 = 32 * part; c0 < 512; c0 += 32 * nparts) {
+            float *d32 = pc32 + (size_t)c0 * UM_D;
+            double *dst = pc + (size_t)c0 * UM_D;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float s[16];
+                double cur[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];"
+                                 : "=f"(s[j]) : "l"(d32 + (size_t)(q * 16 + j) * UM_D) : "memory");
+                    cur[j] = __ldcg(dst + (size_t)(q * 16 + j) * UM_D);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __stcg(dst + (size_t)(q * 16 + j) * UM_D, cur[j] + (double)s[j]);
+                    __stcg(d32 + (size_t)(q * 16 + j) * UM_D, 0.f);
+                }
             }
         }
     }
@@ -535,7 +581,8 @@ tica_umma_kernel(const UmmaParams P)
             sumA += (double)sAh + (double)sAl;           // the tensor pipe is idle here: FP64 is cheap
             sAh = sAl = 0.f;
             if (!(P.dbg_mode & 2))
-                flush_share(P, tmem, pair, cta_rank, cw & 3, cw >> 2, 4, lane, absmax);
+                flush_share(P, tmem, pair, cta_rank, cw & 3, cw >> 2, 4, lane, absmax,
+                            ((next_flush + 1) % P.fold_every) == 0 || next_flush + 1 == n_slabs);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0 && next_flush + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
@@ -920,7 +967,8 @@ static size_t ws_fixed_bytes(int D)
 size_t tica_umma_workspace_bytes(int D)
 {
     if (D > UM_D || (D % 32) != 0) return 0;
-    return ws_fixed_bytes(UM_D) + sizeof(double) * 2 * (size_t)UM_D * UM_D * UM_MAX_PAIRS;
+    // fixed part | float64 partials | float32 second-level partials
+    return ws_fixed_bytes(UM_D) + (sizeof(double) + sizeof(float)) * 2 * (size_t)UM_D * UM_D * UM_MAX_PAIRS;
 }
 
 static int env_int(const char *name, int dflt)
@@ -997,7 +1045,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (n_pairs > UM_MAX_PAIRS) n_pairs = UM_MAX_PAIRS;
     if (tiles < n_pairs) n_pairs = (int)(tiles > 0 ? tiles : 1);
     const size_t DD = (size_t)UM_D * UM_D;          // scratch is always 256 wide
-    const size_t need = ws_fixed_bytes(UM_D) + sizeof(double) * 2 * DD * n_pairs;
+    const size_t need = ws_fixed_bytes(UM_D) + (sizeof(double) + sizeof(float)) * 2 * DD * n_pairs;
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
         set_error("tica_accumulate: workspace too small or misaligned (%zu < %zu); size it with "
                   "msmb200_tica_workspace_bytes", workspace_bytes, need);
@@ -1034,6 +1082,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const size_t w_E = woff; woff = align_up(woff + sizeof(double) * 4 * DD, 256);
     const size_t w_es = woff; woff = align_up(woff + sizeof(double) * 3 * UM_D, 256);
     const size_t w_part = woff; woff += sizeof(double) * 2 * DD * n_pairs;
+    const size_t w_part32 = woff; woff += sizeof(float) * 2 * DD * n_pairs;
     MSMB_CUDA(cudaMemsetAsync(wsb + w_flag, 0, woff - w_flag, st));
 
     std::vector<CUtensorMap> mA(n_seq), mB(n_seq);
@@ -1069,7 +1118,10 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (P.slab_tiles < 1) P.slab_tiles = 1;
     P.passes = f16 ? 3 : bf16 ? passes - 10 : passes;
     P.collector = env_int("MSMB200_UMMA_COLLECTOR", 1);
-    P.flush_red = env_int("MSMB200_UMMA_FLUSH_RED", 1);
+    P.flush_red = env_int("MSMB200_UMMA_FLUSH_RED", 2);
+    P.partials32 = reinterpret_cast<float *>(wsb + w_part32);
+    P.fold_every = env_int("MSMB200_UMMA_FOLD_EVERY", 16);
+    if (P.fold_every < 1) P.fold_every = 1;
     P.dbg_mode = env_int("MSMB200_UMMA_DBGMODE", 0);
     {
         int hb = env_int("MSMB200_UMMA_HBITS", 11);      // significant bits kept in h (11 = all of fp16)
