@@ -424,6 +424,23 @@ def run_ours(args):
                "algorithmic_flops_per_launch": flops_tica, "ms_per_launch": tica_s * 1e3,
                "issued_mma_products": issued, "issued_frac": issued * tica_ach / tf32_peak,
                "share_of_step": tica_s / (ms_per_step / 1e3)}
+    # DRAM traffic per launch from the committed ncu --set full captures (profiles/ncu_traffic.json),
+    # only when this run has the captured shape; otherwise null
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr["frames_per_gpu"] == n_total // ws and tr["features"] == D:
+            if pass_ms and not args.no_lookahead:
+                per = [tr["kcenters_multi_pass_kernel"]["first" if c == 1 and i == 0 else "fused"]
+                       for i, c in enumerate(pass_centres[-n_passes:])]
+                roof_k2["traffic"] = float(np.mean(per))
+            elif args.no_lookahead:
+                roof_k2["traffic"] = tr.get("kcenters_pass_fast_kernel")
+            if args.engine in ("auto", "umma_3xf16"):
+                roof_k1["traffic"] = tr.get("tica_umma_kernel_f16")
+            roof_k1["traffic_source"] = roof_k2["traffic_source"] = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     dominant = roof_k2 if kc_s >= tica_s else roof_k1
 
     line = {

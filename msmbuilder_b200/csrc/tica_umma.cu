@@ -58,6 +58,7 @@ constexpr int UM_CONV_WARPS = 16;               // converter warps per CTA (4 pe
                                                 // conversion is latency bound with fewer)
 constexpr int UM_THREADS = 32 * (4 + UM_CONV_WARPS);   // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4.. converters
 constexpr int UM_FLUSH_WARPS = UM_CONV_WARPS;   // the converters also drain TMEM (4 per lane quarter)
+constexpr int UM_EDGE_SLOTS = 8;                // blocks (= output slots) of the float64 edge kernel per row band
 constexpr int UM_SLAB_TILES_DEFAULT = 32;       // 1024 frames of fp32 TMEM accumulation per flush
 
 struct UmmaParams {
@@ -85,7 +86,7 @@ struct UmmaParams {
     const int *run_if;            // if non-NULL the kernel only runs when *run_if != 0 (rescue launch)
     double *partials;             // [n_pairs][2][col][row]  (C_tau', C_00'), column-major so a
                                   // warp (32 rows) touches 256 contiguous bytes per column
-    double *sums;                 // [2][D]  (S_0', S_tau')  atomically accumulated
+    double *sums;                 // [n_pairs][D]  S_0' of every pair (plain stores, summed in order by finalize)
     long long *dbg;               // optional cycle counters of pair 0 (MSMB200_UMMA_DEBUG=1), else NULL
 };
 
@@ -737,10 +738,17 @@ tica_umma_kernel(const UmmaParams P)
         while (next_flush < n_slabs) help_flush();
         if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync;
                       P.dbg[8] = d_flush; P.dbg[9] = n_slabs; }
-        if (my_tiles > 0) {
-            const int f = UM_F * cta_rank + f_local;
+        // column sums without atomics (bit-reproducible runs): the 4 warps that share a feature
+        // combine through shared memory in a fixed order (the raw ring is idle by now: every TMA
+        // load of this CTA has landed and been converted), one plain store per pair and feature
+        {
+            double *s_sum = reinterpret_cast<double *>(raw_ring);        // [4][UM_F]
             sumA += (double)sAh + (double)sAl;
-            atomicAdd(&P.sums[f], sumA / (double)sc);
+            s_sum[kq * UM_F + f_local] = sumA / (double)sc;
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * UM_CONV_WARPS) : "memory");
+            if (kq == 0)
+                P.sums[(size_t)pair * UM_D + UM_F * cta_rank + f_local] =
+                    ((s_sum[f_local] + s_sum[UM_F + f_local]) + s_sum[2 * UM_F + f_local]) + s_sum[3 * UM_F + f_local];
         }
         // fp16 tops out at 65504: a scaled value beyond it became Inf, and Inf (or the NaN of
         // Inf * 0) is then in the accumulators of its feature -- the whole call is redone by the
@@ -824,6 +832,10 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
         for (int u = 0; u < 16; ++u) acc[m][u] = 0.0;
     double s0 = 0.0, shead = 0.0, stail = 0.0; // column `tid` sums (only blockIdx.y == 0 publishes)
 
+    // block x owns the sequences x, x + gridDim.x, ... and writes ITS slot of E / es with plain
+    // stores (slots are pre-zeroed; finalize adds them in slot order: bit-reproducible)
+    E += (size_t)blockIdx.x * 4 * D * D;
+    es += (size_t)blockIdx.x * 3 * D;
     for (int s = blockIdx.x; s < n_seq; s += gridDim.x) {
         const float *X = seqs[s].base;
         const long long n = seqs[s].n;
@@ -867,11 +879,11 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
     for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int u = 0; u < 16; ++u)
-            if (tid < Dr) atomicAdd(&E[(size_t)m * D * D + (size_t)(i0 + u) * D + tid], acc[m][u]);
+            if (tid < Dr) E[(size_t)m * D * D + (size_t)(i0 + u) * D + tid] = acc[m][u];
     if (blockIdx.y == 0 && tid < Dr) {
-        atomicAdd(&es[tid], s0);
-        atomicAdd(&es[D + tid], s0 + stail - shead);
-        atomicAdd(&es[2 * D + tid], stail);
+        es[tid] = s0;
+        es[D + tid] = s0 + stail - shead;
+        es[2 * D + tid] = stail;
     }
 }
 
@@ -904,13 +916,34 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
         ctau *= inv;
         c00 *= inv;
     }
-    ctau += E[pidx];
-    c00 += E[DD + pidx];
-    const double ctt = c00 - E[2 * DD + pidx] + E[3 * DD + pidx];
+    // edge terms and column sums: fixed-order sums over the edge kernel's slots / the pairs
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    double esi[2] = {0.0, 0.0}, esj[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < UM_EDGE_SLOTS; ++c) {
+        const double *Ec = E + (size_t)c * 4 * DD;
+        const double *ec = es + (size_t)c * 3 * D;
+        e0 += Ec[pidx];
+        e1 += Ec[DD + pidx];
+        e2 += Ec[2 * DD + pidx];
+        e3 += Ec[3 * DD + pidx];
+        esi[0] += ec[i];
+        esi[1] += ec[D + i];
+        esj[0] += ec[j];
+        esj[1] += ec[D + j];
+        esj[2] += ec[2 * D + j];
+    }
+    double sum_i = 0.0, sum_j = 0.0;
+    for (int p = 0; p < n_pairs; ++p) {
+        sum_i += sums[(size_t)p * D + i];
+        sum_j += sums[(size_t)p * D + j];
+    }
+    ctau += e0;
+    c00 += e1;
+    const double ctt = c00 - e2 + e3;
     const double si = (double)shift[i], sj = (double)shift[j];
-    const double S0i = sums[i] + es[i], S0j = sums[j] + es[j];
+    const double S0i = sum_i + esi[0], S0j = sum_j + esj[0];
     // sum over the pair rows of x'_{t+lag} = the same sum of x'_t, minus the head rows, plus the tail rows
-    const double Sti = sums[i] + es[D + i], Stj = sums[j] + es[D + j];
+    const double Sti = sum_i + esi[1], Stj = sum_j + esj[1];
     const double Np = n_pairs_total;
     acc[idx] += ctau + S0i * sj + si * Stj + Np * si * sj;
     acc[RR + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
@@ -918,7 +951,7 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
     if (i == 0) {
         // vectors and counters (one thread per column j)
         const double S0 = S0j, St = Stj;
-        const double Sall = S0 + es[2 * D + j];       // all rows = pair rows + last `lag` rows
+        const double Sall = S0 + esj[2];              // all rows = pair rows + last `lag` rows
         acc[3 * RR + j] += S0 + Np * sj;
         acc[3 * RR + Dr + j] += St + Np * sj;
         acc[3 * RR + 2 * Dr + j] += Sall + n_obs * sj;
@@ -962,7 +995,7 @@ static constexpr int UM_MAX_PAIRS = 96;
 static size_t ws_fixed_bytes(int D)
 {
     const size_t DD = (size_t)D * D;
-    return 4096 + sizeof(double) * (2 * D + 4 * DD + 3 * D) + 1024;
+    return 4096 + sizeof(double) * ((size_t)UM_MAX_PAIRS * D + (size_t)UM_EDGE_SLOTS * (4 * DD + 3 * D)) + 1024;
 }
 size_t tica_umma_workspace_bytes(int D)
 {
@@ -1078,9 +1111,9 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const size_t w_shift = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
     const size_t w_scale = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
     const size_t w_flag = woff; woff = align_up(woff + sizeof(int), 256);       // zeroed with the rest
-    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * 2 * UM_D, 256);
-    const size_t w_E = woff; woff = align_up(woff + sizeof(double) * 4 * DD, 256);
-    const size_t w_es = woff; woff = align_up(woff + sizeof(double) * 3 * UM_D, 256);
+    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * (size_t)UM_MAX_PAIRS * UM_D, 256);
+    const size_t w_E = woff; woff = align_up(woff + sizeof(double) * UM_EDGE_SLOTS * 4 * DD, 256);
+    const size_t w_es = woff; woff = align_up(woff + sizeof(double) * UM_EDGE_SLOTS * 3 * UM_D, 256);
     const size_t w_part = woff; woff += sizeof(double) * 2 * DD * n_pairs;
     const size_t w_part32 = woff; woff += sizeof(float) * 2 * DD * n_pairs;
     MSMB_CUDA(cudaMemsetAsync(wsb + w_flag, 0, woff - w_flag, st));
@@ -1179,7 +1212,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         MSMB_LAUNCH_CHECK();
     }
     {
-        dim3 grid(n_seq < 64 ? n_seq : 64, D / 16);
+        dim3 grid(n_seq < UM_EDGE_SLOTS ? n_seq : UM_EDGE_SLOTS, D / 16);
         tica_umma_edges_kernel<<<grid, 256, 0, st>>>(
             reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq, ld, lag, D, d_shift,
             reinterpret_cast<double *>(wsb + w_E), reinterpret_cast<double *>(wsb + w_es));

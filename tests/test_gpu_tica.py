@@ -253,6 +253,21 @@ def test_umma_f16_engine_range_rescue():
     _assert_moments_close(d[1], d[0], 5e-6)
 
 
+@pytest.mark.parametrize("engine", ["umma_3xf16", "umma_6xbf16"])
+def test_umma_is_bit_reproducible(engine):
+    # no atomics on the result path: single-writer reductions, per-pair column sums and per-slot edge
+    # terms added in a fixed order -> two runs agree bit for bit
+    from msmbuilder_b200.decomposition import tICA
+    lens = [4001, 130, 9000, 777, 2048]
+    seqs = [s[:n] for s, n in zip(ar1_numpy(len(lens), 9000, 256, seed=27), lens)]
+    a = tICA(n_components=4, lag_time=10, engine=engine).fit(seqs)
+    for _ in range(3):
+        b = tICA(n_components=4, lag_time=10, engine=engine).fit(seqs)
+        for name in ("_outer_0_to_T_lagged", "_outer_0_to_TminusTau", "_outer_offset_to_T",
+                     "_sum_0_to_TminusTau", "_sum_tau_to_T", "_sum_0_to_T"):
+            np.testing.assert_array_equal(getattr(a, name), getattr(b, name))
+
+
 @pytest.mark.parametrize("D", [64, 96, 128, 224])
 def test_umma_narrow_feature_counts(D):
     # D = 32k < 256 rides the 256-wide tensor-core tiles (TMA zero-fills the missing feature blocks)
