@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 O=gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > $O/r1c_pytest_gpu.log 2>&1; echo "pytest exit $?" >> $O/r1c_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/r1c_smoke.log 2>&1; tail -1 $O/r1c_smoke.log
 tail -3 $O/r1c_pytest_gpu.log
 timeout 1200 python bench.py > $O/r1c_bench_1gpu.json 2> $O/r1c_bench_1gpu.err
 tail -c 1500 $O/r1c_bench_1gpu.json
