@@ -10,7 +10,7 @@ tail -c 1500 $O/r1c_bench_1gpu.json
 timeout 900 python bench.py --no-lookahead --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/r1c_bench_1gpu_no_lookahead.json 2>/dev/null
 timeout 900 python bench.py --engine umma_6xbf16 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/r1c_bench_1gpu_6xbf16.json 2>/dev/null
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/r1c_bench_reference.json 2>/dev/null
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r1c_launches_step.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:tica_|kcenters_|candidate_' -c 400 --csv --log-file $O/r1c_launches_step.csv \
    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $O/r1c_launches_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:kcenters_multi_pass --launch-skip 3 --launch-count 2 \
    -o $O/r1c_k2b_full -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $O/r1c_ncu_k2b.log 2>&1
