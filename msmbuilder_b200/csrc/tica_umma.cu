@@ -34,7 +34,10 @@
 //    one elected lane issues), w2 TMEM allocator, w4-19 converters: a thread owns one feature and
 //    8 frames of a tile -- gathers them with conflict-free 4-byte shared loads (the transpose),
 //    centres/scales/splits them, stores K-major 16-byte chunks; the same 16 warps drain TMEM
-//    (tcgen05.ld -> red.global.add.f64 into the pair's partials) between slabs.
+//    between slabs: tcgen05.ld -> red.global.add.f32 into the pair's float32 second-level partials
+//    (L2 resident), which each warp folds into its float64 partials every 16 slabs.
+//  * Bit-reproducible: every address of the partials has one writer, column sums and edge terms
+//    are stored per pair / per slot and added in a fixed order by tica_umma_finalize.
 //  * No FP64 instruction runs while the tensor pipe is busy: on B200 it stalls for hundreds of
 //    cycles (column sums are carried as float pairs and folded during the drain).
 #include "common.cuh"
