@@ -72,24 +72,41 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.
+
+    nvidia-smi needs a few hundred ms before its first sample, which is longer than a timed
+    region of a few steps on 8 GPUs: it is started before the warm-up, every sample carries a
+    timestamp, and only those inside [mark_begin, mark_end] count.  If the region is shorter than
+    the sampling period the warm-up samples (same kernels, same load) are used and `window` says so."""
 
     def __init__(self, device_index):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.idx = device_index
+        self.t_begin = self.t_end = None
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
 
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
@@ -102,9 +119,25 @@ class ClockSampler(object):
             self.proc.kill()
         try:
             rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
-            sm = [float(r[1]) for r in rows if len(r) >= 9]
-            pw = [float(r[3]) for r in rows if len(r) >= 9]
+            rows = [r for r in rows if len(r) >= 9]
+            window = "timed region"
+            if self.t_begin is not None and self.t_end is not None:
+                stamped = []
+                for r in rows:
+                    try:
+                        stamped.append((self._stamp(r[0]), r))
+                    except ValueError:
+                        pass
+                inside = [r for t, r in stamped if self.t_begin <= t <= self.t_end + 0.05]
+                if inside:
+                    rows = inside
+                else:       # region shorter than the sampling period: the warm-up ran the same kernels
+                    rows = [r for t, r in stamped if t <= self.t_end + 0.05] or rows
+                    window = "warm-up + timed region (timed region shorter than the sampling period)"
+            sm = [float(r[1]) for r in rows]
+            pw = [float(r[3]) for r in rows]
             out["samples"] = len(sm)
+            out["window"] = window
             if sm:
                 loaded = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
                 out["sm_mhz"] = float(np.median(loaded))
@@ -112,7 +145,7 @@ class ClockSampler(object):
                 out["power_w_max"] = max(pw)
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             for j, nm in enumerate(names):
-                if any(len(r) >= 9 and r[5 + j].strip().lower() == "active" for r in rows):
+                if any(r[5 + j].strip().lower() == "active" for r in rows):
                     out["reasons"].append(nm)
         except Exception as e:  # pragma: no cover
             out["error"] = str(e)
@@ -122,27 +155,6 @@ class ClockSampler(object):
             except OSError:
                 pass
         return out
-
-
-# ----------------------------------------------------------------------------- CPU arm
-def cpu_hot_path(seqs, lag, k, use_ref):
-    """The reference CPU path on host arrays: tICA accumulation in NumPy float64
-    (oracle port of tica.py:401-424, all BLAS threads) + k KCenters passes through
-    the reference's own single-threaded libdistance C++ (oracle/_ref) or its port.
-    Returns (seconds_tica, seconds_kcenters)."""
-    import warnings
-    from oracle.tica_oracle import TicaOracle
-    from oracle import cluster_oracle as co
-    from oracle import libdistance_oracle as lo
-    t0 = time.perf_counter()
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        TicaOracle(n_components=4, lag_time=lag).fit(seqs)
-    t1 = time.perf_counter()
-    X = np.concatenate(seqs)            # cluster/base.py:58 (the reference concatenates on the host)
-    co.kcenters_fit(X, k, "euclidean", random_state=0, impl="reference" if use_ref else "port")
-    t2 = time.perf_counter()
-    return t1 - t0, t2 - t1
 
 
 def host_sample(n_frames, seq_len, D, seed):
@@ -273,18 +285,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()             # before the warm-up: nvidia-smi takes a while to produce samples
     for _ in range(args.warmup):
         step(False)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.msmb200_launch_count()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     profiling = os.environ.get("MSMB_PROFILE") == "1"     # ncu --profile-from-start off
     if profiling:
         torch.cuda.profiler.start()
+    sampler.mark_begin()
     t_start.record()
     state["time_passes"] = True          # CUDA events around every fused K2 launch (look-ahead path)
     pass_ms, pass_centres = [], []
@@ -299,6 +312,7 @@ def run_ours(args):
             pass_centres.append(nc)
     t_stop.record()
     barrier()
+    sampler.mark_end()
     if profiling:
         torch.cuda.profiler.stop()
     launches = int(lib.msmb200_launch_count() - launches0)
