@@ -157,6 +157,27 @@ class ClockSampler(object):
         return out
 
 
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_hot_path(seqs, lag, k, use_ref):
+    """The reference CPU path on host arrays: tICA accumulation in NumPy float64
+    (oracle port of tica.py:401-424, all BLAS threads) + k KCenters passes through
+    the reference's own single-threaded libdistance C++ (oracle/_ref) or its port.
+    Returns (seconds_tica, seconds_kcenters)."""
+    import warnings
+    from oracle.tica_oracle import TicaOracle
+    from oracle import cluster_oracle as co
+    from oracle import libdistance_oracle as lo
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        TicaOracle(n_components=4, lag_time=lag).fit(seqs)
+    t1 = time.perf_counter()
+    X = np.concatenate(seqs)            # cluster/base.py:58 (the reference concatenates on the host)
+    co.kcenters_fit(X, k, "euclidean", random_state=0, impl="reference" if use_ref else "port")
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
 def host_sample(n_frames, seq_len, D, seed):
     """Seeded host sample of the same workload (device-generated when a GPU exists)."""
     n_seq = max(1, n_frames // seq_len)
