@@ -289,7 +289,10 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
                 }
                 const float tot = group_reduce_split_f32<V>(s, G, lane_in_group);
                 // certainly not below the current minimum -> the reference's mask is false
-                const bool need = myrow >= 0 && (j0 + jjsel) < J && !(tot * one_minus_eps >= bound);
+                // (the relative margin needs float32's normal range: a sum below 1e-30, i.e. frames
+                //  closer than 1e-15, always goes to the refine step)
+                const bool need = myrow >= 0 && (j0 + jjsel) < J &&
+                                  !(tot * one_minus_eps >= bound && tot >= 1e-30f);
                 const unsigned need_mask = __ballot_sync(0xffffffffu, need);
                 if (need_mask == 0) continue;
                 // needed slots of ANY group of the warp, lowest first: slot order is (frame, centre),
