@@ -38,6 +38,21 @@ def test_version_and_sizes():
     assert lib.msmb200_candidate_bytes(3, _lib.F64) % 16 == 0
 
 
+def test_lookahead_host_helpers():
+    # shape gate and blob sizes of the look-ahead k-centers (no device needed)
+    lib = _lib.load()
+    eu, sq, cb = (_lib.VECTOR_METRICS.index(m) for m in ("euclidean", "sqeuclidean", "cityblock"))
+    for d, ok in ((256, 1), (128, 1), (64, 1), (16, 1), (512, 1), (5, 0), (12, 0), (8, 0), (1024, 0)):
+        assert lib.msmb200_kcenters_lookahead_supported(d, d, _lib.F32, eu) == ok, d
+    assert lib.msmb200_kcenters_lookahead_supported(256, 256, _lib.F32, sq) == 1
+    assert lib.msmb200_kcenters_lookahead_supported(256, 256, _lib.F32, cb) == 0      # other metrics: one pass per centre
+    assert lib.msmb200_kcenters_lookahead_supported(256, 256, _lib.F64, eu) == 0
+    assert lib.msmb200_kcenters_lookahead_supported(256, 258, _lib.F32, eu) == 0      # rows not 16-byte aligned
+    assert lib.msmb200_kcenters_set_bytes(256, 512) == 32 + 512 * 16 + 512 * 256 * 4
+    assert lib.msmb200_kcenters_centers_bytes(256, 16) == 32 + 16 * 8 + 16 * 256 * 4
+    assert lib.msmb200_kcenters_lane_bytes(0) >= 32 + 32 * 148 * 8 * 256
+
+
 def test_no_cpu_fallback_is_loud():
     import torch
     if torch.cuda.is_available():
