@@ -114,9 +114,20 @@ def check(status, what=""):
             what or "libmsmb200 call", status, msg.decode(errors="replace") if msg else ""))
 
 
+_NVTX = os.environ.get("MSMB200_NVTX") == "1"     # NVTX range per C-ABI call (for nsys / ncu --nvtx timelines)
+
+
 def call(name, *args):
     fn = getattr(load(), name)
-    check(fn(*args), name)
+    if not _NVTX:
+        check(fn(*args), name)
+        return
+    import torch
+    torch.cuda.nvtx.range_push(name)
+    try:
+        check(fn(*args), name)
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 def metric_id(metric):
