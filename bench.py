@@ -19,8 +19,9 @@ the hot path over all frames:
 
 `value` = total frames / step time with the frames already resident in HBM
 (CUDA events, max over ranks).  `e2e` = the same two estimator calls through the
-public Python API on HOST (pinned) arrays: H2D of the frames and D2H of the
-results inside the timed region, on a bounded number of frames (`e2e.frames`).
+public Python API on HOST arrays (pageable NumPy, what a Pipeline caller holds):
+H2D of the frames and D2H of the results inside the timed region, on a bounded
+number of frames (`e2e.frames`, 16M per rank unless the shard is smaller).
 N > 1 shards the same 50M frames across ranks (strong scaling).
 """
 import argparse
@@ -51,10 +52,15 @@ def parse():
     ap.add_argument("--lag", type=int, default=10)
     ap.add_argument("--k", type=int, default=8, help="KCenters n_clusters (reference default 8)")
     ap.add_argument("--engine", default="auto")
-    ap.add_argument("--e2e-frames", type=int, default=4_000_000)
+    ap.add_argument("--e2e-frames", type=int, default=16_000_000,
+                    help="frames PER RANK of the end-to-end measurement (host NumPy arrays)")
     ap.add_argument("--cpu-frames", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-f64-check", action="store_true",
+                    help="skip the float64-engine parity run on the timed frames")
+    ap.add_argument("--no-ref-schedule", action="store_true",
+                    help="skip timing KCenters with one pass per centre beside the look-ahead value")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="KCenters: one pass per centre (the reference's schedule) instead of look-ahead")
     return ap.parse_args()
@@ -203,10 +209,21 @@ def cpu_threads():
         return 1
 
 
+def all_blas_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host
+    core NumPy's BLAS can (the reference does: tica.py:417-422 are plain np.dot calls)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count(), user_api="blas")
+    except Exception:
+        pass
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    all_blas_threads()
     from oracle import libdistance_oracle as lo
     use_ref = lo.have_reference()
     seqs = host_sample(args.cpu_frames, args.seq_len, args.features, seed=1000)
@@ -227,10 +244,16 @@ def run_reference(args):
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": dict(workload_config(args, 1), frames_timed_per_step=n,
+                       note="a bounded sample of the workload is timed (frames_timed_per_step); "
+                            "value is a rate (frames/s) and the CPU path streams, so it does not "
+                            "depend on the sample size"),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count(),
-                         "kind": "reference" if use_ref else "port", "sample": sample,
-                         "blas_threads": cpu_threads()},
+                         "kind": "port",
+                         "kind_by_phase": {"tica": "port (oracle/tica_oracle.py, NumPy f64 restatement of tica.py:401-424)",
+                                           "kcenters": "reference (oracle/_ref/libref.so = the reference's libdistance C++)"
+                                           if use_ref else "port (oracle/libdistance_oracle.c)"},
+                         "sample": sample, "blas_threads": cpu_threads()},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -347,18 +370,79 @@ def run_ours(args):
     ms_per_step = float(total_ms.item()) / args.steps
     value = n_total / (ms_per_step / 1e3)
 
-    # sanity on the timed work: eigenvalues from the device accumulator are sane
-    est2 = tICA(n_components=4, lag_time=lag, engine=args.engine)
-    est2._initialize(D)
-    est2._add_packed(acc.cpu().numpy())
+    # ---- parity AT THE BENCH SIZE, on the very frames that were timed: the float64 CUDA-core
+    # engine (the reference's arithmetic, tica.py:402-422) against the engine that was timed.
+    # Every rank accumulates its shard, one all-reduce, so the sharding dependence shows per N.
+    def fitted(packed):
+        m = tICA(n_components=4, lag_time=lag, engine=args.engine)
+        m._initialize(D)
+        m._add_packed(packed.cpu().numpy())
+        return m
+
+    est2 = fitted(acc)
     eig = [float(v) for v in est2.eigenvalues_]
+    check = {"eigenvalues": eig}
+    if not args.no_f64_check and args.engine != "simt_f64":
+        acc64 = torch.zeros_like(acc)
+        e64 = tICA(n_components=4, lag_time=lag, engine="simt_f64")
+        e64._initialize(D)
+        t64 = time.perf_counter()
+        e64._accumulate_device(seqs, acc=acc64)
+        par.allreduce_packed(acc64)
+        torch.cuda.synchronize()
+        t64 = time.perf_counter() - t64
+        ref64 = fitted(acc64)
+        DD = D * D
+        a, b = acc.cpu().numpy(), acc64.cpu().numpy()
+        sd = np.sqrt(np.abs(np.diag(b[DD:2 * DD].reshape(D, D))))
+        norm = np.outer(sd, sd).ravel()
+        cos = np.abs(np.sum(est2.components_ * ref64.components_, axis=1)) / (
+            np.linalg.norm(est2.components_, axis=1) * np.linalg.norm(ref64.components_, axis=1))
+        check.update({
+            "eigenvalues_f64": [float(v) for v in ref64.eigenvalues_],
+            "eig_err_vs_f64": float(np.abs(est2.eigenvalues_ - ref64.eigenvalues_).max()),
+            "eig_tolerance": 1e-5,
+            "component_cos_min": float(cos.min()),
+            "moment_rel_err": float(max(np.abs(a[m * DD:(m + 1) * DD] - b[m * DD:(m + 1) * DD]).max()
+                                        / np.abs(b[m * DD:(m + 1) * DD]).max() for m in range(3))),
+            "moment_err_per_unit_variance": float(max(
+                (np.abs(a[m * DD:(m + 1) * DD] - b[m * DD:(m + 1) * DD]) / norm).max() for m in range(3))),
+            "f64_engine_seconds": t64,
+            "what": "engine=%s vs engine=simt_f64 (float64 CUDA cores) on all %d x %d frames, "
+                    "sharded over %d rank(s)" % (args.engine, n_total, D, ws)})
+        del acc64
+
+    # ---- the reference's schedule for KCenters (one read of the frames per centre), same frames
+    value_ref_schedule = None
+    if not args.no_lookahead and not args.no_ref_schedule:
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2
+        par.kcenters_fit_gpu(X, row_offset, k, "euclidean", seed_global=12345 % n_total, lookahead=False)
+        barrier()
+        ev_a.record()
+        for _ in range(reps):
+            ids_ref, _, _, _ = par.kcenters_fit_gpu(X, row_offset, k, "euclidean",
+                                                    seed_global=12345 % n_total, lookahead=False)
+        ev_b.record()
+        barrier()
+        kc_ref_ms = torch.tensor([ev_a.elapsed_time(ev_b) / reps], dtype=torch.float64, device="cuda")
+        if ws > 1:
+            dist.all_reduce(kc_ref_ms, op=dist.ReduceOp.MAX)
+        step_ref_ms = float(tica_ms.item()) + float(kc_ref_ms.item())
+        value_ref_schedule = {
+            "value": n_total / (step_ref_ms / 1e3), "unit": "frames/s",
+            "kcenters_fit_ms": float(kc_ref_ms.item()),
+            "ids_equal_lookahead": bool(torch.equal(ids_ref, state["ids"])),
+            "what": "same tICA phase + KCenters with one pass per centre (kcenters.py:91-97 schedule, "
+                    "%d reads of the frames); the look-ahead gain is data dependent" % k}
 
     # ---------------- e2e: public estimator API on pinned host arrays -----------------
     e2e = None
     if not args.no_e2e:
-        ne = min(args.e2e_frames // ws, n_local) // L * L
+        ne = min(args.e2e_frames, n_local) // L * L
         ne = max(ne, L)
-        host = [X[i * L:(i + 1) * L].cpu().pin_memory() for i in range(ne // L)]
+        # what a Pipeline caller holds: plain (pageable) NumPy arrays
+        host = [X[i * L:(i + 1) * L].cpu().numpy() for i in range(ne // L)]
         torch.cuda.synchronize()
 
         def e2e_step():
@@ -413,6 +497,7 @@ def run_ours(args):
         d2h = int(lib.msmb200_tica_acc_len(D)) * 8 + ne * (8 + 4) + k * (8 + D * 4)
         e2e = {"value": ne * ws / float(dt.item()), "unit": "frames/s", "frames": ne * ws,
                "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": d2h * ws,
+               "host_memory": "pageable NumPy arrays (uploaded through the pinned chunk ring of _device.HostUploader)",
                "api": "tICA.fit(host arrays) + KCenters.fit(host arrays)"
                       + ("" if ws == 1 else " via parallel.*_fit_sharded"),
                "upload_once": {"value": ne * ws / float(dt1.item()), "unit": "frames/s",
@@ -498,7 +583,8 @@ def run_ours(args):
                       "kcenters_launches": [[int(c), round(float(m), 3)] for c, m in
                                             zip(pass_centres[-n_passes:], pass_ms[-n_passes:])] if pass_ms else None},
         "tica_engine": args.engine,
-        "check": {"eigenvalues": eig, "kcenters_ids": [int(i) for i in state["ids"].cpu().numpy()]},
+        "value_reference_schedule": value_ref_schedule,
+        "check": dict(check, kcenters_ids=[int(i) for i in state["ids"].cpu().numpy()]),
     }
 
     if ws == 1 and not args.no_cpu_baseline:
@@ -506,10 +592,14 @@ def run_ours(args):
         use_ref = lo.have_reference()
         nc = max(L, min(args.cpu_frames, n_local) // L * L)
         hs = [X[i * L:(i + 1) * L].cpu().numpy() for i in range(nc // L)]
+        all_blas_threads()
         a, b = cpu_hot_path(hs, lag, k, use_ref)
         line["cpu_baseline"] = {
             "value": nc / (a + b), "unit": "frames/s", "cores": os.cpu_count(),
-            "blas_threads": cpu_threads(), "kind": "reference" if use_ref else "port",
+            "blas_threads": cpu_threads(), "kind": "port",
+            "kind_by_phase": {"tica": "port (NumPy f64 restatement of tica.py:401-424)",
+                              "kcenters": "reference (the reference's libdistance C++, oracle/_ref)"
+                              if use_ref else "port (oracle/libdistance_oracle.c)"},
             "sample": "%d of the same frames (D2H copy): tICA NumPy f64 %.2f s on %d BLAS threads + "
                       "%d KCenters passes %.2f s on 1 thread (the reference's libdistance is "
                       "single-threaded)" % (nc, a, cpu_threads(), k, b)}

@@ -275,6 +275,19 @@ int msmb200_transition_counts(const void *labels, int label_bytes, const int64_t
                               const int32_t *remap, int64_t remap_lo, int64_t remap_len,
                               int32_t n_states, int64_t *counts, void *stream);
 
+/* LandmarkAgglomerative.predict, cluster/agglomerative.py:234-269: dists is the (n, n_landmarks)
+ * float64 row-major output of msmb200_cdist against the landmarks, the landmarks ordered by
+ * cluster (group_offsets: n_clusters + 1 device int32 column offsets).  pool: 0 average, 1 complete,
+ * 2 single, 3 ward (POOLING_FUNCTIONS, agglomerative.py:31-43; ward needs the device float64
+ * arrays cardinality[n_clusters] and sqsum[n_clusters] = squared_distances_within_cluster_).
+ * labels (int32, n): arg-min over clusters of the pooled distance, first cluster wins ties, empty
+ * clusters skipped; pooled (f64, n, may be NULL): that minimum; any_negative (device int32, may
+ * be NULL) is OR-ed with 1 when a pooled distance was negative (the reference warns). */
+int msmb200_pooled_assign(const double *dists, int64_t n, int n_landmarks,
+                          const int32_t *group_offsets, int n_clusters, int pool,
+                          const double *cardinality, const double *sqsum, int32_t *labels,
+                          double *pooled, int32_t *any_negative, void *stream);
+
 /* ======================================================================== *
  *  Host k-medoids on a condensed distance matrix (npass == 0 branch)       *
  *  replaces _kmedoids.kmedoids / contigify_ids                             *

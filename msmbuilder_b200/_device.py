@@ -59,6 +59,112 @@ def to_device(X, ndim=2):
     return t
 
 
+class HostUploader(object):
+    """Pageable host arrays -> device memory at (close to) the PCIe rate.
+
+    ``tensor.cuda()`` on pageable memory is one driver thread copying through a small staging
+    buffer (a few GB/s).  Here a few Python threads fill a ring of PINNED chunks with
+    ``np.copyto`` (the GIL is released for the copy) while earlier chunks are already on their
+    way with ``cudaMemcpyAsync`` on a side stream; the compute stream only waits for the last
+    chunk.  This is what a Pipeline caller holds: plain NumPy arrays (cluster/base.py:55-58 and
+    tica.py:401-403 both start from them)."""
+
+    CHUNK = 32 << 20
+    SLOTS = 8
+    THREADS = 4
+
+    def __init__(self):
+        self._pinned = None
+        self._pool = None
+        self._stream = {}
+
+    def _ring(self):
+        if self._pinned is None:
+            self._pinned = torch.empty(self.SLOTS * self.CHUNK, dtype=torch.uint8).pin_memory()
+        return self._pinned
+
+    def upload(self, pairs):
+        """pairs: [(C-contiguous ndarray, CUDA tensor of the same byte size)].  Asynchronous with
+        respect to the host only in its tail: returns when every chunk has been ISSUED; the current
+        stream is made to wait for the copies."""
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        jobs = []
+        for src, dst in pairs:
+            if src.nbytes == 0:
+                continue
+            sb = src.reshape(-1).view(np.uint8)
+            db = dst.reshape(-1).view(torch.uint8)
+            if sb.nbytes != db.numel():
+                raise ValueError("upload: size mismatch")
+            for o in range(0, sb.nbytes, self.CHUNK):
+                jobs.append((sb[o:o + self.CHUNK], db[o:o + self.CHUNK]))
+        if not jobs:
+            return
+        cur = torch.cuda.current_stream()
+        devi = torch.cuda.current_device()
+        if devi not in self._stream:
+            self._stream[devi] = torch.cuda.Stream()
+        cs = self._stream[devi]
+        cs.wait_stream(cur)                      # the destination blocks may still be in use there
+        if len(jobs) == 1 and jobs[0][0].nbytes < (1 << 20):
+            jobs[0][1].copy_(torch.from_numpy(jobs[0][0]), non_blocking=False)
+            return
+        ring = self._ring()
+        ring_np = ring.numpy()
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(self.THREADS, thread_name_prefix="msmb200-h2d")
+        issued = [threading.Event() for _ in jobs]
+        events = [None] * len(jobs)
+
+        def fill(k):
+            if k >= self.SLOTS:                  # the slot's previous chunk must have left the host
+                issued[k - self.SLOTS].wait()
+                events[k - self.SLOTS].synchronize()
+            slot = (k % self.SLOTS) * self.CHUNK
+            n = jobs[k][0].nbytes
+            np.copyto(ring_np[slot:slot + n], jobs[k][0])
+            return slot, n
+
+        futs = [self._pool.submit(fill, k) for k in range(len(jobs))]
+        try:
+            with torch.cuda.stream(cs):
+                for k, f in enumerate(futs):
+                    slot, n = f.result()
+                    jobs[k][1].copy_(ring[slot:slot + n], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    events[k] = ev
+                    issued[k].set()
+        finally:
+            for k in range(len(jobs)):           # never leave a worker waiting on a failed upload
+                if events[k] is None:
+                    events[k] = torch.cuda.Event()
+                    events[k].record(cs)
+                issued[k].set()
+        cur.wait_stream(cs)
+        # the ring is reused by the next call: its chunks must have been read by then
+        events[-1].synchronize()
+
+
+_UPLOADER = None
+
+
+def uploader():
+    global _UPLOADER
+    if _UPLOADER is None:
+        _UPLOADER = HostUploader()
+    return _UPLOADER
+
+
+def host_array(a):
+    """ndarray in the dtype the device path keeps it in (float32 / float64, C-contiguous)."""
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return np.ascontiguousarray(a)
+
+
 class FrameStore(object):
     """The concatenation of a list of sequences as ONE (N, ...) device tensor.
 
@@ -100,6 +206,8 @@ class FrameStore(object):
             self.data = adopted
         else:
             self.data = torch.empty((n_total,) + inner, dtype=dtype, device="cuda")
+            np_dtype = np.float64 if dtype == torch.float64 else np.float32
+            host_pairs = []
             for s, o, n in zip(seqs, self.offsets[:-1], self.lengths):
                 if n == 0:
                     continue
@@ -107,10 +215,8 @@ class FrameStore(object):
                 if is_tensor(s):
                     dst.copy_(s, non_blocking=True)
                 else:
-                    a = np.asarray(s)
-                    if a.dtype not in (np.float32, np.float64):
-                        a = a.astype(np.float64)
-                    dst.copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=False)
+                    host_pairs.append((host_array(s).astype(np_dtype, copy=False), dst))
+            uploader().upload(host_pairs)        # pageable arrays: pinned ring + copy threads
         self.n = n_total
         self.inner = inner
 
@@ -148,16 +254,17 @@ def to_host(t, dtype=None):
 
 
 class Workspace(object):
-    """Grow-only device scratch buffer keyed by purpose."""
+    """Grow-only device scratch buffers keyed by (purpose, device, stream): two calls on
+    different CUDA streams or devices never share scratch (they would race on it)."""
 
     def __init__(self):
         self._bufs = {}
 
     def get(self, key, nbytes):
         nbytes = max(int(nbytes), 256)
+        key = (key, torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
         buf = self._bufs.get(key)
-        if buf is None or buf.numel() < nbytes or not buf.is_cuda \
-                or buf.device != torch.device("cuda", torch.cuda.current_device()):
+        if buf is None or buf.numel() < nbytes:
             buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
             self._bufs[key] = buf
         return buf

@@ -280,6 +280,13 @@ def regular_spatial_fit(data, d_min, metric, traces=None):
 
 
 # --------------------------------------------------------------------------- K3
+def _same_width(X, Y, msg='X and Y must have the same number of columns'):
+    """The C ABI takes ONE width for both operands: a mismatch would read out of bounds on the
+    device.  The reference raises (libdistance.pyx:378,398 assert; :447,456 ValueError)."""
+    if X.dim() != 2 or Y.dim() != 2 or int(X.shape[1]) != int(Y.shape[1]):
+        raise ValueError(msg)
+
+
 def assign_nearest(X, Y, metric, rows=None, want_min_dist=False):
     """labels (i32), min_dist (f64 or None), inertia (0-d f64 tensor)."""
     _lib.require_gpu()
@@ -296,6 +303,7 @@ def assign_nearest(X, Y, metric, rows=None, want_min_dist=False):
     m = _lib.metric_id(metric)
     if X.dtype != Y.dtype:
         raise TypeError('X and y must be both float32 or float64')
+    _same_width(X, Y)
     d, k = int(X.shape[1]), int(Y.shape[0])
     ws_bytes = int(lib.msmb200_assign_workspace_bytes(n_out, k, d))
     ws = dev.workspace().get("assign", ws_bytes)
@@ -308,6 +316,9 @@ def assign_nearest(X, Y, metric, rows=None, want_min_dist=False):
 
 def rmsd_assign_nearest(xyz, traces, Y, Y_traces, rows=None, want_min_dist=False):
     _lib.require_gpu()
+    if int(xyz.shape[1]) != int(Y.shape[1]):
+        raise ValueError("Input trajectories must have same number of atoms. found %d and %d."
+                         % (int(xyz.shape[1]), int(Y.shape[1])))          # libdistance.pyx:320-322
     rows_t = _rows_tensor(rows)
     n_out = int(xyz.shape[0]) if rows_t is None else int(rows_t.numel())
     labels = torch.empty((n_out,), dtype=torch.int32, device="cuda")
@@ -324,6 +335,8 @@ def rmsd_assign_nearest(xyz, traces, Y, Y_traces, rows=None, want_min_dist=False
 # --------------------------------------------------------------------------- K4
 def dist(X, y, metric, rows=None):
     _lib.require_gpu()
+    if int(y.numel()) != int(X.shape[1]):
+        raise ValueError('X and y must have the same number of columns')   # libdistance.pyx:378,398 assert
     rows_t = _rows_tensor(rows)
     n_out = int(X.shape[0]) if rows_t is None else int(rows_t.numel())
     out = torch.empty((n_out,), dtype=torch.float64, device="cuda")
@@ -336,6 +349,9 @@ def dist(X, y, metric, rows=None):
 
 def cdist(XA, XB, metric):
     _lib.require_gpu()
+    _same_width(XA, XB, 'XA and XB must have the same number of columns')
+    if XA.dtype != XB.dtype:
+        raise TypeError('XA and XB must be both float32 or float64')
     out = torch.empty((int(XA.shape[0]), int(XB.shape[0])), dtype=torch.float64, device="cuda")
     if out.numel():
         _lib.call("msmb200_cdist", dev.ptr(XA), int(XA.shape[0]), dev.ptr(XB), int(XB.shape[0]),

@@ -74,6 +74,8 @@ SIGNATURES = {
                                           ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64)]),
     "msmb200_contigify_ids": (c_int, [c_vp, c_i64, c_vp, ctypes.POINTER(c_i64)]),
     "msmb200_first_above": (c_int, [c_vp, c_i64, c_i64, c_dbl, c_vp, c_vp]),
+    "msmb200_pooled_assign": (c_int, [c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
+                                      c_vp, c_vp, c_vp]),
     "msmb200_label_range": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "msmb200_label_presence": (c_int, [c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_vp]),
     "msmb200_transition_counts": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_i64, c_vp,

@@ -6,6 +6,7 @@ from .minibatchkmedoids import MiniBatchKMedoids
 from .minibatchkmeans import MiniBatchKMeans
 from .regularspatial import RegularSpatial
 from .kmedoids import KMedoids
+from .agglomerative import LandmarkAgglomerative
 
-__all__ = ['KCenters', 'MiniBatchKMedoids', 'MiniBatchKMeans', 'RegularSpatial', 'KMedoids',
+__all__ = ['KCenters', 'MiniBatchKMedoids', 'MiniBatchKMeans', 'RegularSpatial', 'KMedoids', 'LandmarkAgglomerative',
            'MultiSequenceClusterMixin']

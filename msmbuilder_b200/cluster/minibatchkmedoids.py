@@ -12,7 +12,6 @@ medoids.
 """
 from __future__ import absolute_import, print_function, division
 
-from operator import itemgetter
 
 import numpy as np
 from sklearn.utils import check_random_state
@@ -30,6 +29,71 @@ def _to_host_intp(labels):
     return to_host(labels, torch.int64)
 
 __all__ = ['MiniBatchKMedoids']
+
+
+class _MedoidSearch(object):
+    """The sequential part of MiniBatchKMedoids.fit (minibatchkmedoids.py:90-134): a host loop over
+    small problems -- k current medoids plus `batch_size` random frames -- whose pairwise distances
+    come from the device (K4, gathered rows, nothing but the (k + batch)^2 / 2 distances leaves
+    the GPU) and whose k-medoids sweep runs in msmb200_kmedoids (host C++).
+
+    Parity with the reference depends on the ORDER of the RandomState draws: first the k starting
+    medoids, then a provisional medoid number for every frame, then one draw of `batch_size` frame
+    indices per round (the k-medoids call itself draws nothing with npass = 0).  Everything else
+    here is bookkeeping and is written around three arrays:
+
+      medoids[k]    frame index of each medoid
+      member_of[n]  medoid number last given to each frame (only touched frames are meaningful)
+      quiet         consecutive rounds that changed no frame's medoid number
+    """
+
+    def __init__(self, est, data, traces):
+        self.k = int(est.n_clusters)
+        self.batch = int(est.batch_size)
+        self.metric = est.metric
+        self.patience = est.max_no_improvement
+        self.data, self.traces = data, traces
+        self.n = int(data.shape[0])
+        rounds_per_sweep = -(-self.n // self.batch)              # ceil(n / batch)
+        self.max_rounds = int(est.max_iter) * rounds_per_sweep
+        self.rng = check_random_state(est.random_state)
+        self.medoids = self.rng.randint(0, self.n, size=self.k)          # draw 1
+        self.member_of = self.rng.randint(0, self.k, size=self.n)        # draw 2
+        self.quiet = 0
+
+    def _distances(self, frames):
+        from .. import _kernels as K
+        rows = np.asarray(frames, dtype=np.intp)
+        if self.metric == 'rmsd':
+            return K.rmsd_pdist(self.data, self.traces, rows=rows).cpu().numpy()
+        return K.pdist(self.data, self.metric, rows=rows).cpu().numpy()
+
+    def _round(self):
+        """One mini-batch: returns False when the search has gone quiet for long enough."""
+        from .. import _kernels as K
+        k = self.k
+        fresh = self.rng.randint(0, self.n, self.batch)                  # draw 3, 4, ...
+        frames = np.concatenate([self.medoids, fresh])                   # positions 0..k-1 = medoids
+        # starting assignment inside the batch: a medoid belongs to itself, a fresh frame keeps
+        # the number it had
+        start = np.concatenate([np.arange(k), self.member_of[fresh]]).astype(np.intp)
+        solved, _, _ = K.kmedoids(k, self._distances(frames), 0, start, random_state=self.rng)
+        # the sweep names a cluster by the batch position of its medoid; renumber 0..k-1 in order
+        # of first appearance and remember which position carries each number
+        numbered, position_to_number = K.contigify_ids(solved)
+        by_number = sorted(position_to_number, key=position_to_number.get)
+        self.medoids = frames[np.asarray(by_number, dtype=np.intp)]
+        if np.array_equal(self.member_of[frames], numbered):
+            self.quiet += 1
+        else:
+            self.member_of[frames] = numbered
+            self.quiet = 0
+        return self.quiet < self.patience
+
+    def run(self):
+        for _ in range(self.max_rounds):
+            if not self._round():
+                break
 
 
 class _MiniBatchKMedoids(ClusterMixin, TransformerMixin):
@@ -76,51 +140,12 @@ class _MiniBatchKMedoids(ClusterMixin, TransformerMixin):
         if self.metric != 'rmsd':
             _lib.metric_id(self.metric)   # ValueError on an unknown metric, before any work
         data, traces = _prepare(X, self.metric)
-        n_samples = int(data.shape[0])
-        n_batches = int(np.ceil(float(n_samples) / self.batch_size))
-        n_iter = int(self.max_iter * n_batches)
-        random_state = check_random_state(self.random_state)
-
-        cluster_ids_ = random_state.randint(0, n_samples, size=self.n_clusters)
-        labels_ = random_state.randint(0, self.n_clusters, size=n_samples)
-
-        n_iters_no_improvement = 0
-        for kk in range(n_iter):
-            # batch = current medoids + fresh random frames
-            minibatch_indices = np.concatenate([
-                cluster_ids_,
-                random_state.randint(0, n_samples, self.batch_size),
-            ])
-            rows = np.array(minibatch_indices, dtype=np.intp)
-            if self.metric == 'rmsd':
-                dmat = K.rmsd_pdist(data, traces, rows=rows).cpu().numpy()
-            else:
-                dmat = K.pdist(data, self.metric, rows=rows).cpu().numpy()
-            minibatch_labels = np.array(np.concatenate([
-                np.arange(self.n_clusters),
-                labels_[minibatch_indices[self.n_clusters:]]
-            ]), dtype=np.intp)
-
-            ids, intertia, _ = K.kmedoids(self.n_clusters, dmat, 0, minibatch_labels,
-                                          random_state=random_state)
-            minibatch_labels, m = K.contigify_ids(ids)
-
-            # new medoids, in label order
-            minibatch_cluster_ids = np.array(sorted(m.items(), key=itemgetter(1)))[:, 0]
-            cluster_ids_ = minibatch_indices[minibatch_cluster_ids]
-
-            n_changed = np.sum(labels_[minibatch_indices] != minibatch_labels)
-            if n_changed == 0:
-                n_iters_no_improvement += 1
-            else:
-                labels_[minibatch_indices] = minibatch_labels
-                n_iters_no_improvement = 0
-            if n_iters_no_improvement >= self.max_no_improvement:
-                break
+        search = _MedoidSearch(self, data, traces)
+        search.run()
 
         import torch
-        self.cluster_ids_ = cluster_ids_
-        idx = torch.from_numpy(np.asarray(cluster_ids_, dtype=np.int64)).cuda()
+        self.cluster_ids_ = search.medoids
+        idx = torch.from_numpy(np.asarray(search.medoids, dtype=np.int64)).cuda()
         centers = data[idx].contiguous()
         self.cluster_centers_ = centers.cpu().numpy()
         if self.metric == 'rmsd':

@@ -229,6 +229,82 @@ extern "C" int msmb200_label_presence(const void *labels, int64_t n, int label_b
     return MSMB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// LandmarkAgglomerative.predict (cluster/agglomerative.py:234-269): given the (n, L) float64
+// distances of n frames to the L landmarks -- columns ordered so that the landmarks of cluster c
+// occupy [group_offsets[c], group_offsets[c + 1]) -- pool each cluster's distances
+// (POOLING_FUNCTIONS, agglomerative.py:31-43) and give the frame to the cluster with the smallest
+// pooled value; clusters are visited in order with a strict '<', empty clusters are skipped
+// (agglomerative.py:256-266).  One warp per frame: coalesced reads of its row.
+//   pool 0 = average (mean), 1 = complete (max), 2 = single (min),
+//        3 = ward: (card * sum(x^2) - sqsum_c) / (card * (card + 1) / 2)
+__global__ void __launch_bounds__(256)
+pooled_assign_kernel(const double *__restrict__ dists, long long n, int L,
+                     const int *__restrict__ group_offsets, int n_clusters, int pool,
+                     const double *__restrict__ cardinality, const double *__restrict__ sqsum,
+                     int32_t *__restrict__ labels, double *__restrict__ pooled_out,
+                     int *__restrict__ any_negative)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < n; r += n_warps) {
+        const double *row = dists + r * (long long)L;
+        double best = INFINITY;
+        int best_c = 0;
+        bool neg = false;
+        for (int c = 0; c < n_clusters; ++c) {
+            const int lo = group_offsets[c], hi = group_offsets[c + 1];
+            if (hi <= lo) continue;
+            double a = pool == 1 ? -INFINITY : pool == 2 ? INFINITY : 0.0;
+            for (int j = lo + lane; j < hi; j += 32) {
+                const double x = row[j];
+                a = pool == 0 ? a + x : pool == 1 ? fmax(a, x) : pool == 2 ? fmin(a, x) : a + x * x;
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, a, off);
+                a = (pool == 0 || pool == 3) ? a + o : pool == 1 ? fmax(a, o) : fmin(a, o);
+            }
+            double d;
+            if (pool == 0) d = a / (double)(hi - lo);
+            else if (pool == 3) {
+                const double card = cardinality[c];
+                d = (card * a - sqsum[c]) / (card * (card + 1.0) / 2.0);
+            } else d = a;
+            neg |= d < 0.0;
+            if (d < best) { best = d; best_c = c; }
+        }
+        if (lane == 0) {
+            labels[r] = best_c;
+            if (pooled_out) pooled_out[r] = best;
+            if (neg && any_negative) atomicOr(any_negative, 1);
+        }
+    }
+}
+
+extern "C" int msmb200_pooled_assign(const double *dists, int64_t n, int n_landmarks,
+                                     const int32_t *group_offsets, int n_clusters, int pool,
+                                     const double *cardinality, const double *sqsum,
+                                     int32_t *labels, double *pooled, int32_t *any_negative,
+                                     void *stream)
+{
+    MSMB_REQUIRE(n >= 0 && n_landmarks > 0 && n_clusters > 0 && pool >= 0 && pool <= 3,
+                 "pooled_assign: bad args n=%lld L=%d k=%d pool=%d", (long long)n, n_landmarks,
+                 n_clusters, pool);
+    if (n == 0) return MSMB200_OK;
+    MSMB_REQUIRE(dists && group_offsets && labels, "pooled_assign: null pointer");
+    MSMB_REQUIRE(pool != 3 || (cardinality && sqsum), "pooled_assign: ward needs cardinality and sqsum");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long blocks = (n + 7) / 8;
+    const long long cap = 16LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    pooled_assign_kernel<<<(unsigned)blocks, 256, 0, st>>>(dists, n, n_landmarks, group_offsets,
+                                                          n_clusters, pool, cardinality, sqsum,
+                                                          labels, pooled, any_negative);
+    MSMB_LAUNCH_CHECK();
+    return MSMB200_OK;
+}
+
 extern "C" int msmb200_transition_counts(const void *labels, int label_bytes,
                                          const int64_t *seq_offsets, int64_t n_seq, int64_t n_total,
                                          int64_t lag, const int32_t *remap,

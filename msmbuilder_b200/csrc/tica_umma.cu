@@ -43,6 +43,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <vector>
+#include <unordered_map>
+#include <mutex>
 
 namespace msmb {
 
@@ -768,25 +770,44 @@ tica_umma_kernel(const UmmaParams P)
 }
 
 // ---------------------------------------------------------------------------------------
-// provisional per-feature mean of the first rows of the first sequence -> float32 shift, and
-// (fp16 engine) a power-of-two scale 2^-e that brings the largest centred magnitude m of those
-// rows into [1, 2): fp16 then has 2^15 of headroom above the sample and 11-bit components of
-// everything down to 2^-14 of it.  m is floored at |mean| / 256 so that a feature which is
-// (nearly) constant in the sample cannot be blown up into fp16's ceiling by a later excursion.
-__global__ void tica_shift_kernel(const float *__restrict__ X, long long n, long long ld, int D,
-                                  float *__restrict__ shift, float *__restrict__ scale)
+// provisional per-feature mean -> float32 shift, and (fp16 engine) a power-of-two scale 2^-e that
+// brings the largest centred magnitude m of the sample into [1, 2): fp16 then has 2^15 of headroom
+// above the sample and 11-bit components of everything down to 2^-14 of it.  The sample is
+// UM_SAMPLE_ROWS rows spread evenly over ALL frames of the call (row j of the sample = frame
+// floor(j * total / rows) of the concatenated sequences), so a drifting or bursty feature is seen over
+// its whole range, not only at the start of the first sequence.  m is floored at |mean| / 256 so that
+// a feature which is (nearly) constant in the sample cannot be blown up into fp16's ceiling by a
+// later excursion (an excursion beyond 2^15 m still trips the range check -> bf16 rescue).
+// Any shift / scale gives the same moments up to rounding: they only set where the roundings fall.
+constexpr int UM_SAMPLE_ROWS = 1024;
+struct EdgeSeq {
+    const float *base;
+    long long n;
+};
+__global__ void tica_shift_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long total,
+                                  long long ld, int D, float *__restrict__ shift,
+                                  float *__restrict__ scale)
 {
-    const long long rows = n < 512 ? n : 512;
+    const long long rows = total < UM_SAMPLE_ROWS ? total : UM_SAMPLE_ROWS;
     // shift[] is padded to UM_D entries; features >= D do not exist (TMA zero-fills them)
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < UM_D; c += gridDim.x * blockDim.x) {
-        double s = 0.0;
-        if (c < D)
-            for (long long r = 0; r < rows; ++r) s += (double)X[r * ld + c];
-        const float sh = (float)(s / (double)rows);
+        float sh = 0.f, m = 0.f;
+        if (c < D) {
+            for (int pass = 0; pass < 2; ++pass) {
+                double s = 0.0;
+                int q = 0;
+                long long before = 0;                 // frames in sequences < q
+                for (long long j = 0; j < rows; ++j) {
+                    const long long g = j * total / rows;          // j < 1024: no overflow below 2^53 frames
+                    while (g >= before + seqs[q].n) { before += seqs[q].n; ++q; }
+                    const float v = seqs[q].base[(g - before) * ld + c];
+                    if (pass == 0) s += (double)v;
+                    else m = fmaxf(m, fabsf(v - sh));
+                }
+                if (pass == 0) sh = (float)(s / (double)rows);
+            }
+        }
         shift[c] = sh;
-        float m = 0.f;
-        if (c < D)
-            for (long long r = 0; r < rows; ++r) m = fmaxf(m, fabsf(X[r * ld + c] - sh));
         m = fmaxf(m, fabsf(sh) * (1.f / 256.f));
         int e = 0;
         if (m > 0.f && m < INFINITY) e = ilogbf(m);
@@ -804,11 +825,6 @@ __global__ void tica_umma_rescue_clear_kernel(const int *__restrict__ flag, doub
          i += (size_t)gridDim.x * blockDim.x)
         buf[i] = 0.0;
 }
-
-struct EdgeSeq {
-    const float *base;
-    long long n;
-};
 
 // float64 edge terms, in the SAME centred coordinates x' = fl32(x - shift):
 //   E[0] += sum over the remainder pair indices t in [4*floor(P/4), P) of x'_t x'_{t+lag}^T
@@ -1013,6 +1029,63 @@ static int env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
+// ---- host-side staging: the per-call tables travel through a small ring of PINNED buffers (one
+// cudaMemcpyAsync per call, no stream synchronisation), and encoded tensor maps are cached by
+// (base, rows, pitch, width): a partial_fit stream of sequences that live in one FrameStore, or a
+// bench step over the same frames, encodes each map once.
+struct MapKey {
+    const void *base;
+    long long rows, ld;
+    int D;
+    bool operator==(const MapKey &o) const { return base == o.base && rows == o.rows && ld == o.ld && D == o.D; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const
+    {
+        size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+        h ^= (size_t)k.rows * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.D;
+        return h ^ (h >> 29);
+    }
+};
+static std::mutex g_host_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+struct PinnedSlot {
+    void *host = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+constexpr int UM_PINNED_SLOTS = 8;
+constexpr int UM_MAX_DEVICES = 64;
+static PinnedSlot g_pinned[UM_MAX_DEVICES][UM_PINNED_SLOTS];     // events belong to a device
+static int g_pinned_next[UM_MAX_DEVICES] = {0};
+static bool g_pool_tuned[UM_MAX_DEVICES] = {false};              // one-time set-up, per device
+static bool g_attr_set[UM_MAX_DEVICES] = {false};
+
+// a pinned buffer of >= bytes whose previous copy (if any) has left the host; call with g_host_mu held
+static int pinned_acquire(int dev, size_t bytes, PinnedSlot **out)
+{
+    PinnedSlot &s = g_pinned[dev][g_pinned_next[dev]];
+    g_pinned_next[dev] = (g_pinned_next[dev] + 1) % UM_PINNED_SLOTS;
+    if (s.in_flight) {
+        MSMB_CUDA(cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    if (s.bytes < bytes) {
+        if (s.host) MSMB_CUDA(cudaFreeHost(s.host));
+        s.host = nullptr;
+        s.bytes = 0;
+        size_t cap = 1 << 16;
+        while (cap < bytes) cap <<= 1;
+        MSMB_CUDA(cudaMallocHost(&s.host, cap));
+        s.bytes = cap;
+    }
+    if (!s.done) MSMB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    *out = &s;
+    return MSMB200_OK;
+}
+
 int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, int n_seq_in,
                          int D, int64_t ld, int lag, int passes, double *acc, void *workspace,
                          size_t workspace_bytes, cudaStream_t st)
@@ -1041,8 +1114,34 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const int n_seq = (int)seqs.size();
     if (n_seq == 0) return MSMB200_OK;
 
-    std::vector<CUtensorMap> maps(2 * (size_t)n_seq);
-    std::vector<int> tile_prefix(n_seq + 1, 0), seq_pairs(n_seq, 0);
+    // per-call tables, laid out once and built straight into a pinned staging buffer:
+    //   [mapsA | mapsB | tile_prefix | seq_pairs | edge seqs]
+    auto align_up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    size_t off = 0;
+    const size_t o_mapsA = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
+    const size_t o_mapsB = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
+    const size_t o_prefix = off; off = align_up(off + sizeof(int) * (n_seq + 1), 128);
+    const size_t o_blocks = off; off = align_up(off + sizeof(int) * n_seq, 128);
+    const size_t o_eseq = off; off = align_up(off + sizeof(EdgeSeq) * n_seq, 128);
+    int dev = 0;
+    MSMB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= UM_MAX_DEVICES) {
+        set_error("device ordinal %d out of range", dev);
+        return MSMB200_E_UNSUPPORTED;
+    }
+    std::unique_lock<std::mutex> host_lock(g_host_mu);
+    PinnedSlot *slot = nullptr;
+    {
+        int rc = pinned_acquire(dev, off, &slot);
+        if (rc != MSMB200_OK) return rc;
+    }
+    unsigned char *hb = reinterpret_cast<unsigned char *>(slot->host);
+    CUtensorMap *mapsA = reinterpret_cast<CUtensorMap *>(hb + o_mapsA);
+    CUtensorMap *mapsB = reinterpret_cast<CUtensorMap *>(hb + o_mapsB);
+    int *tile_prefix = reinterpret_cast<int *>(hb + o_prefix);
+    int *seq_pairs = reinterpret_cast<int *>(hb + o_blocks);
+    memcpy(hb + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq);
+    if (g_map_cache.size() > (1u << 16)) g_map_cache.clear();
     long long tiles = 0;
     for (int s = 0; s < n_seq; ++s) {
         const long long Pn = seqs[s].n - lag;           // pair indices (>= 1)
@@ -1059,12 +1158,19 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         }
         for (int which = 0; which < 2; ++which) {
             // (32 features, Pn rows, D/32 blocks); rows >= Pn read as zeros
+            void *base = (void *)(seqs[s].base + (which ? (size_t)lag * ld : 0));
+            CUtensorMap *dst = which ? &mapsB[s] : &mapsA[s];
+            const MapKey key{base, Pn, (long long)ld, D};
+            auto hit = g_map_cache.find(key);
+            if (hit != g_map_cache.end()) {
+                *dst = hit->second;
+                continue;
+            }
             cuuint64_t dims[3] = {32, (cuuint64_t)Pn, (cuuint64_t)(D / 32)};
             cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
             cuuint32_t box[3] = {32, UM_KT, 4};
             cuuint32_t es[3] = {1, 1, 1};
-            void *base = (void *)(seqs[s].base + (which ? (size_t)lag * ld : 0));
-            CUresult r = enc(&maps[2 * (size_t)s + which], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
+            CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                              dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1072,6 +1178,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                 set_error("cuTensorMapEncodeTiled failed (%d) for sequence %d", (int)r, s);
                 return MSMB200_E_CUDA;
             }
+            g_map_cache.emplace(key, *dst);
         }
     }
     tile_prefix[n_seq] = (int)tiles;
@@ -1087,25 +1194,16 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                   "msmb200_tica_workspace_bytes", workspace_bytes, need);
         return MSMB200_E_INVALID;
     }
-    static bool pool_tuned = false;
-    if (!pool_tuned) {   // keep the small stream-ordered table allocations cached
-        int dev = 0;
+    if (!g_pool_tuned[dev]) {   // keep the small stream-ordered table allocations cached
         cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t thr = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
-        pool_tuned = true;
+        g_pool_tuned[dev] = true;
     }
 
-    // small per-call tables: stream-ordered allocation  [mapsA | mapsB | tile_prefix | seq_pairs | edge seqs]
-    auto align_up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
-    size_t off = 0;
-    const size_t o_mapsA = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
-    const size_t o_mapsB = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
-    const size_t o_prefix = off; off = align_up(off + sizeof(int) * (n_seq + 1), 128);
-    const size_t o_blocks = off; off = align_up(off + sizeof(int) * n_seq, 128);
-    const size_t o_eseq = off; off = align_up(off + sizeof(EdgeSeq) * n_seq, 128);
+    // device copy of the tables: stream-ordered allocation
     unsigned char *scratch = nullptr;
     MSMB_CUDA(cudaMallocAsync(&scratch, off, st));
     // big zero-initialised part: caller's workspace  [shift | sums | E | es | partials]
@@ -1121,19 +1219,17 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const size_t w_part32 = woff; woff += sizeof(float) * 2 * DD * n_pairs;
     MSMB_CUDA(cudaMemsetAsync(wsb + w_flag, 0, woff - w_flag, st));
 
-    std::vector<CUtensorMap> mA(n_seq), mB(n_seq);
-    for (int s = 0; s < n_seq; ++s) { mA[s] = maps[2 * (size_t)s]; mB[s] = maps[2 * (size_t)s + 1]; }
-    MSMB_CUDA(cudaMemcpyAsync(scratch + o_mapsA, mA.data(), sizeof(CUtensorMap) * n_seq, cudaMemcpyHostToDevice, st));
-    MSMB_CUDA(cudaMemcpyAsync(scratch + o_mapsB, mB.data(), sizeof(CUtensorMap) * n_seq, cudaMemcpyHostToDevice, st));
-    MSMB_CUDA(cudaMemcpyAsync(scratch + o_prefix, tile_prefix.data(), sizeof(int) * (n_seq + 1), cudaMemcpyHostToDevice, st));
-    MSMB_CUDA(cudaMemcpyAsync(scratch + o_blocks, seq_pairs.data(), sizeof(int) * n_seq, cudaMemcpyHostToDevice, st));
-    MSMB_CUDA(cudaMemcpyAsync(scratch + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq, cudaMemcpyHostToDevice, st));
-    MSMB_CUDA(cudaStreamSynchronize(st));    // host vectors are pageable: keep them alive until copied
+    // ONE asynchronous copy from pinned memory; the slot is reusable once `done` has passed
+    MSMB_CUDA(cudaMemcpyAsync(scratch, hb, off, cudaMemcpyHostToDevice, st));
+    MSMB_CUDA(cudaEventRecord(slot->done, st));
+    slot->in_flight = true;
+    host_lock.unlock();
 
     float *d_shift = reinterpret_cast<float *>(wsb + w_shift);
     float *d_scale = reinterpret_cast<float *>(wsb + w_scale);
     int *d_flag = reinterpret_cast<int *>(wsb + w_flag);
-    tica_shift_kernel<<<1, 256, 0, st>>>(seqs[0].base, seqs[0].n, ld, D, d_shift, d_scale);
+    tica_shift_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq,
+                                         (long long)n_obs, ld, D, d_shift, d_scale);
     MSMB_LAUNCH_CHECK();
 
     UmmaParams P;
@@ -1182,15 +1278,14 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
 
     if (tiles > 0) {
         const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + sizeof(UmmaSmem) + 1024;
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!g_attr_set[dev]) {
             MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_TF32>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_BF16>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_F16>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
+            g_attr_set[dev] = true;
         }
         if (f16) {
             tica_umma_kernel<UM_KIND_F16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);

@@ -242,8 +242,9 @@ class tICA(BaseEstimator, TransformerMixin):
     def _fit(self, X):
         self._fit_many([X])
 
-    # batches of at most this many bytes of HOST data are staged on the device
-    _stage_bytes = 4 << 30
+    # batches of at most this many bytes of HOST data are staged on the device: the upload of
+    # batch i+1 (side stream, _device.HostUploader) overlaps K1 of batch i (compute stream)
+    _stage_bytes = 1 << 30
 
     def _fit_many(self, sequences):
         """Device accumulation of any number of sequences (tica.py:401-424 per
@@ -253,10 +254,13 @@ class tICA(BaseEstimator, TransformerMixin):
         from .. import _device as dev
 
         batch, batch_bytes = [], 0
+        state = {"acc": None}
 
         def flush():
+            # every batch ADDS into one device accumulator; nothing is read back (and nothing
+            # synchronises) until the last batch has been enqueued
             if batch:
-                self._accumulate_batch(batch)
+                state["acc"] = self._accumulate_device(batch, acc=state["acc"])
                 del batch[:]
 
         for X in sequences:
@@ -293,15 +297,15 @@ class tICA(BaseEstimator, TransformerMixin):
             batch.append(X)
             batch_bytes += nbytes
         flush()
-
-    def _accumulate_batch(self, seqs):
-        packed = self._accumulate_device(seqs).cpu().numpy()   # synchronises
-        self._add_packed(packed)
+        if state["acc"] is not None:
+            self._add_packed(state["acc"].cpu().numpy())       # the one synchronisation of a fit
 
     def _accumulate_device(self, seqs, acc=None):
         """Run K1 over `seqs` (host arrays are uploaded, device tensors used in
-        place); returns the packed float64 accumulator as a CUDA tensor (layout:
-        include/msmb200.h).  Asynchronous on torch's current stream."""
+        place); ADDS their statistics to `acc` (a new zeroed one by default) and returns it: the
+        packed float64 accumulator as a CUDA tensor (layout: include/msmb200.h).  Device work is
+        enqueued on torch's current stream and not waited for; host arrays are uploaded through
+        the pinned ring, which returns once the last chunk has been issued."""
         import torch
         from .. import _device as dev
         _lib.require_gpu()
@@ -309,19 +313,26 @@ class tICA(BaseEstimator, TransformerMixin):
         dts = {torch.float64 if (s.dtype in (np.float64, torch.float64)) else torch.float32
                for s in seqs}
         dtype = torch.float64 if torch.float64 in dts else torch.float32
-        dev_seqs = []
-        for s in seqs:
+        np_dtype = np.float64 if dtype == torch.float64 else np.float32
+        dev_seqs = [None] * len(seqs)
+        host = [(i, dev.host_array(s).astype(np_dtype, copy=False))
+                for i, s in enumerate(seqs) if not is_tensor(s)]
+        if host:
+            # one device block for the batch's host arrays, rows padded to 16-byte multiples
+            # apart is not needed: D * 4 is the pitch and every slot starts on a row boundary
+            rows = [a.shape[0] for _, a in host]
+            block = torch.empty((sum(rows), D), dtype=dtype, device="cuda")
+            pairs, o = [], 0
+            for (i, a), n in zip(host, rows):
+                dev_seqs[i] = block[o:o + n]
+                pairs.append((a, dev_seqs[i]))
+                o += n
+            dev.uploader().upload(pairs)
+        for i, s in enumerate(seqs):
             if is_tensor(s):
                 t = s if s.dtype == dtype else s.to(dtype)
                 t = t.cuda(non_blocking=True) if not t.is_cuda else t
-                t = t.contiguous()
-            else:
-                a = np.ascontiguousarray(s if s.dtype == (np.float64 if dtype == torch.float64
-                                                          else np.float32) else
-                                         s.astype(np.float64 if dtype == torch.float64
-                                                  else np.float32))
-                t = torch.from_numpy(a).cuda()
-            dev_seqs.append(t)
+                dev_seqs[i] = t.contiguous()
         n_seq = len(dev_seqs)
         ptrs = (ctypes.c_void_p * n_seq)(*[t.data_ptr() for t in dev_seqs])
         rows = (ctypes.c_int64 * n_seq)(*[int(t.shape[0]) for t in dev_seqs])

@@ -41,6 +41,19 @@ def world():
     return 0, 1
 
 
+def _agree_max(values, group=None):
+    """Element-wise MAX of a few Python ints over the ranks (device tensor under NCCL, CPU tensor
+    under gloo); every rank returns the same list."""
+    _, ws = world()
+    vals = [int(v) for v in values]
+    if ws == 1:
+        return vals
+    on_gpu = dist.get_backend(group) == "nccl"
+    t = torch.tensor(vals, dtype=torch.int64, device="cuda" if on_gpu else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return [int(v) for v in t.cpu().tolist()]
+
+
 def shard_sequences(lengths, world_size):
     """Longest-processing-time assignment of whole sequences to ranks.
     Returns a list (per rank) of sequence indices, each in ascending order."""
@@ -211,15 +224,26 @@ def tica_fit_sharded(est, local_sequences, group=None):
     all-reduce every rank holds the same fitted estimator (tica.py:261-290)."""
     import warnings
     est._initialized = False
+    local_sequences = list(local_sequences)
+    # a rank may hold no sequence at all (fewer sequences than ranks): the width is agreed on
+    # first, every rank initialises, and an empty rank contributes a zero accumulator
+    widths = {int(X.shape[1]) for X in local_sequences}
+    if len(widths) > 1:
+        raise ValueError("sequences have different numbers of features: %s" % sorted(widths))
+    D = _agree_max([max(widths) if widths else 0], group=group)[0]
+    if D == 0:
+        raise ValueError("no sequences on any rank")
+    if widths and max(widths) != D:
+        raise ValueError("sequence has %d features, other ranks have %d" % (max(widths), D))
+    est._initialize(D)
     seqs = []
     for X in local_sequences:
-        est._initialize(int(X.shape[1]))
         if not int(X.shape[0]) > est.lag_time:
             warnings.warn("length of data (%d) is too short for the lag time (%d)"
                           % (int(X.shape[0]), est.lag_time))
             continue
         seqs.append(X)
-    lib_len = 3 * est.n_features ** 2 + 3 * est.n_features + 2
+    lib_len = 3 * D * D + 3 * D + 2
     if seqs:
         acc = est._accumulate_device(seqs)
     else:
@@ -237,7 +261,12 @@ def kcenters_fit_sharded(est, local_sequences, row_offset, n_total, group=None):
     fitted attributes; labels_/distances_ cover the local sequences only."""
     from sklearn.utils import check_random_state
     from ._device import FrameStore
-    store = FrameStore(list(local_sequences))
+    local_sequences = list(local_sequences)
+    if not local_sequences:
+        # an empty shard still takes part in every collective: an (0, ...) block of the agreed shape
+        raise ValueError("kcenters_fit_sharded: this rank holds no sequence; pass an empty "
+                         "(0, n_features) array so the frame width is known")
+    store = FrameStore(local_sequences)
     seed = check_random_state(est.random_state).randint(0, int(n_total))   # same draw on every rank
     traces = None
     data = store.data
@@ -249,7 +278,7 @@ def kcenters_fit_sharded(est, local_sequences, row_offset, n_total, group=None):
                                                     seed, traces=traces, group=group)
     k = int(est.n_clusters)
     est.cluster_ids_ = [int(c) for c in ids.cpu().numpy()]
-    row_elems = data[0].numel()
+    row_elems = int(np.prod(data.shape[1:]))       # not data[0]: the shard may hold no frame
     es = data.element_size()
     cent = ring[:k, CAND_HEADER:CAND_HEADER + row_elems * es].contiguous().view(data.dtype)
     est.cluster_centers_ = cent.reshape((k,) + tuple(data.shape[1:])).cpu().numpy()

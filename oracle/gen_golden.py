@@ -60,6 +60,66 @@ def gen_tica():
         print("wrote", c["name"], m.eigenvalues_)
 
 
+def gen_config1():
+    """BASELINE.json configs[0]: tICA(lag_time=10, n_components=4) on AlanineDipeptide dihedral
+    features through the reference's CPU path.  The dataset itself needs mdtraj + a download
+    (example_datasets/alanine_dipeptide.py:18-54), so the seeded stand-in of the same shape is used:
+    10 trajectories x 9,999 frames x [sin phi, cos phi, sin psi, cos psi]."""
+    from msmbuilder_b200.synthetic import dihedral_standin_numpy
+    tICA = ref_loader.load_tica()
+    seqs = dihedral_standin_numpy()
+    m = tICA(n_components=4, lag_time=10).fit(seqs)
+    proj = m.transform([seqs[0][:50]])[0]
+    mk = tICA(n_components=2, lag_time=10, kinetic_mapping=True).fit(seqs)
+    np.savez_compressed(
+        os.path.join(GOLD, "tica_config1_dihedral.npz"),
+        eigenvalues=m.eigenvalues_, eigenvectors=m.eigenvectors_, means=m.means_,
+        timescales=m.timescales_, n_observations=m.n_observations_, n_sequences=m.n_sequences_,
+        shrinkage_=m.shrinkage_, covariance=m.covariance_, offset_correlation=m.offset_correlation_,
+        proj50=proj, proj50_kinetic=mk.transform([seqs[0][:50]])[0],
+        score=m.score(seqs[:3]), summary=np.array(m.summarize()))
+    print("wrote tica_config1_dihedral", m.eigenvalues_)
+
+
+def gen_agglomerative():
+    """LandmarkAgglomerative fit + predict from the reference class (cluster/agglomerative.py),
+    over the compiled reference libdistance: 4 linkages x (ward predictors) x 2 metrics/dtypes."""
+    LA = ref_loader.load_agglomerative()
+    out = {}
+    cases = []
+    for linkage in ("average", "complete", "single", "ward"):
+        for metric, dtype in (("euclidean", "float32"), ("cityblock", "float64")):
+            preds = ("ward", "average") if linkage == "ward" else (None,)
+            for wp in preds:
+                cases.append((linkage, metric, dtype, wp))
+    for ci, (linkage, metric, dtype, wp) in enumerate(cases):
+        seqs = cluster_inputs(40 + ci, 3, 300, 6, np.dtype(dtype))
+        kw = dict(n_clusters=5, n_landmarks=60, linkage=linkage, metric=metric,
+                  landmark_strategy="stride" if ci % 2 == 0 else "random", random_state=7)
+        if wp is not None:
+            kw["ward_predictor"] = wp
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = LA(**kw).fit(seqs)
+            new = cluster_inputs(90 + ci, 2, 250, 6, np.dtype(dtype))
+            pred = m.predict(new)
+        key = "ag%d_" % ci
+        out[key + "landmark_labels"] = m.landmark_labels_
+        out[key + "landmarks"] = m.landmarks_
+        out[key + "centers"] = m.cluster_centers_
+        out[key + "cardinality"] = m.cardinality_
+        out[key + "sqsum"] = m.squared_distances_within_cluster_
+        out[key + "labels"] = np.concatenate(m.labels_) if hasattr(m, "labels_") else np.zeros(0)
+        out[key + "pred"] = np.concatenate(pred)
+        # margin between the best and second-best pooled distance of every predicted frame,
+        # so the parity test can exempt genuine near-ties
+        out[key + "kw"] = np.array(repr(sorted(kw.items())))
+    out["n_cases"] = len(cases)
+    out["cases"] = np.array([repr(c) for c in cases])
+    np.savez_compressed(os.path.join(GOLD, "agglomerative.npz"), **out)
+    print("wrote agglomerative", len(cases), "cases")
+
+
 def cluster_inputs(seed, n_seq, length, D, dtype):
     rs = np.random.RandomState(seed)
     centers = rs.randn(7, D) * 3
@@ -152,10 +212,10 @@ def main():
     if not ref_loader.available():
         raise SystemExit("reference tree absent: goldens can only be generated in the build container")
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["tica", "cluster", "cluster_more", "msm"]
+    which = sys.argv[1:] or ["tica", "cluster", "cluster_more", "msm", "config1", "agglomerative"]
     for name in which:
         {"tica": gen_tica, "cluster": gen_cluster, "cluster_more": gen_cluster_more,
-         "msm": gen_msm}[name]()
+         "msm": gen_msm, "config1": gen_config1, "agglomerative": gen_agglomerative}[name]()
 
 
 if __name__ == "__main__":

@@ -202,3 +202,24 @@ def load_more_clusterers():
         km = _load_file("msmbuilder.cluster.kmedoids", os.path.join("cluster", "kmedoids.py"))
         _loaded["cluster_more"] = (rs.RegularSpatial, km.KMedoids)
     return _loaded["cluster_more"]
+
+
+def load_agglomerative():
+    """Returns the reference's LandmarkAgglomerative (cluster/agglomerative.py:296), unmodified.
+    `fastcluster.linkage` (absent here) is SciPy's `linkage`: fastcluster is a drop-in
+    reimplementation of that function with the same stepwise-dendrogram output; np.infty
+    (agglomerative.py:252, gone in NumPy 2) is aliased to np.inf."""
+    if "agglomerative" not in _loaded:
+        load_cluster()
+        import numpy as np
+        import scipy.cluster.hierarchy
+        if "fastcluster" not in sys.modules:
+            fc = types.ModuleType("fastcluster")
+            fc.linkage = scipy.cluster.hierarchy.linkage
+            fc.__stub__ = True
+            sys.modules["fastcluster"] = fc
+        if not hasattr(np, "infty"):
+            np.infty = np.inf
+        ag = _load_file("msmbuilder.cluster.agglomerative", os.path.join("cluster", "agglomerative.py"))
+        _loaded["agglomerative"] = ag.LandmarkAgglomerative
+    return _loaded["agglomerative"]

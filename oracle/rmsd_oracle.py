@@ -114,3 +114,11 @@ def pdist(X, X_indices=None, GX=None):
     D = rmsd_qcp(X, X, GX, GX)
     iu = np.triu_indices(len(X), k=1)
     return D[iu]
+
+
+def cdist_rmsd(XA, XB):
+    """libdistance.cdist(XA, XB, 'rmsd') on UNCENTRED coordinates (libdistance.pyx:424-440 centres
+    private copies first): what RMSDFeaturizer.partial_transform returns (featurizer.py:318-320)."""
+    a, ga = center_and_trace(XA)
+    b, gb = center_and_trace(XB)
+    return rmsd_qcp(a, b, ga, gb)

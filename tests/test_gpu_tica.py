@@ -164,15 +164,17 @@ def test_umma_ragged_sequences_match_f64(lag):
     np.testing.assert_allclose(b.eigenvalues_, a.eigenvalues_, rtol=0, atol=UMMA_EIG_ATOL)
 
 
-def test_umma_long_run_eigenvalues_1e5():
-    # BASELINE config "eigenvalues vs reference within 1e-5", at a size the f64 engine finishes fast
+@pytest.mark.parametrize("engine", ["auto", "umma_3xf16", "umma_3xtf32"])
+def test_umma_long_run_eigenvalues_1e5(engine):
+    # BASELINE config "eigenvalues vs reference within 1e-5", at a size the f64 engine finishes fast;
+    # "auto" is the engine the bench and every default-constructed estimator run
     import torch
     from msmbuilder_b200.synthetic import ar1_device
     from msmbuilder_b200.decomposition import tICA
     X = ar1_device(20, 50000, 256, seed=5)
     seqs = [X[i * 50000:(i + 1) * 50000] for i in range(20)]
     a = tICA(n_components=8, lag_time=10, engine="simt_f64").fit(seqs)
-    b = tICA(n_components=8, lag_time=10, engine="umma_3xtf32").fit(seqs)
+    b = tICA(n_components=8, lag_time=10, engine=engine).fit(seqs)
     # raw moments: fp32 tensor-core accumulation over <= 1024-frame slabs (biased by
     # ~2^-25 per MMA step) bounds the relative error by ~3e-6
     _assert_moments_close(b, a, 5e-6)
@@ -181,7 +183,7 @@ def test_umma_long_run_eigenvalues_1e5():
         np.linalg.norm(a.components_, axis=1) * np.linalg.norm(b.components_, axis=1))
     assert cos.min() > 1 - 1e-4
     # additivity: fit(seqs) == partial_fit one sequence at a time (size-independent property)
-    c = tICA(n_components=8, lag_time=10, engine="umma_3xtf32")
+    c = tICA(n_components=8, lag_time=10, engine=engine)
     for s in seqs:
         c.partial_fit(s)
     np.testing.assert_allclose(c.eigenvalues_, b.eigenvalues_, rtol=0, atol=2e-6)

@@ -30,8 +30,10 @@ def _round_to_bits(a, bits=11):
 def device_algebra(seqs, lag, split=True):
     D = seqs[0].shape[1]
     usable = [np.ascontiguousarray(s, dtype=F32) for s in seqs if len(s) > lag]
-    first = usable[0][:512]
-    shift = (first.astype(np.float64).sum(0) / len(first)).astype(F32)           # tica_shift_kernel
+    allrows = np.concatenate(usable)                                             # tica_shift_kernel: 1024 rows
+    rows = min(len(allrows), 1024)                                               # spread over the whole call
+    first = allrows[(np.arange(rows, dtype=np.int64) * len(allrows)) // rows]
+    shift = (first.astype(np.float64).sum(0) / len(first)).astype(F32)
     m = np.maximum(np.abs(first - shift).max(0), np.abs(shift) / F32(256)).astype(F32)
     e = np.where((m > 0) & np.isfinite(m), np.floor(np.log2(np.maximum(m, 1e-300))), 0)
     scale = np.ldexp(F32(1), -e.astype(int)).astype(F32)
