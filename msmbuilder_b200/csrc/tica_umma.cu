@@ -266,15 +266,57 @@ __device__ __forceinline__ void flush_prefetch(const UmmaParams &P, int pair, ui
 // dealt round-robin to the `nparts` warps that share a quarter.
 __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, int pair,
                                             uint32_t cta_rank, int quarter, int part, int nparts,
-                                            int lane, uint32_t &absmax, bool fold)
+                                            int lane, uint32_t &absmax, bool fold, float *stage)
 {
     const int row = UM_F * cta_rank + quarter * 32 + lane;
     double *pc = P.partials + (size_t)pair * 2 * UM_D * UM_D + row;
     float *pc32 = P.partials32 + (size_t)pair * 2 * UM_D * UM_D + row;
+    // flush_red 3 / 4: the float32 level is laid out per (CTA, lane quarter, 32-column chunk) as one
+    // contiguous 4 KB block, [col][row] (3: TMA bulk reduce from shared memory) or
+    // [col / 4][row][col % 4] (4: 16-byte vector reductions)
+    float *blk32 = P.partials32 + (size_t)pair * 2 * UM_D * UM_D
+                   + (size_t)((cta_rank * 4 + quarter) * 16) * 1024;
 #pragma unroll 1
     for (int c0 = 32 * part; c0 < 512; c0 += 32 * nparts) {
         uint32_t v[32];
         UM_TMEM_LD32(v, tmem + ((uint32_t)(quarter * 32) << 16) + c0);
+        if (P.flush_red == 3) {
+            float *g = blk32 + (size_t)(c0 >> 5) * 1024;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // the bulk reduction that last read this warp's 2 KB staging buffer must be done with it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    absmax = max(absmax, v[16 * h + j] & 0x7FFFFFFFu);
+                    stage[j * 32 + lane] = __uint_as_float(v[16 * h + j]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 :: "l"(g + h * 512), "r"(smem_u32(stage)), "r"(2048) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            continue;
+        }
+        if (P.flush_red == 4) {
+            float *g = blk32 + (size_t)(c0 >> 5) * 1024 + lane * 4;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                absmax = max(max(absmax, v[4 * q] & 0x7FFFFFFFu), v[4 * q + 1] & 0x7FFFFFFFu);
+                absmax = max(max(absmax, v[4 * q + 2] & 0x7FFFFFFFu), v[4 * q + 3] & 0x7FFFFFFFu);
+                asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                             :: "l"(g + q * 128), "f"(__uint_as_float(v[4 * q])),
+                                "f"(__uint_as_float(v[4 * q + 1])), "f"(__uint_as_float(v[4 * q + 2])),
+                                "f"(__uint_as_float(v[4 * q + 3])) : "memory");
+            }
+            continue;
+        }
         // element (row, col) of matrix m lives at ((m*256 + col) * 256 + row); c0 runs over
         // [C_tau cols 0..255 | C_00 cols 0..255] = m*256 + col directly
         double *dst = pc + (size_t)c0 * UM_D;
@@ -316,6 +358,40 @@ __device__ __forceinline__ void flush_share(const UmmaParams &P, uint32_t tmem, 
                 absmax = max(absmax, v[q * 8 + j] & 0x7FFFFFFFu);
                 __stcg(dst + (size_t)(q * 8 + j) * UM_D,
                        cur[j] + (double)__uint_as_float(v[q * 8 + j]));
+            }
+        }
+    }
+    if (P.flush_red >= 3 && fold) {
+        if (P.flush_red == 3) {
+            // every bulk reduction of this warp has been performed before its sums are read back
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int c0 = 32 * part; c0 < 512; c0 += 32 * nparts) {
+            float *g = blk32 + (size_t)(c0 >> 5) * 1024;
+            double *dst = pc + (size_t)c0 * UM_D;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float s[16];
+                double cur[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int jj = q * 16 + j;
+                    float *a = P.flush_red == 3 ? g + jj * 32 + lane
+                                                : g + ((jj >> 2) * 32 + lane) * 4 + (jj & 3);
+                    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(s[j]) : "l"(a) : "memory");
+                    cur[j] = __ldcg(dst + (size_t)jj * UM_D);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int jj = q * 16 + j;
+                    float *a = P.flush_red == 3 ? g + jj * 32 + lane
+                                                : g + ((jj >> 2) * 32 + lane) * 4 + (jj & 3);
+                    __stcg(dst + (size_t)jj * UM_D, cur[j] + (double)s[j]);
+                    __stcg(a, 0.f);
+                }
             }
         }
     }
@@ -363,6 +439,8 @@ tica_umma_kernel(const UmmaParams P)
     unsigned char *raw_ring = ring;                                   // [UM_STAGES][A raw | B raw]
     unsigned char *op_ring = ring + UM_STAGES * UM_RAW_BYTES;         // [UM_STAGES][A_hi|A_lo|B_hi|B_lo]
     UmmaSmem *ctl = reinterpret_cast<UmmaSmem *>(op_ring + UM_STAGES * UM_STAGE_BYTES);
+    // 2 KB per converter warp: staging of the TMA bulk-reduce drain (flush_red == 3)
+    float *drain_stage = reinterpret_cast<float *>(op_ring + UM_STAGES * UM_STAGE_BYTES + 1024);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (see elect_one)
@@ -588,7 +666,8 @@ tica_umma_kernel(const UmmaParams P)
             sAh = sAl = 0.f;
             if (!(P.dbg_mode & 2))
                 flush_share(P, tmem, pair, cta_rank, cw & 3, cw >> 2, 4, lane, absmax,
-                            ((next_flush + 1) % P.fold_every) == 0 || next_flush + 1 == n_slabs);
+                            ((next_flush + 1) % P.fold_every) == 0 || next_flush + 1 == n_slabs,
+                            drain_stage + cw * 512);
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0 && next_flush + 1 < n_slabs) mbar_arrive_cluster(&ctl->acc_empty, 0);
@@ -1277,7 +1356,9 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     }
 
     if (tiles > 0) {
-        const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + sizeof(UmmaSmem) + 1024;
+        const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + 1024 /* control block */
+                            + (size_t)UM_CONV_WARPS * 2048 /* drain staging */ + 1024 /* alignment */;
+        static_assert(sizeof(UmmaSmem) <= 1024, "control block");
         if (!g_attr_set[dev]) {
             MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_TF32>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
