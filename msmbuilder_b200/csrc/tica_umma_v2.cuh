@@ -1,0 +1,666 @@
+// tica_umma_v2.cuh -- K1, second generation of the fp16 3-product engine (included by tica_umma.cu).
+//
+// Same mathematics as tica_umma_kernel<UM_KIND_F16> (centred, power-of-two scaled frame x' = h + l in
+// fp16; raw moments rebuilt in float64 by the finalize kernel), reorganised around what the round-1
+// profile showed (tensor pipe 75 % active, 25 % lost to the TMEM drain):
+//
+//  * 5 products instead of 6.  C_00 = sum x x^T is symmetric, so only G = h (h/2)^T + h l^T is
+//    accumulated and C_00 = G + G^T (= h h^T + h l^T + l h^T) is formed by the finalize kernel.
+//    C_tau keeps its three products h b^T + h bl^T + l b^T.  Operand tiles per stage:
+//    a = h, al = l, ah = h / 2 (exact), b, bl  (8 KB each, K-major, no swizzle).
+//  * The drain is hidden.  TMEM holds FOUR accumulator regions (C_tau | C_00) x (column half 0 | 1);
+//    every UMMA is M x (N = RW) into one region.  The regions' slab boundaries are staggered by a
+//    quarter slab, so at any time at most one region is being drained; its MMAs are deferred (the
+//    operand ring is 4 deep) while the tensor pipe keeps working on the other three, and the region
+//    catches up as soon as its accumulators have been read out.
+//  * Dedicated drain warps (4: one per TMEM lane quarter) so the converters never stop:
+//    tcgen05.ld -> fire-and-forget red.global.add.f32 into this CTA's float32 level (L2 resident);
+//    the region is released as soon as its last column chunk is in registers.  Every `fold_every`
+//    slabs the float32 level moves into a float-float (hi, lo) pair with an error-free TwoSum.
+//    No FP64 instruction runs in this kernel at all (FP64 issued under a busy tensor pipe stalls for
+//    hundreds of cycles, profiles/r1_k1_issue.txt); the pairs become doubles in the finalize kernel.
+//  * template <CG>: CG = 2 is the CTA-pair kernel (cta_group::2, M = 256, D in (128, 256]);
+//    CG = 1 is the single-CTA kernel for D <= 128 (cta_group::1, M = 128, regions of 64 columns,
+//    148 independent CTAs): narrow inputs no longer pay 256-wide tiles (config 2, 10M x 64).
+//  * Bit-reproducible like v1: every address has one writer, all sums are taken in a fixed order.
+#pragma once
+
+namespace msmb {
+
+constexpr int V2_TILE = UM_KT * UM_F * 2;           // one fp16 component tile: 8 KB
+constexpr int V2_NTILES = 5;                        // a, al, ah, b, bl
+constexpr int V2_STAGE_BYTES = V2_NTILES * V2_TILE; // 40 KB
+constexpr int V2_RAW_STAGES = 2;
+constexpr int V2_OP_STAGES = 4;
+constexpr int V2_CONV_WARPS = 16;
+constexpr int V2_DRAIN_WARPS = 4;
+constexpr int V2_FIRST_DRAIN_WARP = 4 + V2_CONV_WARPS;              // 20: 20 % 4 == 0 -> lane quarter 0
+constexpr int V2_THREADS = 32 * (4 + V2_CONV_WARPS + V2_DRAIN_WARPS);   // 768
+constexpr int V2_REGIONS = 4;                       // (C_tau, C_00) x (column half 0, 1)
+constexpr int V2_T_A = 0, V2_T_AL = 1, V2_T_AH = 2, V2_T_B = 3, V2_T_BL = 4;
+
+struct V2Params {
+    const CUtensorMap *mapsA;     // [n_seq] unlagged
+    const CUtensorMap *mapsB;     // [n_seq] base shifted by lag rows
+    const int *tile_prefix;       // [n_seq + 1]
+    const int *seq_pairs;         // [n_seq]
+    int n_seq;
+    int n_tiles;
+    int n_groups;                 // CTA pairs (CG = 2) or CTAs (CG = 1)
+    int slab_tiles;               // 32-frame tiles per TMEM slab
+    int fold_every;               // slabs of a region between folds of the float32 level
+    int n_halves;                 // 2; 1 when D <= 64 (CG = 1): the upper column half does not exist
+    uint32_t h_add, h_mask;       // integer rounding of the h component
+    int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
+    const float *shift;           // [UM_D]
+    const float *scale;           // [UM_D]
+    int *overflow;                // set to 1 when an accumulator went non-finite (fp16 range)
+    float *lvl1;                  // [n_ctas][4][RW][128] float32 level (red.add target)
+    float *hi, *lo;               // same shape: float-float second level
+    double *sums;                 // [n_groups][UM_D] column sums of x' (unscaled)
+    long long *dbg;
+};
+
+struct V2Smem {
+    uint64_t raw_full[V2_RAW_STAGES];
+    uint64_t raw_empty[V2_RAW_STAGES];
+    uint64_t conv[V2_OP_STAGES];       // leader's copy is used; CG arrivals
+    uint64_t empty[V2_OP_STAGES];      // local; one commit arrival
+    uint64_t acc_full[V2_REGIONS];     // local; one commit arrival
+    uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 4 * CG arrivals
+    uint32_t tmem_base;
+    int valid_rows[V2_RAW_STAGES];
+};
+
+__device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return __shfl_sync(0xffffffffu, ok, 0);          // one answer for the whole warp
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// One UMMA (kind::f16, fp16 x fp16 -> fp32).  `mode` picks the collector hint for the A operand:
+// 0 none, 1 fill, 2 use, 3 lastuse -- the caller strings together the MMAs that share A.
+#define V2_MMA_ASM(CGS, VEC, QUAL) asm volatile( \
+    "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t" \
+    "@q tcgen05.mma.cta_group::" CGS ".kind::f16" QUAL " [%0], %1, %2, %3, " VEC ", p;\n\t}" \
+    :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(leader) : "memory")
+#define V2_VEC8 "{%5, %5, %5, %5, %5, %5, %5, %5}"
+#define V2_VEC4 "{%5, %5, %5, %5}"
+template <int CG>
+__device__ __forceinline__ void v2_mma(int mode, uint32_t tmem_d, uint64_t da, uint64_t db,
+                                       uint32_t idesc, uint32_t acc, uint32_t leader)
+{
+    if constexpr (CG == 2) {
+        switch (mode) {
+        case 1: V2_MMA_ASM("2", V2_VEC8, ".collector::a::fill"); break;
+        case 2: V2_MMA_ASM("2", V2_VEC8, ".collector::a::use"); break;
+        case 3: V2_MMA_ASM("2", V2_VEC8, ".collector::a::lastuse"); break;
+        default: V2_MMA_ASM("2", V2_VEC8, ""); break;
+        }
+    } else {
+        switch (mode) {
+        case 1: V2_MMA_ASM("1", V2_VEC4, ".collector::a::fill"); break;
+        case 2: V2_MMA_ASM("1", V2_VEC4, ".collector::a::use"); break;
+        case 3: V2_MMA_ASM("1", V2_VEC4, ".collector::a::lastuse"); break;
+        default: V2_MMA_ASM("1", V2_VEC4, ""); break;
+        }
+    }
+}
+// arrive on `bar` (in every CTA of the group) when all MMAs issued so far have completed
+template <int CG>
+__device__ __forceinline__ void v2_commit(uint64_t *bar, uint32_t leader)
+{
+    if constexpr (CG == 2) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+            "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            :: "r"(smem_u32(bar)), "h"((uint16_t)3), "r"(leader) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+            "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+            :: "r"(smem_u32(bar)), "r"(leader) : "memory");
+    }
+}
+// (fp16 x fp16) -> f32, K-major A and B, M = 128 * CG, N = 64 * CG
+template <int CG>
+__device__ __forceinline__ uint32_t v2_idesc()
+{
+    uint32_t d = 0;
+    d |= 1u << 4;                                   // D format F32; A, B format F16 = 0
+    d |= (uint32_t)((64 * CG) >> 3) << 17;          // N
+    d |= (uint32_t)((128 * CG) >> 4) << 24;         // M
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Params P)
+{
+    constexpr int RW = 64 * CG;                      // columns of a region = N of every UMMA
+    constexpr int TMEM_COLS = V2_REGIONS * RW;       // 512 (CG = 2) or 256 (CG = 1)
+    constexpr int S = V2_OP_STAGES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *ring = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *raw_ring = ring;                                        // [2][A raw | B raw]
+    unsigned char *op_ring = ring + V2_RAW_STAGES * UM_RAW_BYTES;          // [4][a|al|ah|b|bl]
+    V2Smem *ctl = reinterpret_cast<V2Smem *>(op_ring + S * V2_STAGE_BYTES);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    uint32_t cta_rank = 0;
+    if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int group = blockIdx.x / CG;
+    const int cta_global = blockIdx.x;
+
+    const long long t_begin = (long long)P.n_tiles * group / P.n_groups;
+    const long long t_end = (long long)P.n_tiles * (group + 1) / P.n_groups;
+    const int my_tiles = (int)(t_end - t_begin);
+    const int ST = P.slab_tiles;
+    // slab boundaries: staggered across groups (so the drains of the whole chip do not coincide)
+    // and by a quarter slab across the four regions of a group
+    const int slab_off = (int)(((long long)group * ST) / P.n_groups);
+    auto region_off = [&](int q) { return (slab_off + (q * ST) / V2_REGIONS) % ST; };
+    auto slab_first = [&](int q, int t) { return t == 0 || ((t + region_off(q)) % ST) == 0; };
+    auto slab_last = [&](int q, int t) { return ((t + region_off(q) + 1) % ST) == 0 || t + 1 == my_tiles; };
+    auto region_active = [&](int q) { return (q & 1) < P.n_halves; };
+
+    if (tid == 0) {
+        for (int s = 0; s < V2_RAW_STAGES; ++s) {
+            mbar_init(&ctl->raw_full[s], 1);
+            mbar_init(&ctl->raw_empty[s], 1);
+        }
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&ctl->conv[s], CG);
+            mbar_init(&ctl->empty[s], 1);
+        }
+        for (int q = 0; q < V2_REGIONS; ++q) {
+            mbar_init(&ctl->acc_full[q], 1);
+            mbar_init(&ctl->acc_empty[q], V2_DRAIN_WARPS * CG);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(&ctl->tmem_base)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(&ctl->tmem_base)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer (one lane, every CTA) =============
+        if (lane == 0 && my_tiles > 0) {
+            int s = 0;
+            {
+                int lo = 0, hi = P.n_seq;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (P.tile_prefix[mid] <= t_begin) lo = mid; else hi = mid;
+                }
+                s = lo;
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint64_t policy = l2_evict_first_policy();
+            for (long long t = t_begin; t < t_end; ++t) {
+                while (t >= P.tile_prefix[s + 1]) ++s;
+                const int row0 = (int)(t - P.tile_prefix[s]) * UM_KT;
+                int valid = P.seq_pairs[s] - row0;
+                if (valid > UM_KT) valid = UM_KT;
+                mbar_wait(&ctl->raw_empty[stage], phase ^ 1);
+                ctl->valid_rows[stage] = valid;
+                mbar_expect_tx(&ctl->raw_full[stage], 2 * UM_TILE_BYTES);
+                unsigned char *st = raw_ring + stage * UM_RAW_BYTES;
+                tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
+                tma_load_3d(st + UM_TILE_BYTES, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
+                            4 * (int)cta_rank, policy);
+                if (++stage == V2_RAW_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA; warp-uniform, one elected lane issues)
+        if (cta_rank == 0 && my_tiles > 0) {
+            const uint32_t leader = elect_one();
+            const uint32_t idesc = v2_idesc<CG>();
+            const uint32_t ring_addr = smem_u32(op_ring);
+            const bool dbg_on = P.dbg != nullptr && group == 0;
+            const long long d_start = clock64();
+            long long d_idle = 0, d_deferred = 0;
+            int nt[V2_REGIONS];                      // next tile of each region
+            uint32_t acc_ph[V2_REGIONS];
+#pragma unroll
+            for (int q = 0; q < V2_REGIONS; ++q) {
+                nt[q] = region_active(q) ? 0 : my_tiles;
+                acc_ph[q] = 0;
+            }
+            int conv_done = 0;                       // tiles whose conversion has been observed
+            int released = 0;                        // tiles whose operand stage has been handed back
+            while (released < my_tiles) {
+                while (conv_done < my_tiles && conv_done < released + S &&
+                       mbar_test(&ctl->conv[conv_done % S], (uint32_t)((conv_done / S) & 1)))
+                    ++conv_done;
+                bool progressed = false;
+                // every tile index some region is waiting at: batch the regions that can go
+                for (int tt = released; tt < conv_done; ++tt) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int q = 0; q < V2_REGIONS; ++q) {
+                        if (nt[q] != tt) continue;
+                        if (tt > 0 && slab_first(q, tt)) {
+                            // the region's previous slab must have left TMEM
+                            if (!mbar_test(&ctl->acc_empty[q], acc_ph[q])) {
+                                if (dbg_on) ++d_deferred;
+                                continue;
+                            }
+                            acc_ph[q] ^= 1;
+                        }
+                        mask |= 1u << q;
+                    }
+                    if (!mask) continue;
+                    progressed = true;
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t st = ring_addr + (uint32_t)(tt % S) * V2_STAGE_BYTES;
+                    const int n_tau = __popc(mask & 3u), n_00 = __popc(mask & 12u);
+                    const bool one_mma = (P.dbg_mode & 4) != 0;
+#pragma unroll
+                    for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                        const uint32_t off = ks * 2 * UM_LBO;
+                        const uint64_t dA = umma_desc(st + V2_T_A * V2_TILE + off);
+                        const uint64_t dAl = umma_desc(st + V2_T_AL * V2_TILE + off);
+                        // --- the MMAs whose A operand is a (= h of the unlagged frames)
+                        int left = 2 * n_tau + 2 * n_00;        // MMAs sharing A = a
+                        int idx = 0;
+#pragma unroll
+                        for (int q = 0; q < V2_REGIONS; ++q) {
+                            if (!(mask & (1u << q))) continue;
+                            const uint32_t hb = (uint32_t)(q & 1) * (64 * 16);   // column half: 64 features on
+                            const uint32_t d = tmem + (uint32_t)(RW * q);
+                            const uint32_t first = (ks == 0 && slab_first(q, tt)) ? 0u : 1u;
+                            const uint32_t t0 = q < 2 ? V2_T_B : V2_T_AH, t1 = q < 2 ? V2_T_BL : V2_T_AL;
+                            const uint64_t dB0 = umma_desc(st + t0 * V2_TILE + off + hb);
+                            const uint64_t dB1 = umma_desc(st + t1 * V2_TILE + off + hb);
+                            int m0 = left == 1 ? 0 : idx == 0 ? 1 : idx == left - 1 ? 3 : 2;
+                            v2_mma<CG>(m0, d, dA, dB0, idesc, first, leader);
+                            ++idx;
+                            if (one_mma) continue;
+                            int m1 = idx == left - 1 ? 3 : 2;
+                            v2_mma<CG>(m1, d, dA, dB1, idesc, 1u, leader);
+                            ++idx;
+                        }
+                        // --- the MMAs whose A operand is al (C_tau only)
+                        if (!one_mma) {
+                            int k = 0;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                if (!(mask & (1u << q))) continue;
+                                const uint32_t hb = (uint32_t)(q & 1) * (64 * 16);
+                                const uint64_t dB = umma_desc(st + V2_T_B * V2_TILE + off + hb);
+                                int m = n_tau == 1 ? 0 : k == 0 ? 1 : 3;
+                                v2_mma<CG>(m, tmem + (uint32_t)(RW * q), dAl, dB, idesc, 1u, leader);
+                                ++k;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < V2_REGIONS; ++q) {
+                        if (!(mask & (1u << q))) continue;
+                        nt[q] = tt + 1;
+                        if (slab_last(q, tt)) v2_commit<CG>(&ctl->acc_full[q], leader);
+                    }
+                }
+                int low = my_tiles;
+#pragma unroll
+                for (int q = 0; q < V2_REGIONS; ++q)
+                    if (region_active(q) && nt[q] < low) low = nt[q];
+                for (; released < low; ++released) v2_commit<CG>(&ctl->empty[released % S], leader);
+                if (!progressed) {
+                    if (dbg_on) { const long long c = clock64(); __nanosleep(20); d_idle += clock64() - c; }
+                    else __nanosleep(20);
+                }
+            }
+            if (dbg_on && lane == 0) {
+                P.dbg[0] = clock64() - d_start;
+                P.dbg[1] = d_idle;
+                P.dbg[2] = d_deferred;
+                P.dbg[3] = my_tiles;
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + V2_CONV_WARPS) {
+        // ================================ converters (512 threads, every CTA) ==========
+        // warp cw: feature block cw & 3 (32 features, lane = feature), frame octet cw >> 2.  A thread
+        // gathers 8 frames of its feature with conflict-free 4-byte shared loads from the swizzled
+        // raw tile (this is the transpose), centres / scales / splits, stores 16-byte K-major chunks.
+        const int cw = warp - 4;
+        const int fb = cw & 3, kq = cw >> 2;
+        const int f_local = 32 * fb + lane;
+        const int chunk = lane >> 2, within = (lane & 3) * 4;
+        const float sh = P.shift[UM_F * cta_rank + f_local];
+        const float sc = P.scale[UM_F * cta_rank + f_local];
+        const float nsh = -sh * sc;
+        const uint32_t h_add = P.h_add, h_mask = P.h_mask;
+        float sAh = 0.f, sAl = 0.f;                  // column sum of the unlagged rows as a float pair
+        int stage = 0, ostage = 0;
+        uint32_t phase = 0, ophase = 0;
+        const bool dbg_on = P.dbg != nullptr && group == 0 && tid == 128 && cta_rank == 0;
+        long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            long long q0 = dbg_on ? clock64() : 0;
+            mbar_wait(&ctl->raw_full[stage], phase);
+            long long q1 = dbg_on ? clock64() : 0;
+            mbar_wait(&ctl->empty[ostage], ophase ^ 1);
+            long long q2 = dbg_on ? clock64() : 0;
+            const int valid = ctl->valid_rows[stage];
+            const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
+            unsigned char *st = op_ring + ostage * V2_STAGE_BYTES;
+            float tsA = 0.f;
+            auto convert_tile = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
+                for (int op = 0; op < 2; ++op) {
+                    const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
+                    unsigned char *h_buf = st + (op == 0 ? V2_T_A : V2_T_B) * V2_TILE + f_local * 16;
+                    unsigned char *l_buf = st + (op == 0 ? V2_T_AL : V2_T_BL) * V2_TILE + f_local * 16;
+                    float h[8], l[8];
+                    float s8 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 8 * kq + i;
+                        const float v = *reinterpret_cast<const float *>(
+                            raw + r * 128 + ((chunk ^ (r & 7)) << 4));
+                        const float as = (FULL || r < valid) ? fmaf(v, sc, nsh) : 0.f;
+                        s8 += as;
+                        h[i] = __uint_as_float((__float_as_uint(as) + h_add) & h_mask);
+                        l[i] = as - h[i];
+                    }
+                    uint4 hw, lw;
+                    hw.x = pack_f16(h[0], h[1]); hw.y = pack_f16(h[2], h[3]);
+                    hw.z = pack_f16(h[4], h[5]); hw.w = pack_f16(h[6], h[7]);
+                    lw.x = pack_f16(l[0], l[1]); lw.y = pack_f16(l[2], l[3]);
+                    lw.z = pack_f16(l[4], l[5]); lw.w = pack_f16(l[6], l[7]);
+                    *reinterpret_cast<uint4 *>(h_buf + kq * UM_LBO) = hw;
+                    *reinterpret_cast<uint4 *>(l_buf + kq * UM_LBO) = lw;
+                    if (op == 0) {
+                        tsA += s8;
+                        // h / 2 (one exact fp16 multiply per pair): the second factor of the C_00 product
+                        uint4 hh;
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.x) : "r"(hw.x), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.y) : "r"(hw.y), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.z) : "r"(hw.z), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.w) : "r"(hw.w), "r"(0x38003800u));
+                        *reinterpret_cast<uint4 *>(st + V2_T_AH * V2_TILE + f_local * 16 + kq * UM_LBO) = hh;
+                    }
+                }
+            };
+            if (P.dbg_mode & 1) { /* timing experiment: no conversion traffic */ }
+            else if (valid == UM_KT) convert_tile(std::true_type());
+            else convert_tile(std::false_type());
+            {   // TwoSum: (sAh, sAl) += tsA without losing the rounding error
+                const float tt = sAh + tsA, bp = tt - sAh;
+                sAl += (sAh - (tt - bp)) + (tsA - bp);
+                sAh = tt;
+            }
+            long long q3 = dbg_on ? clock64() : 0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
+            if (tid == 128) {
+                mbar_arrive_local(&ctl->raw_empty[stage]);
+                if constexpr (CG == 2) mbar_arrive_cluster(&ctl->conv[ostage], 0);
+                else mbar_arrive_local(&ctl->conv[ostage]);
+            }
+            if (dbg_on) { long long q4 = clock64(); d_raw += q1 - q0; d_empty += q2 - q1; d_comp += q3 - q2; d_sync += q4 - q3; }
+            if (++stage == V2_RAW_STAGES) { stage = 0; phase ^= 1; }
+            if (++ostage == S) { ostage = 0; ophase ^= 1; }
+        }
+        if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync; }
+        // column sums: the 4 warps that share a feature combine through shared memory in a fixed
+        // order (the raw ring is idle: every TMA load has landed and been converted); the doubles
+        // appear only here, after this CTA's last tile
+        {
+            double *s_sum = reinterpret_cast<double *>(raw_ring);        // [4][UM_F]
+            s_sum[kq * UM_F + f_local] = ((double)sAh + (double)sAl) / (double)sc;
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
+            if (kq == 0)
+                P.sums[(size_t)group * UM_D + UM_F * cta_rank + f_local] =
+                    ((s_sum[f_local] + s_sum[UM_F + f_local]) + s_sum[2 * UM_F + f_local]) + s_sum[3 * UM_F + f_local];
+        }
+    } else if (warp >= V2_FIRST_DRAIN_WARP) {
+        // ================================ drain warps (one per TMEM lane quarter, every CTA) ======
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;                     // accumulator row = feature in this CTA
+        const size_t cta_base = (size_t)cta_global * V2_REGIONS * RW * UM_F;
+        int next_end[V2_REGIONS], slabs_done[V2_REGIONS];
+        uint32_t full_ph[V2_REGIONS];
+        uint32_t absmax = 0;
+        const bool dbg_on = P.dbg != nullptr && group == 0 && cta_rank == 0 && quarter == 0 && lane == 0;
+        long long d_wait = 0, d_ld = 0, d_red = 0, d_fold = 0, n_events = 0;
+#pragma unroll
+        for (int q = 0; q < V2_REGIONS; ++q) {
+            int e = ST - 1 - region_off(q);
+            if (e > my_tiles - 1) e = my_tiles - 1;
+            next_end[q] = (region_active(q) && my_tiles > 0) ? e : 0x7fffffff;
+            slabs_done[q] = 0;
+            full_ph[q] = 0;
+        }
+        while (true) {
+            int q = 0;
+#pragma unroll
+            for (int r = 1; r < V2_REGIONS; ++r)
+                if (next_end[r] < next_end[q]) q = r;
+            const int e = next_end[q];
+            if (e == 0x7fffffff) break;
+            const bool last = e == my_tiles - 1;
+            const bool fold = last || ((slabs_done[q] + 1) % P.fold_every) == 0;
+            const long long c0 = dbg_on ? clock64() : 0;
+            mbar_wait(&ctl->acc_full[q], full_ph[q]);
+            full_ph[q] ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const long long c1 = dbg_on ? clock64() : 0;
+            float *l1 = P.lvl1 + cta_base + (size_t)q * RW * UM_F + row;
+            long long t_ld = 0;
+            if (!(P.dbg_mode & 2)) {
+#pragma unroll 1
+                for (int c = 0; c < RW / 32; ++c) {
+                    uint32_t v[32];
+                    const long long a0 = dbg_on ? clock64() : 0;
+                    UM_TMEM_LD32(v, tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RW * q + 32 * c));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c == RW / 32 - 1) {
+                        // the region's accumulators are in registers: hand TMEM back before the
+                        // reductions are issued
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        __syncwarp();
+                        if (lane == 0 && !last) {
+                            if constexpr (CG == 2) mbar_arrive_cluster(&ctl->acc_empty[q], 0);
+                            else mbar_arrive_local(&ctl->acc_empty[q]);
+                        }
+                    }
+                    if (dbg_on) t_ld += clock64() - a0;
+                    float *dst = l1 + (size_t)(32 * c) * UM_F;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        absmax = max(absmax, v[j] & 0x7FFFFFFFu);     // Inf / NaN sort above every finite value
+                        asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;"
+                                     :: "l"(dst + (size_t)j * UM_F), "f"(__uint_as_float(v[j])) : "memory");
+                    }
+                }
+            } else {
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0 && !last) {
+                    if constexpr (CG == 2) mbar_arrive_cluster(&ctl->acc_empty[q], 0);
+                    else mbar_arrive_local(&ctl->acc_empty[q]);
+                }
+            }
+            const long long c2 = dbg_on ? clock64() : 0;
+            if (fold) {
+                // float32 level -> float-float pair, error-free (TwoSum), then clear the level.  This
+                // warp is the only one that ever touches these addresses; its own reductions above
+                // are ordered before these loads (same thread, same address, gpu scope).
+                float *hi = P.hi + cta_base + (size_t)q * RW * UM_F + row;
+                float *lo = P.lo + cta_base + (size_t)q * RW * UM_F + row;
+#pragma unroll 1
+                for (int c = 0; c < RW; c += 16) {
+                    float s[16], H[16], L[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];"
+                                     : "=f"(s[j]) : "l"(l1 + (size_t)(c + j) * UM_F) : "memory");
+                        H[j] = __ldcg(hi + (size_t)(c + j) * UM_F);
+                        L[j] = __ldcg(lo + (size_t)(c + j) * UM_F);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float t = H[j] + s[j], bp = t - H[j];
+                        const float err = (H[j] - (t - bp)) + (s[j] - bp);
+                        __stcg(hi + (size_t)(c + j) * UM_F, t);
+                        __stcg(lo + (size_t)(c + j) * UM_F, L[j] + err);
+                        __stcg(l1 + (size_t)(c + j) * UM_F, 0.f);
+                    }
+                }
+            }
+            if (dbg_on) {
+                const long long c3 = clock64();
+                d_wait += c1 - c0; d_ld += t_ld; d_red += (c2 - c1) - t_ld; d_fold += c3 - c2; ++n_events;
+            }
+            ++slabs_done[q];
+            if (last) next_end[q] = 0x7fffffff;
+            else next_end[q] = e + ST < my_tiles - 1 ? e + ST : my_tiles - 1;
+        }
+        if (absmax >= 0x7F800000u) atomicOr(P.overflow, 1);
+        if (dbg_on) { P.dbg[8] = d_wait; P.dbg[9] = d_ld; P.dbg[10] = d_red; P.dbg[11] = d_fold; P.dbg[12] = n_events; }
+    }
+
+    // teardown: nobody may still be using the peer's barriers / TMEM
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();
+    if (warp == 2) {
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// reduce the CTA partials (float-float pairs -> double), symmetrise C_00, add the float64 edge
+// terms, undo scale and shift, add into `acc`.  When the fp16 range check tripped (*rescued != 0)
+// the v1 bf16 kernel rewrote the SAME memory as its float64 partials ([pair][2][col][row], unscaled).
+template <int CG>
+__global__ void __launch_bounds__(256)
+tica_umma_v2_finalize_kernel(const float *__restrict__ hi, const float *__restrict__ lo,
+                             const double *__restrict__ v1_partials, int n_groups, int v1_pairs,
+                             const double *__restrict__ sums, int n_sum_groups_v1,
+                             const double *__restrict__ E, const double *__restrict__ es,
+                             const float *__restrict__ shift, const float *__restrict__ scale,
+                             const int *__restrict__ rescued, double n_pairs_total, double n_obs,
+                             double n_seq, int Dr, double *__restrict__ acc)
+{
+    constexpr int D = UM_D;
+    constexpr int RW = 64 * CG;
+    const size_t DD = (size_t)D * D;
+    const size_t RR = (size_t)Dr * Dr;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int)RR) return;
+    const int i = idx / Dr, j = idx % Dr;
+    const bool resc = *rescued != 0;
+    double ctau = 0.0, c00 = 0.0;
+    int n_sum_groups;
+    if (!resc) {
+        // element (row i, feature column j) of matrix m: CTA i / 128 of the group, region 2 m + half,
+        // column (j / 128) * 64 + j % 64 of the region (half = (j % 128) / 64), row i % 128
+        auto at = [&](int g, int m, int r, int cidx) -> double {
+            const int cta = g * CG + r / UM_F;
+            const int half = (cidx % UM_F) / 64;
+            const int col = (cidx / UM_F) * 64 + (cidx % 64);
+            const size_t a = ((size_t)cta * V2_REGIONS + (size_t)(2 * m + half)) * RW * UM_F
+                             + (size_t)col * UM_F + (size_t)(r % UM_F);
+            return (double)hi[a] + (double)lo[a];
+        };
+        for (int g = 0; g < n_groups; ++g) {
+            ctau += at(g, 0, i, j);
+            c00 += at(g, 1, i, j) + at(g, 1, j, i);      // C_00 = G + G^T
+        }
+        const double inv = 1.0 / ((double)scale[i] * (double)scale[j]);
+        ctau *= inv;
+        c00 *= inv;
+        n_sum_groups = n_groups;
+    } else {
+        const size_t tidx = (size_t)j * D + i;
+        for (int p = 0; p < v1_pairs; ++p) {
+            ctau += v1_partials[(size_t)p * 2 * DD + tidx];
+            c00 += v1_partials[(size_t)p * 2 * DD + DD + tidx];
+        }
+        n_sum_groups = n_sum_groups_v1;
+    }
+    const size_t pidx = (size_t)i * D + j;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    double esi[2] = {0.0, 0.0}, esj[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < UM_EDGE_SLOTS; ++c) {
+        const double *Ec = E + (size_t)c * 4 * DD;
+        const double *ec = es + (size_t)c * 3 * D;
+        e0 += Ec[pidx];
+        e1 += Ec[DD + pidx];
+        e2 += Ec[2 * DD + pidx];
+        e3 += Ec[3 * DD + pidx];
+        esi[0] += ec[i];
+        esi[1] += ec[D + i];
+        esj[0] += ec[j];
+        esj[1] += ec[D + j];
+        esj[2] += ec[2 * D + j];
+    }
+    double sum_i = 0.0, sum_j = 0.0;
+    for (int p = 0; p < n_sum_groups; ++p) {
+        sum_i += sums[(size_t)p * D + i];
+        sum_j += sums[(size_t)p * D + j];
+    }
+    ctau += e0;
+    c00 += e1;
+    const double ctt = c00 - e2 + e3;
+    const double si = (double)shift[i], sj = (double)shift[j];
+    const double S0i = sum_i + esi[0], S0j = sum_j + esj[0];
+    const double Sti = sum_i + esi[1], Stj = sum_j + esj[1];
+    const double Np = n_pairs_total;
+    acc[idx] += ctau + S0i * sj + si * Stj + Np * si * sj;
+    acc[RR + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
+    acc[2 * RR + idx] += ctt + Sti * sj + si * Stj + Np * si * sj;
+    if (i == 0) {
+        const double S0 = S0j, St = Stj;
+        const double Sall = S0 + esj[2];
+        acc[3 * RR + j] += S0 + Np * sj;
+        acc[3 * RR + Dr + j] += St + Np * sj;
+        acc[3 * RR + 2 * Dr + j] += Sall + n_obs * sj;
+        if (j == 0) {
+            acc[3 * RR + 3 * Dr] += n_obs;
+            acc[3 * RR + 3 * Dr + 1] += n_seq;
+        }
+    }
+}
+
+__global__ void tica_umma_rescue_clear32_kernel(const int *__restrict__ flag, float *__restrict__ buf, size_t n)
+{
+    if (*flag == 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        buf[i] = 0.f;
+}
+
+}  // namespace msmb

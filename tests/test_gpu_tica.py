@@ -237,12 +237,16 @@ def test_umma_f16_engine_feature_scales():
 
 
 def test_umma_f16_engine_range_rescue():
-    # a later excursion 10^7 times the spread of the first 512 frames leaves fp16's range: the
-    # call must redo itself with the bf16 engine on the stream and still match float64
+    # an excursion 10^7 times the spread of the shift/scale sample leaves fp16's range: the call
+    # must redo itself with the bf16 engine on the stream and still match float64.  The sample is
+    # frame floor(j * 8000 / 1024) of the concatenated call (tica_shift_kernel), so the excursions
+    # sit on frames between two sample points (global 7001..7005 and 7501).
     seqs = ar1_numpy(2, 4000, 256, seed=26)
     seqs[1] = seqs[1].copy()
-    seqs[1][3000:3100, 5] += 3.0e7
-    seqs[1][3500, 200] = -8.0e6
+    sampled = {(j * 8000) // 1024 for j in range(1024)}
+    assert not (sampled & set(range(7001, 7006))) and 7501 not in sampled
+    seqs[1][3001:3006, 5] += 3.0e7
+    seqs[1][3501, 200] = -8.0e6
     a, b = _umma_vs_simt(seqs, 10, engine="umma_3xf16")
     c = _umma_vs_simt(seqs, 10, engine="umma_6xbf16")[1]
     assert a.n_observations_ == b.n_observations_
