@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libmsmb200.so")
 SOURCES = ["lib.cu", "dist_kernels.cu", "kcenters_lookahead.cu", "tica_simt.cu", "tica_umma.cu", "rmsd.cu",
            "scan_kernels.cu", "kmedoids_host.cpp"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "msmb200.h")]
+HEADERS = ["common.cuh", "tica_umma_v2.cuh", os.path.join("..", "..", "include", "msmb200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

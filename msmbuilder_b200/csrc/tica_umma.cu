@@ -859,40 +859,56 @@ tica_umma_kernel(const UmmaParams P)
 // later excursion (an excursion beyond 2^15 m still trips the range check -> bf16 rescue).
 // Any shift / scale gives the same moments up to rounding: they only set where the roundings fall.
 constexpr int UM_SAMPLE_ROWS = 1024;
+constexpr int UM_SAMPLE_BLOCKS = 32;            // 32 sample rows per block
 struct EdgeSeq {
     const float *base;
     long long n;
 };
-__global__ void tica_shift_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long total,
-                                  long long ld, int D, float *__restrict__ shift,
-                                  float *__restrict__ scale)
+// The host resolves the sample rows to pointers (sample[j] = first feature of frame
+// floor(j * total / rows) of the concatenated call); three tiny launches then take the mean and the
+// largest centred magnitude over the sample with every partial result added in a fixed order.
+__global__ void __launch_bounds__(UM_D)
+tica_sample_sum_kernel(const float *const *__restrict__ sample, int rows, int D,
+                       double *__restrict__ psum /* [UM_SAMPLE_BLOCKS][UM_D] */)
 {
-    const long long rows = total < UM_SAMPLE_ROWS ? total : UM_SAMPLE_ROWS;
+    const int c = threadIdx.x, b = blockIdx.x;
+    double s = 0.0;
+    if (c < D)
+        for (int j = b * 32; j < rows && j < b * 32 + 32; ++j) s += (double)sample[j][c];
+    psum[b * UM_D + c] = s;
+}
+__global__ void __launch_bounds__(UM_D)
+tica_sample_max_kernel(const float *const *__restrict__ sample, int rows, int D,
+                       const double *__restrict__ psum, float *__restrict__ pmax)
+{
+    const int c = threadIdx.x, b = blockIdx.x;
+    double s = 0.0;
+    for (int k = 0; k < UM_SAMPLE_BLOCKS; ++k) s += psum[k * UM_D + c];
+    const float sh = (float)(s / (double)rows);
+    float m = 0.f;
+    if (c < D)
+        for (int j = b * 32; j < rows && j < b * 32 + 32; ++j) m = fmaxf(m, fabsf(sample[j][c] - sh));
+    pmax[b * UM_D + c] = m;
+}
+__global__ void __launch_bounds__(UM_D)
+tica_shift_kernel(const double *__restrict__ psum, const float *__restrict__ pmax, int rows, int D,
+                  float *__restrict__ shift, float *__restrict__ scale)
+{
     // shift[] is padded to UM_D entries; features >= D do not exist (TMA zero-fills them)
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < UM_D; c += gridDim.x * blockDim.x) {
-        float sh = 0.f, m = 0.f;
-        if (c < D) {
-            for (int pass = 0; pass < 2; ++pass) {
-                double s = 0.0;
-                int q = 0;
-                long long before = 0;                 // frames in sequences < q
-                for (long long j = 0; j < rows; ++j) {
-                    const long long g = j * total / rows;          // j < 1024: no overflow below 2^53 frames
-                    while (g >= before + seqs[q].n) { before += seqs[q].n; ++q; }
-                    const float v = seqs[q].base[(g - before) * ld + c];
-                    if (pass == 0) s += (double)v;
-                    else m = fmaxf(m, fabsf(v - sh));
-                }
-                if (pass == 0) sh = (float)(s / (double)rows);
-            }
-        }
-        shift[c] = sh;
-        m = fmaxf(m, fabsf(sh) * (1.f / 256.f));
-        int e = 0;
-        if (m > 0.f && m < INFINITY) e = ilogbf(m);
-        e = e < -100 ? -100 : (e > 100 ? 100 : e);
-        scale[c] = ldexpf(1.f, -e);
+    const int c = threadIdx.x;
+    double s = 0.0;
+    float m = 0.f;
+    for (int k = 0; k < UM_SAMPLE_BLOCKS; ++k) {
+        s += psum[k * UM_D + c];
+        m = fmaxf(m, pmax[k * UM_D + c]);
     }
+    const float sh = c < D ? (float)(s / (double)rows) : 0.f;
+    shift[c] = sh;
+    m = fmaxf(m, fabsf(sh) * (1.f / 256.f));
+    int e = 0;
+    if (m > 0.f && m < INFINITY) e = ilogbf(m);
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    scale[c] = ldexpf(1.f, -e);
 }
 
 // rescue path of the fp16 engine: when the range check tripped, forget what that launch wrote
@@ -992,9 +1008,11 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
                           const double *__restrict__ es, const float *__restrict__ shift,
                           const float *__restrict__ scale /* NULL: partials are unscaled */,
                           const int *__restrict__ rescued /* != 0: the bf16 rescue wrote them */,
+                          int only_if_rescued /* v2 engine: this kernel only finishes a rescued call */,
                           double n_pairs_total /* sum_s (n_s - lag) */, double n_obs, double n_seq,
                           int Dr, double *__restrict__ acc)
 {
+    if (only_if_rescued && *rescued == 0) return;
     constexpr int D = UM_D;                              // padded scratch width
     const size_t DD = (size_t)D * D;                     // scratch matrix size
     const size_t RR = (size_t)Dr * Dr;                   // output matrix size
@@ -1060,6 +1078,10 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
     }
 }
 
+}  // namespace msmb
+#include "tica_umma_v2.cuh"
+namespace msmb {
+
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -1093,7 +1115,10 @@ static constexpr int UM_MAX_PAIRS = 96;
 static size_t ws_fixed_bytes(int D)
 {
     const size_t DD = (size_t)D * D;
-    return 4096 + sizeof(double) * ((size_t)UM_MAX_PAIRS * D + (size_t)UM_EDGE_SLOTS * (4 * DD + 3 * D)) + 1024;
+    // shift, scale, flag | sample partials | sums | E | es | R (v2 group sums) + alignment slack
+    return 4096 + (sizeof(double) + sizeof(float)) * (size_t)UM_SAMPLE_BLOCKS * UM_D
+           + sizeof(double) * ((size_t)V2_MAX_GROUPS * D + (size_t)UM_EDGE_SLOTS * (4 * DD + 3 * D) + 2 * DD)
+           + 4096;
 }
 size_t tica_umma_workspace_bytes(int D)
 {
@@ -1194,14 +1219,17 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (n_seq == 0) return MSMB200_OK;
 
     // per-call tables, laid out once and built straight into a pinned staging buffer:
-    //   [mapsA | mapsB | tile_prefix | seq_pairs | edge seqs]
+    //   [mapsA | mapsB | tile_prefix | seq_pairs | edge seqs | sample row pointers]
     auto align_up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    const long long total_rows = (long long)n_obs;
+    const int sample_rows = (int)(total_rows < UM_SAMPLE_ROWS ? total_rows : UM_SAMPLE_ROWS);
     size_t off = 0;
     const size_t o_mapsA = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
     const size_t o_mapsB = off; off = align_up(off + sizeof(CUtensorMap) * n_seq, 128);
     const size_t o_prefix = off; off = align_up(off + sizeof(int) * (n_seq + 1), 128);
     const size_t o_blocks = off; off = align_up(off + sizeof(int) * n_seq, 128);
     const size_t o_eseq = off; off = align_up(off + sizeof(EdgeSeq) * n_seq, 128);
+    const size_t o_sample = off; off = align_up(off + sizeof(const float *) * UM_SAMPLE_ROWS, 128);
     int dev = 0;
     MSMB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= UM_MAX_DEVICES) {
@@ -1220,6 +1248,18 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     int *tile_prefix = reinterpret_cast<int *>(hb + o_prefix);
     int *seq_pairs = reinterpret_cast<int *>(hb + o_blocks);
     memcpy(hb + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq);
+    {
+        // sample row j = frame floor(j * total / rows) of the concatenated call
+        const float **sample = reinterpret_cast<const float **>(hb + o_sample);
+        int q = 0;
+        long long before = 0;
+        for (int j = 0; j < sample_rows; ++j) {
+            const long long g = (long long)(((__int128)j * total_rows) / sample_rows);
+            while (g >= before + seqs[q].n) { before += seqs[q].n; ++q; }
+            sample[j] = seqs[q].base + (size_t)(g - before) * (size_t)ld;
+        }
+        for (int j = sample_rows; j < UM_SAMPLE_ROWS; ++j) sample[j] = nullptr;
+    }
     if (g_map_cache.size() > (1u << 16)) g_map_cache.clear();
     long long tiles = 0;
     for (int s = 0; s < n_seq; ++s) {
@@ -1262,12 +1302,29 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     }
     tile_prefix[n_seq] = (int)tiles;
 
+    const bool f16 = passes == 23;                  // 23 = 3xF16 (see lib.cu)
+    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16: 2-byte operands, K = 16
+    // second-generation fp16 engine (tica_umma_v2.cuh): single-CTA tiles for D <= 128, CTA pairs above
+    const bool v2 = f16 && env_int("MSMB200_UMMA_V1", 0) == 0;
+    const int v2_cg = D <= UM_F ? 1 : 2;
+
+    // v1 CTA pairs (also the rescue engine of v2)
     int n_pairs = sm_count() / 2;
     n_pairs = env_int("MSMB200_UMMA_PAIRS", n_pairs);
     if (n_pairs > UM_MAX_PAIRS) n_pairs = UM_MAX_PAIRS;
     if (tiles < n_pairs) n_pairs = (int)(tiles > 0 ? tiles : 1);
+    // v2 groups: CTA pairs (CG = 2) or single CTAs (CG = 1)
+    int n_groups = sm_count() / v2_cg;
+    n_groups = env_int("MSMB200_UMMA_GROUPS", n_groups);
+    if (n_groups > V2_MAX_GROUPS) n_groups = V2_MAX_GROUPS;
+    if (n_groups > UM_MAX_PAIRS * 2 / v2_cg) n_groups = UM_MAX_PAIRS * 2 / v2_cg;   // fits the partial area
+    if (tiles < n_groups) n_groups = (int)(tiles > 0 ? tiles : 1);
     const size_t DD = (size_t)UM_D * UM_D;          // scratch is always 256 wide
-    const size_t need = ws_fixed_bytes(UM_D) + (sizeof(double) + sizeof(float)) * 2 * DD * n_pairs;
+    const size_t v1_part_bytes = (sizeof(double) + sizeof(float)) * 2 * DD * n_pairs;
+    const size_t v2_per_cta = (size_t)V2_REGIONS * (64 * v2_cg) * UM_F;            // floats per array
+    const size_t v2_part_bytes = v2 ? 3 * sizeof(float) * v2_per_cta * (size_t)(n_groups * v2_cg) : 0;
+    const size_t part_bytes = v1_part_bytes > v2_part_bytes ? v1_part_bytes : v2_part_bytes;
+    const size_t need = ws_fixed_bytes(UM_D) + part_bytes;
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
         set_error("tica_accumulate: workspace too small or misaligned (%zu < %zu); size it with "
                   "msmb200_tica_workspace_bytes", workspace_bytes, need);
@@ -1285,17 +1342,20 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     // device copy of the tables: stream-ordered allocation
     unsigned char *scratch = nullptr;
     MSMB_CUDA(cudaMallocAsync(&scratch, off, st));
-    // big zero-initialised part: caller's workspace  [shift | sums | E | es | partials]
+    // big zero-initialised part: caller's workspace
+    //   [shift | scale | psum | pmax | flag | sums | E | es | R | partials]
     unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
     size_t woff = 0;
     const size_t w_shift = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
     const size_t w_scale = woff; woff = align_up(woff + sizeof(float) * UM_D, 256);
+    const size_t w_psum = woff; woff = align_up(woff + sizeof(double) * UM_SAMPLE_BLOCKS * UM_D, 256);
+    const size_t w_pmax = woff; woff = align_up(woff + sizeof(float) * UM_SAMPLE_BLOCKS * UM_D, 256);
     const size_t w_flag = woff; woff = align_up(woff + sizeof(int), 256);       // zeroed with the rest
-    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * (size_t)UM_MAX_PAIRS * UM_D, 256);
+    const size_t w_sums = woff; woff = align_up(woff + sizeof(double) * (size_t)V2_MAX_GROUPS * UM_D, 256);
     const size_t w_E = woff; woff = align_up(woff + sizeof(double) * UM_EDGE_SLOTS * 4 * DD, 256);
     const size_t w_es = woff; woff = align_up(woff + sizeof(double) * UM_EDGE_SLOTS * 3 * UM_D, 256);
-    const size_t w_part = woff; woff += sizeof(double) * 2 * DD * n_pairs;
-    const size_t w_part32 = woff; woff += sizeof(float) * 2 * DD * n_pairs;
+    const size_t w_R = woff; woff = align_up(woff + sizeof(double) * 2 * DD, 256);
+    const size_t w_part = woff; woff += v2 ? v2_part_bytes : v1_part_bytes;
     MSMB_CUDA(cudaMemsetAsync(wsb + w_flag, 0, woff - w_flag, st));
 
     // ONE asynchronous copy from pinned memory; the slot is reusable once `done` has passed
@@ -1307,9 +1367,17 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     float *d_shift = reinterpret_cast<float *>(wsb + w_shift);
     float *d_scale = reinterpret_cast<float *>(wsb + w_scale);
     int *d_flag = reinterpret_cast<int *>(wsb + w_flag);
-    tica_shift_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const EdgeSeq *>(scratch + o_eseq), n_seq,
-                                         (long long)n_obs, ld, D, d_shift, d_scale);
-    MSMB_LAUNCH_CHECK();
+    {
+        const float *const *d_sample = reinterpret_cast<const float *const *>(scratch + o_sample);
+        double *d_psum = reinterpret_cast<double *>(wsb + w_psum);
+        float *d_pmax = reinterpret_cast<float *>(wsb + w_pmax);
+        tica_sample_sum_kernel<<<UM_SAMPLE_BLOCKS, UM_D, 0, st>>>(d_sample, sample_rows, D, d_psum);
+        MSMB_LAUNCH_CHECK();
+        tica_sample_max_kernel<<<UM_SAMPLE_BLOCKS, UM_D, 0, st>>>(d_sample, sample_rows, D, d_psum, d_pmax);
+        MSMB_LAUNCH_CHECK();
+        tica_shift_kernel<<<1, UM_D, 0, st>>>(d_psum, d_pmax, sample_rows, D, d_shift, d_scale);
+        MSMB_LAUNCH_CHECK();
+    }
 
     UmmaParams P;
     P.mapsA = reinterpret_cast<const CUtensorMap *>(scratch + o_mapsA);
@@ -1319,8 +1387,6 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.n_seq = n_seq;
     P.n_tiles = (int)tiles;
     P.n_pairs = n_pairs;
-    const bool f16 = passes == 23;                  // 23 = 3xF16 (see lib.cu)
-    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16: 2-byte operands, K = 16
     // bf16 MMAs cover 16 frames per accumulate step (tf32: 8), so twice the frames per slab
     // carry the same truncation bias
     // (the fp16 engine's eigenvalue error grows ~3e-6 per 1024 frames of slab, measured: it stays at 1024)
@@ -1330,7 +1396,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     P.passes = f16 ? 3 : bf16 ? passes - 10 : passes;
     P.collector = env_int("MSMB200_UMMA_COLLECTOR", 1);
     P.flush_red = env_int("MSMB200_UMMA_FLUSH_RED", 2);
-    P.partials32 = reinterpret_cast<float *>(wsb + w_part32);
+    P.partials32 = reinterpret_cast<float *>(wsb + w_part + sizeof(double) * 2 * DD * n_pairs);
     P.fold_every = env_int("MSMB200_UMMA_FOLD_EVERY", 16);
     if (P.fold_every < 1) P.fold_every = 1;
     P.dbg_mode = env_int("MSMB200_UMMA_DBGMODE", 0);
@@ -1354,22 +1420,66 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         MSMB_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16, st));
         P.dbg = d_dbg;
     }
+    V2Params V;
+    V.mapsA = P.mapsA;
+    V.mapsB = P.mapsB;
+    V.tile_prefix = P.tile_prefix;
+    V.seq_pairs = P.seq_pairs;
+    V.n_seq = n_seq;
+    V.n_tiles = (int)tiles;
+    V.n_groups = n_groups;
+    V.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", UM_SLAB_TILES_DEFAULT);
+    if (V.slab_tiles < 1) V.slab_tiles = 1;
+    V.D = D;
+    V.dbg_mode = P.dbg_mode;
+    V.shift = d_shift;
+    V.scale = d_scale;
+    V.overflow = d_flag;
+    V.lvl1 = reinterpret_cast<float *>(wsb + w_part);
+    V.hi = V.lvl1 + v2_per_cta * (size_t)(n_groups * v2_cg);
+    V.lo = V.hi + v2_per_cta * (size_t)(n_groups * v2_cg);
+    V.sums = P.sums;
+    V.dbg = d_dbg;
 
+    const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + 1024 /* control block */
+                        + (size_t)UM_CONV_WARPS * 2048 /* drain staging */ + 1024 /* alignment */;
+    const size_t smem_v2 = (size_t)V2_RAW_STAGES * UM_RAW_BYTES + (size_t)V2_OP_STAGES * V2_STAGE_BYTES
+                           + 1536 /* control block */ + 1024 /* alignment */;
+    static_assert(sizeof(UmmaSmem) <= 1024, "control block");
+    static_assert(sizeof(V2Smem) <= 1536, "control block");
+    if (!g_attr_set[dev]) {
+        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_TF32>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_BF16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_F16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_v2_kernel<1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
+        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_v2_kernel<2>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
+        g_attr_set[dev] = true;
+    }
     if (tiles > 0) {
-        const size_t smem = (size_t)UM_STAGES * (UM_RAW_BYTES + UM_STAGE_BYTES) + 1024 /* control block */
-                            + (size_t)UM_CONV_WARPS * 2048 /* drain staging */ + 1024 /* alignment */;
-        static_assert(sizeof(UmmaSmem) <= 1024, "control block");
-        if (!g_attr_set[dev]) {
-            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_TF32>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_BF16>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_F16>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            g_attr_set[dev] = true;
-        }
         if (f16) {
-            tica_umma_kernel<UM_KIND_F16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+            if (v2) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(n_groups * v2_cg));
+                cfg.blockDim = dim3(V2_THREADS);
+                cfg.dynamicSmemBytes = smem_v2;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = (unsigned)v2_cg;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (v2_cg == 2) MSMB_CUDA(cudaLaunchKernelEx(&cfg, tica_umma_v2_kernel<2>, V));
+                else MSMB_CUDA(cudaLaunchKernelEx(&cfg, tica_umma_v2_kernel<1>, V));
+            } else {
+                tica_umma_kernel<UM_KIND_F16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
+            }
             MSMB_LAUNCH_CHECK();
             // Range rescue, all on the stream (no host round trip): if a scaled value left fp16's
             // range the two launches below wipe the partials and redo the call with the 6xBF16
@@ -1378,7 +1488,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                 d_flag, reinterpret_cast<double *>(wsb + w_sums), (w_E - w_sums) / sizeof(double));
             MSMB_LAUNCH_CHECK();
             tica_umma_rescue_clear_kernel<<<4 * sm_count(), 256, 0, st>>>(
-                d_flag, P.partials, 2 * DD * (size_t)n_pairs);
+                d_flag, P.partials, (v2 ? (v1_part_bytes > v2_part_bytes ? v2_part_bytes : v1_part_bytes)
+                                        : v1_part_bytes) / sizeof(double));
             MSMB_LAUNCH_CHECK();
             UmmaParams Q = P;
             Q.passes = 6;
@@ -1397,21 +1508,53 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
             reinterpret_cast<double *>(wsb + w_E), reinterpret_cast<double *>(wsb + w_es));
         MSMB_LAUNCH_CHECK();
     }
-    tica_umma_finalize_kernel<<<(unsigned)(((size_t)D * D + 255) / 256), 256, 0, st>>>(
+    const unsigned fin_blocks = (unsigned)(((size_t)D * D + 255) / 256);
+    if (v2) {
+        double *d_R = reinterpret_cast<double *>(wsb + w_R);
+        const unsigned red_blocks = (unsigned)((v2_cg * v2_per_cta + 255) / 256);
+        if (v2_cg == 2) {
+            tica_umma_v2_reduce_kernel<2><<<red_blocks, 256, 0, st>>>(V.lvl1, V.hi, V.lo, n_groups, d_flag, d_R);
+            MSMB_LAUNCH_CHECK();
+            tica_umma_v2_finalize_kernel<2><<<fin_blocks, 256, 0, st>>>(
+                d_R, V.sums, n_groups, reinterpret_cast<const double *>(wsb + w_E),
+                reinterpret_cast<const double *>(wsb + w_es), d_shift, d_scale, d_flag,
+                n_pairs_total, n_obs, (double)n_seq, D, acc);
+        } else {
+            tica_umma_v2_reduce_kernel<1><<<red_blocks, 256, 0, st>>>(V.lvl1, V.hi, V.lo, n_groups, d_flag, d_R);
+            MSMB_LAUNCH_CHECK();
+            tica_umma_v2_finalize_kernel<1><<<fin_blocks, 256, 0, st>>>(
+                d_R, V.sums, n_groups, reinterpret_cast<const double *>(wsb + w_E),
+                reinterpret_cast<const double *>(wsb + w_es), d_shift, d_scale, d_flag,
+                n_pairs_total, n_obs, (double)n_seq, D, acc);
+        }
+        MSMB_LAUNCH_CHECK();
+    }
+    // v1 engines, and the rescued call of v2 (the bf16 kernel wrote v1's float64 partials)
+    tica_umma_finalize_kernel<<<fin_blocks, 256, 0, st>>>(
         P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(wsb + w_E),
         reinterpret_cast<const double *>(wsb + w_es), d_shift, f16 ? d_scale : nullptr, d_flag,
-        n_pairs_total, n_obs, (double)n_seq, D, acc);
+        v2 ? 1 : 0, n_pairs_total, n_obs, (double)n_seq, D, acc);
     MSMB_LAUNCH_CHECK();
     if (d_dbg) {
         long long h[16];
         MSMB_CUDA(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
         MSMB_CUDA(cudaStreamSynchronize(st));
-        fprintf(stderr, "[umma dbg pair0] tiles=%lld mma_loop=%lld cyc (%.0f/tile) wait_conv=%.1f%% wait_flush=%.1f%% | "
-                "conv thread: wait_raw=%.0f wait_empty=%.0f compute=%.0f fence+sync+arrive=%.0f cyc/tile | "
-                "flush=%.0f cyc/slab (%lld slabs)\n", h[3], h[0], (double)h[0] / (h[3] ? h[3] : 1),
-                100.0 * h[1] / (h[0] ? h[0] : 1), 100.0 * h[2] / (h[0] ? h[0] : 1),
-                (double)h[4] / (h[3] ? h[3] : 1), (double)h[5] / (h[3] ? h[3] : 1), (double)h[6] / (h[3] ? h[3] : 1),
-                (double)h[7] / (h[3] ? h[3] : 1), (double)h[8] / (h[9] ? h[9] : 1), h[9]);
+        const double nt = (double)(h[3] ? h[3] : 1);
+        if (v2)
+            fprintf(stderr, "[umma v2 dbg group0 cg=%d] tiles=%lld mma_loop=%lld cyc (%.0f/tile) idle=%.1f%% deferred_polls=%lld "
+                    "fast_tiles=%lld | conv thread: wait_raw=%.0f wait_empty=%.0f compute=%.0f fence+sync+arrive=%.0f cyc/tile | "
+                    "drain warp: %lld events, wait=%.0f ld=%.0f red=%.0f fold=%.0f cyc/event\n", v2_cg, h[3], h[0],
+                    (double)h[0] / nt, 100.0 * h[1] / (h[0] ? h[0] : 1), h[2], h[13],
+                    (double)h[4] / nt, (double)h[5] / nt, (double)h[6] / nt, (double)h[7] / nt, h[12],
+                    (double)h[8] / (h[12] ? h[12] : 1), (double)h[9] / (h[12] ? h[12] : 1),
+                    (double)h[10] / (h[12] ? h[12] : 1), (double)h[11] / (h[12] ? h[12] : 1));
+        else
+            fprintf(stderr, "[umma dbg pair0] tiles=%lld mma_loop=%lld cyc (%.0f/tile) wait_conv=%.1f%% wait_flush=%.1f%% | "
+                    "conv thread: wait_raw=%.0f wait_empty=%.0f compute=%.0f fence+sync+arrive=%.0f cyc/tile | "
+                    "flush=%.0f cyc/slab (%lld slabs)\n", h[3], h[0], (double)h[0] / nt,
+                    100.0 * h[1] / (h[0] ? h[0] : 1), 100.0 * h[2] / (h[0] ? h[0] : 1),
+                    (double)h[4] / nt, (double)h[5] / nt, (double)h[6] / nt,
+                    (double)h[7] / nt, (double)h[8] / (h[9] ? h[9] : 1), h[9]);
         MSMB_CUDA(cudaFreeAsync(d_dbg, st));
     }
     MSMB_CUDA(cudaFreeAsync(scratch, st));

@@ -2,23 +2,29 @@
 //
 // Same mathematics as tica_umma_kernel<UM_KIND_F16> (centred, power-of-two scaled frame x' = h + l in
 // fp16; raw moments rebuilt in float64 by the finalize kernel), reorganised around what the round-1
-// profile showed (tensor pipe 75 % active, 25 % lost to the TMEM drain):
+// profile showed (tensor pipe 75 % active, 25 % lost to the TMEM drain, the
+// converters as slow as the MMAs, narrow inputs paying 256-wide tiles):
 //
 //  * 5 products instead of 6.  C_00 = sum x x^T is symmetric, so only G = h (h/2)^T + h l^T is
 //    accumulated and C_00 = G + G^T (= h h^T + h l^T + l h^T) is formed by the finalize kernel.
 //    C_tau keeps its three products h b^T + h bl^T + l b^T.  Operand tiles per stage:
 //    a = h, al = l, ah = h / 2 (exact), b, bl  (8 KB each, K-major, no swizzle).
-//  * The drain is hidden.  TMEM holds FOUR accumulator regions (C_tau | C_00) x (column half 0 | 1);
+//  * The drain is hidden.  TMEM holds FOUR accumulator regions (C_tau | G) x (column half 0 | 1);
 //    every UMMA is M x (N = RW) into one region.  The regions' slab boundaries are staggered by a
-//    quarter slab, so at any time at most one region is being drained; its MMAs are deferred (the
+//    quarter slab, so at most one region is being drained at a time; its MMAs are deferred (the
 //    operand ring is 4 deep) while the tensor pipe keeps working on the other three, and the region
 //    catches up as soon as its accumulators have been read out.
-//  * Dedicated drain warps (4: one per TMEM lane quarter) so the converters never stop:
+//  * Dedicated drain warps (4: one per TMEM lane quarter), so the converters never stop:
 //    tcgen05.ld -> fire-and-forget red.global.add.f32 into this CTA's float32 level (L2 resident);
-//    the region is released as soon as its last column chunk is in registers.  Every `fold_every`
-//    slabs the float32 level moves into a float-float (hi, lo) pair with an error-free TwoSum.
-//    No FP64 instruction runs in this kernel at all (FP64 issued under a busy tensor pipe stalls for
-//    hundreds of cycles, profiles/r1_k1_issue.txt); the pairs become doubles in the finalize kernel.
+//    the region is released as soon as its last column chunk is in registers.  After every drain the
+//    warp moves ONE 16-column group of the region from the float32 level into a float-float (hi, lo)
+//    pair with an error-free TwoSum (round robin: a group is folded every RW/16 slabs), so the float32
+//    level never sums more than RW/16 slabs and no drain event takes long.  The finalize path adds
+//    hi + lo + level in float64.  No FP64 instruction runs in this kernel while the tensor pipe is
+//    busy (FP64 issued under a busy tensor pipe stalls for hundreds of cycles, profiles/r1_k1_issue.txt).
+//  * Converters: a thread owns one feature and the 8 frames of one K chunk of one operand; packed
+//    f32x2 math (FFMA2 / FADD2 of sm_100), h = cvt.rn.f16x2, l = fp16(x' - h): ~40 instructions per
+//    8 values instead of ~70.  Only the feature blocks that exist are converted (D < 128 per CTA).
 //  * template <CG>: CG = 2 is the CTA-pair kernel (cta_group::2, M = 256, D in (128, 256]);
 //    CG = 1 is the single-CTA kernel for D <= 128 (cta_group::1, M = 128, regions of 64 columns,
 //    148 independent CTAs): narrow inputs no longer pay 256-wide tiles (config 2, 10M x 64).
@@ -34,10 +40,13 @@ constexpr int V2_RAW_STAGES = 2;
 constexpr int V2_OP_STAGES = 4;
 constexpr int V2_CONV_WARPS = 16;
 constexpr int V2_DRAIN_WARPS = 4;
-constexpr int V2_FIRST_DRAIN_WARP = 4 + V2_CONV_WARPS;              // 20: 20 % 4 == 0 -> lane quarter 0
-constexpr int V2_THREADS = 32 * (4 + V2_CONV_WARPS + V2_DRAIN_WARPS);   // 768
-constexpr int V2_REGIONS = 4;                       // (C_tau, C_00) x (column half 0, 1)
+constexpr int V2_FIRST_CONV_WARP = 2;               // w0 TMA producer (+ TMEM allocation), w1 MMA issuer
+constexpr int V2_FIRST_DRAIN_WARP = V2_FIRST_CONV_WARP + V2_CONV_WARPS;   // 18..21: four distinct lane quarters
+constexpr int V2_THREADS = 32 * (V2_FIRST_DRAIN_WARP + V2_DRAIN_WARPS);   // 704 (93 -> 88 registers per thread)
+constexpr int V2_CONV_TID0 = 32 * V2_FIRST_CONV_WARP;
+constexpr int V2_REGIONS = 4;                       // (C_tau, G) x (column half 0, 1)
 constexpr int V2_T_A = 0, V2_T_AL = 1, V2_T_AH = 2, V2_T_B = 3, V2_T_BL = 4;
+constexpr int V2_MAX_GROUPS = 192;                  // CTA pairs (CG = 2) or CTAs (CG = 1)
 
 struct V2Params {
     const CUtensorMap *mapsA;     // [n_seq] unlagged
@@ -48,9 +57,7 @@ struct V2Params {
     int n_tiles;
     int n_groups;                 // CTA pairs (CG = 2) or CTAs (CG = 1)
     int slab_tiles;               // 32-frame tiles per TMEM slab
-    int fold_every;               // slabs of a region between folds of the float32 level
-    int n_halves;                 // 2; 1 when D <= 64 (CG = 1): the upper column half does not exist
-    uint32_t h_add, h_mask;       // integer rounding of the h component
+    int D;                        // real feature count (32k)
     int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
@@ -70,6 +77,8 @@ struct V2Smem {
     uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 4 * CG arrivals
     uint32_t tmem_base;
     int valid_rows[V2_RAW_STAGES];
+    float sc[UM_F];                    // this CTA's per-feature scale and -shift * scale
+    float nsh[UM_F];
 };
 
 __device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, uint32_t parity)
@@ -86,7 +95,7 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// One UMMA (kind::f16, fp16 x fp16 -> fp32).  `mode` picks the collector hint for the A operand:
+// One UMMA (kind::f16, fp16 x fp16 -> fp32).  MODE picks the collector hint for the A operand:
 // 0 none, 1 fill, 2 use, 3 lastuse -- the caller strings together the MMAs that share A.
 #define V2_MMA_ASM(CGS, VEC, QUAL) asm volatile( \
     "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t" \
@@ -94,24 +103,20 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t *bar)
     :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(leader) : "memory")
 #define V2_VEC8 "{%5, %5, %5, %5, %5, %5, %5, %5}"
 #define V2_VEC4 "{%5, %5, %5, %5}"
-template <int CG>
-__device__ __forceinline__ void v2_mma(int mode, uint32_t tmem_d, uint64_t da, uint64_t db,
+template <int CG, int MODE>
+__device__ __forceinline__ void v2_mma(uint32_t tmem_d, uint64_t da, uint64_t db,
                                        uint32_t idesc, uint32_t acc, uint32_t leader)
 {
     if constexpr (CG == 2) {
-        switch (mode) {
-        case 1: V2_MMA_ASM("2", V2_VEC8, ".collector::a::fill"); break;
-        case 2: V2_MMA_ASM("2", V2_VEC8, ".collector::a::use"); break;
-        case 3: V2_MMA_ASM("2", V2_VEC8, ".collector::a::lastuse"); break;
-        default: V2_MMA_ASM("2", V2_VEC8, ""); break;
-        }
+        if constexpr (MODE == 1) V2_MMA_ASM("2", V2_VEC8, ".collector::a::fill");
+        else if constexpr (MODE == 2) V2_MMA_ASM("2", V2_VEC8, ".collector::a::use");
+        else if constexpr (MODE == 3) V2_MMA_ASM("2", V2_VEC8, ".collector::a::lastuse");
+        else V2_MMA_ASM("2", V2_VEC8, "");
     } else {
-        switch (mode) {
-        case 1: V2_MMA_ASM("1", V2_VEC4, ".collector::a::fill"); break;
-        case 2: V2_MMA_ASM("1", V2_VEC4, ".collector::a::use"); break;
-        case 3: V2_MMA_ASM("1", V2_VEC4, ".collector::a::lastuse"); break;
-        default: V2_MMA_ASM("1", V2_VEC4, ""); break;
-        }
+        if constexpr (MODE == 1) V2_MMA_ASM("1", V2_VEC4, ".collector::a::fill");
+        else if constexpr (MODE == 2) V2_MMA_ASM("1", V2_VEC4, ".collector::a::use");
+        else if constexpr (MODE == 3) V2_MMA_ASM("1", V2_VEC4, ".collector::a::lastuse");
+        else V2_MMA_ASM("1", V2_VEC4, "");
     }
 }
 // arrive on `bar` (in every CTA of the group) when all MMAs issued so far have completed
@@ -141,13 +146,52 @@ __device__ __forceinline__ uint32_t v2_idesc()
     return d;
 }
 
+// packed float32 pairs (sm_100: FFMA2 / FADD2, two elements per issue slot)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// fp16 pair -> the two floats it holds (exact)
+__device__ __forceinline__ uint64_t h2_to_f2(uint32_t h)
+{
+    float a, b;
+    asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+        : "=f"(a), "=f"(b) : "r"(h));
+    return f2_pack(a, b);
+}
+
 // ---------------------------------------------------------------------------------------
 template <int CG>
-__global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Params P)
+__global__ void __maxnreg__(88) tica_umma_v2_kernel(const V2Params P)
 {
     constexpr int RW = 64 * CG;                      // columns of a region = N of every UMMA
     constexpr int TMEM_COLS = V2_REGIONS * RW;       // 512 (CG = 2) or 256 (CG = 1)
     constexpr int S = V2_OP_STAGES;
+    constexpr int NG = RW / 16;                      // 16-column fold groups of a region
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *ring = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -166,13 +210,20 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     const long long t_end = (long long)P.n_tiles * (group + 1) / P.n_groups;
     const int my_tiles = (int)(t_end - t_begin);
     const int ST = P.slab_tiles;
+    // features of this CTA that exist, in blocks of 32 (TMA zero-fills the rest of the raw tile; the
+    // operand rows of the missing blocks are zeroed once, below, and never written again)
+    int d_local = P.D - UM_F * (int)cta_rank;
+    d_local = d_local < 0 ? 0 : (d_local > UM_F ? UM_F : d_local);
+    const int nfb = d_local / 32;
+    // column halves in use: the upper half only exists when some CTA has more than 64 features
+    const int n_halves = (CG == 2 || P.D > 64) ? 2 : 1;
     // slab boundaries: staggered across groups (so the drains of the whole chip do not coincide)
     // and by a quarter slab across the four regions of a group
     const int slab_off = (int)(((long long)group * ST) / P.n_groups);
     auto region_off = [&](int q) { return (slab_off + (q * ST) / V2_REGIONS) % ST; };
     auto slab_first = [&](int q, int t) { return t == 0 || ((t + region_off(q)) % ST) == 0; };
     auto slab_last = [&](int q, int t) { return ((t + region_off(q) + 1) % ST) == 0 || t + 1 == my_tiles; };
-    auto region_active = [&](int q) { return (q & 1) < P.n_halves; };
+    auto region_active = [&](int q) { return (q & 1) < n_halves; };
 
     if (tid == 0) {
         for (int s = 0; s < V2_RAW_STAGES; ++s) {
@@ -189,7 +240,20 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (tid < UM_F) {
+        const float sc = P.scale[UM_F * cta_rank + tid];
+        ctl->sc[tid] = sc;
+        ctl->nsh[tid] = -P.shift[UM_F * cta_rank + tid] * sc;      // exact (power-of-two scale)
+    }
+    if (nfb < 4) {
+        // operand rows of feature blocks that do not exist: zero (an uninitialised row could hold a
+        // NaN pattern and trip the range check through its accumulators)
+        uint4 *p = reinterpret_cast<uint4 *>(op_ring);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < S * V2_STAGE_BYTES / 16; i += V2_THREADS) p[i] = z;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
         if constexpr (CG == 2) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
                          :: "r"(smem_u32(&ctl->tmem_base)), "r"(TMEM_COLS));
@@ -244,14 +308,26 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const uint32_t ring_addr = smem_u32(op_ring);
             const bool dbg_on = P.dbg != nullptr && group == 0;
             const long long d_start = clock64();
-            long long d_idle = 0, d_deferred = 0;
+            long long d_idle = 0;
+            int d_deferred = 0, d_fast = 0;
             int nt[V2_REGIONS];                      // next tile of each region
-            uint32_t acc_ph[V2_REGIONS];
+            int nf[V2_REGIONS];                      // tile at which the region's next slab starts
+            uint32_t acc_ph = 0;                     // phase bit of acc_empty[q] in bit q
 #pragma unroll
             for (int q = 0; q < V2_REGIONS; ++q) {
                 nt[q] = region_active(q) ? 0 : my_tiles;
-                acc_ph[q] = 0;
+                nf[q] = ST - region_off(q);
             }
+            const uint32_t full_mask = n_halves == 2 ? 15u : 5u;
+            // descriptor of (tile, byte offset) in the stage whose low word is `base_lo`: only the
+            // 14-bit start-address field changes (shared addresses stay below 2^18: no carry)
+            auto desc = [](uint32_t base_lo, uint32_t byte_off) -> uint64_t {
+                uint64_t d;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(d)
+                    : "r"(base_lo + (byte_off >> 4)), "r"((uint32_t)((UM_SBO >> 4) | (1u << 14))));
+                return d;
+            };
+            constexpr uint32_t HB = 64 * 16;         // byte offset of the upper column half in a B tile
             int conv_done = 0;                       // tiles whose conversion has been observed
             int released = 0;                        // tiles whose operand stage has been handed back
             while (released < my_tiles) {
@@ -261,62 +337,72 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 bool progressed = false;
                 // every tile index some region is waiting at: batch the regions that can go
                 for (int tt = released; tt < conv_done; ++tt) {
-                    uint32_t mask = 0;
+                    uint32_t mask = 0, firsts = 0;
 #pragma unroll
                     for (int q = 0; q < V2_REGIONS; ++q) {
                         if (nt[q] != tt) continue;
-                        if (tt > 0 && slab_first(q, tt)) {
-                            // the region's previous slab must have left TMEM
-                            if (!mbar_test(&ctl->acc_empty[q], acc_ph[q])) {
-                                if (dbg_on) ++d_deferred;
+                        if (tt == nf[q]) {
+                            // a new slab: the region's previous slab must have left TMEM
+                            if (!mbar_test(&ctl->acc_empty[q], (acc_ph >> q) & 1u)) {
+                                ++d_deferred;
                                 continue;
                             }
-                            acc_ph[q] ^= 1;
+                            acc_ph ^= 1u << q;
+                            nf[q] += ST;
+                            firsts |= 1u << q;
                         }
                         mask |= 1u << q;
                     }
                     if (!mask) continue;
+                    if (tt == 0) firsts = mask;
                     progressed = true;
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t st = ring_addr + (uint32_t)(tt % S) * V2_STAGE_BYTES;
-                    const int n_tau = __popc(mask & 3u), n_00 = __popc(mask & 12u);
-                    const bool one_mma = (P.dbg_mode & 4) != 0;
+                    const uint32_t base_lo = ((st >> 4) & 0x3FFFu) | ((uint32_t)((UM_LBO >> 4) & 0x3FFF) << 16);
+                    if (mask == 15u) {
+                        // all four regions: 10 UMMAs per K step, A = h kept in the collector for 8 of them
+                        ++d_fast;
 #pragma unroll
-                    for (int ks = 0; ks < UM_KT / 16; ++ks) {
-                        const uint32_t off = ks * 2 * UM_LBO;
-                        const uint64_t dA = umma_desc(st + V2_T_A * V2_TILE + off);
-                        const uint64_t dAl = umma_desc(st + V2_T_AL * V2_TILE + off);
-                        // --- the MMAs whose A operand is a (= h of the unlagged frames)
-                        int left = 2 * n_tau + 2 * n_00;        // MMAs sharing A = a
-                        int idx = 0;
-#pragma unroll
-                        for (int q = 0; q < V2_REGIONS; ++q) {
-                            if (!(mask & (1u << q))) continue;
-                            const uint32_t hb = (uint32_t)(q & 1) * (64 * 16);   // column half: 64 features on
-                            const uint32_t d = tmem + (uint32_t)(RW * q);
-                            const uint32_t first = (ks == 0 && slab_first(q, tt)) ? 0u : 1u;
-                            const uint32_t t0 = q < 2 ? V2_T_B : V2_T_AH, t1 = q < 2 ? V2_T_BL : V2_T_AL;
-                            const uint64_t dB0 = umma_desc(st + t0 * V2_TILE + off + hb);
-                            const uint64_t dB1 = umma_desc(st + t1 * V2_TILE + off + hb);
-                            int m0 = left == 1 ? 0 : idx == 0 ? 1 : idx == left - 1 ? 3 : 2;
-                            v2_mma<CG>(m0, d, dA, dB0, idesc, first, leader);
-                            ++idx;
-                            if (one_mma) continue;
-                            int m1 = idx == left - 1 ? 3 : 2;
-                            v2_mma<CG>(m1, d, dA, dB1, idesc, 1u, leader);
-                            ++idx;
+                        for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                            const uint32_t off = ks * 2 * UM_LBO;
+                            const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
+                            const uint64_t dAl = desc(base_lo, V2_T_AL * V2_TILE + off);
+                            const uint32_t f0 = (ks == 0 && (firsts & 1u)) ? 0u : 1u;
+                            const uint32_t f1 = (ks == 0 && (firsts & 2u)) ? 0u : 1u;
+                            const uint32_t f2 = (ks == 0 && (firsts & 4u)) ? 0u : 1u;
+                            const uint32_t f3 = (ks == 0 && (firsts & 8u)) ? 0u : 1u;
+                            v2_mma<CG, 1>(tmem + 0 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off), idesc, f0, leader);
+                            v2_mma<CG, 2>(tmem + 0 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u, leader);
+                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, f1, leader);
+                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off + HB), idesc, 1u, leader);
+                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, f2, leader);
+                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u, leader);
+                            v2_mma<CG, 2>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off + HB), idesc, f3, leader);
+                            v2_mma<CG, 3>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off + HB), idesc, 1u, leader);
+                            v2_mma<CG, 1>(tmem + 0 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off), idesc, 1u, leader);
+                            v2_mma<CG, 3>(tmem + 1 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, 1u, leader);
                         }
-                        // --- the MMAs whose A operand is al (C_tau only)
-                        if (!one_mma) {
-                            int k = 0;
+                    } else {
+                        // some regions only (one is being drained, or is catching up): no collector hints
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
+                        for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                            const uint32_t off = ks * 2 * UM_LBO;
+                            const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
+#pragma unroll
+                            for (int q = 0; q < V2_REGIONS; ++q) {
                                 if (!(mask & (1u << q))) continue;
-                                const uint32_t hb = (uint32_t)(q & 1) * (64 * 16);
-                                const uint64_t dB = umma_desc(st + V2_T_B * V2_TILE + off + hb);
-                                int m = n_tau == 1 ? 0 : k == 0 ? 1 : 3;
-                                v2_mma<CG>(m, tmem + (uint32_t)(RW * q), dAl, dB, idesc, 1u, leader);
-                                ++k;
+                                const uint32_t hb = (uint32_t)(q & 1) * HB;
+                                const uint32_t d = tmem + (uint32_t)(RW * q);
+                                const uint32_t first = (ks == 0 && (firsts & (1u << q))) ? 0u : 1u;
+                                if (q < 2) {
+                                    const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off + hb);
+                                    v2_mma<CG, 0>(d, dA, dB, idesc, first, leader);
+                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_BL * V2_TILE + off + hb), idesc, 1u, leader);
+                                    v2_mma<CG, 0>(d, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u, leader);
+                                } else {
+                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AH * V2_TILE + off + hb), idesc, first, leader);
+                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AL * V2_TILE + off + hb), idesc, 1u, leader);
+                                }
                             }
                         }
                     }
@@ -324,8 +410,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     for (int q = 0; q < V2_REGIONS; ++q) {
                         if (!(mask & (1u << q))) continue;
                         nt[q] = tt + 1;
-                        if (slab_last(q, tt)) v2_commit<CG>(&ctl->acc_full[q], leader);
+                        if (tt + 1 == nf[q] || tt + 1 == my_tiles) v2_commit<CG>(&ctl->acc_full[q], leader);
                     }
+                    if (mask != full_mask) break;    // re-evaluate from `released`: a deferred region comes first
                 }
                 int low = my_tiles;
 #pragma unroll
@@ -342,25 +429,39 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 P.dbg[1] = d_idle;
                 P.dbg[2] = d_deferred;
                 P.dbg[3] = my_tiles;
+                P.dbg[13] = d_fast;
             }
         }
-    } else if (warp >= 4 && warp < 4 + V2_CONV_WARPS) {
+    } else if (warp >= V2_FIRST_CONV_WARP && warp < V2_FIRST_DRAIN_WARP) {
         // ================================ converters (512 threads, every CTA) ==========
-        // warp cw: feature block cw & 3 (32 features, lane = feature), frame octet cw >> 2.  A thread
-        // gathers 8 frames of its feature with conflict-free 4-byte shared loads from the swizzled
-        // raw tile (this is the transpose), centres / scales / splits, stores 16-byte K-major chunks.
-        const int cw = warp - 4;
-        const int fb = cw & 3, kq = cw >> 2;
-        const int f_local = 32 * fb + lane;
+        // Work unit = (operand, K chunk of 8 frames, block of 32 features): 8 * nfb units per tile,
+        // dealt to the 16 warps (unit cw and, when there are more than 16, unit cw + 16).  lane =
+        // feature inside the block.  A thread gathers the 8 frames of its feature with conflict-free
+        // 4-byte shared loads from the swizzled raw tile (one 128-byte row segment per warp load:
+        // this is the transpose), centres / scales / splits them and stores 16-byte K-major chunks
+        // (512 contiguous bytes per warp store).
+        const int cw = warp - V2_FIRST_CONV_WARP;
+        const int n_units = 8 * nfb;
+        int u_op[2], u_kq[2], u_fl[2];
+        float u_sc[2], u_nsh[2];
+        bool u_on[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int u = cw + 16 * k;
+            u_on[k] = u < n_units;
+            const int uu = u_on[k] ? u : 0;
+            const int nf = nfb > 0 ? nfb : 1;
+            u_op[k] = uu / (4 * nf);
+            u_kq[k] = (uu / nf) & 3;
+            u_fl[k] = 32 * (uu % nf) + lane;
+            u_sc[k] = ctl->sc[u_fl[k]];
+            u_nsh[k] = ctl->nsh[u_fl[k]];
+        }
         const int chunk = lane >> 2, within = (lane & 3) * 4;
-        const float sh = P.shift[UM_F * cta_rank + f_local];
-        const float sc = P.scale[UM_F * cta_rank + f_local];
-        const float nsh = -sh * sc;
-        const uint32_t h_add = P.h_add, h_mask = P.h_mask;
-        float sAh = 0.f, sAl = 0.f;                  // column sum of the unlagged rows as a float pair
+        float sAh[2] = {0.f, 0.f}, sAl[2] = {0.f, 0.f};   // column sums (operand 0 units) as float pairs
         int stage = 0, ostage = 0;
         uint32_t phase = 0, ophase = 0;
-        const bool dbg_on = P.dbg != nullptr && group == 0 && tid == 128 && cta_rank == 0;
+        const bool dbg_on = P.dbg != nullptr && group == 0 && tid == V2_CONV_TID0 && cta_rank == 0;
         long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0;
         for (int t = 0; t < my_tiles; ++t) {
             long long q0 = dbg_on ? clock64() : 0;
@@ -371,57 +472,78 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const int valid = ctl->valid_rows[stage];
             const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
             unsigned char *st = op_ring + ostage * V2_STAGE_BYTES;
-            float tsA = 0.f;
             auto convert_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
+                float v[2][8];
 #pragma unroll
-                for (int op = 0; op < 2; ++op) {
-                    const unsigned char *raw = rawst + op * UM_TILE_BYTES + fb * (UM_KT * 128) + within;
-                    unsigned char *h_buf = st + (op == 0 ? V2_T_A : V2_T_B) * V2_TILE + f_local * 16;
-                    unsigned char *l_buf = st + (op == 0 ? V2_T_AL : V2_T_BL) * V2_TILE + f_local * 16;
-                    float h[8], l[8];
-                    float s8 = 0.f;
+                for (int k = 0; k < 2; ++k) {
+                    if (!u_on[k]) continue;
+                    const unsigned char *raw = rawst + u_op[k] * UM_TILE_BYTES
+                                               + (u_fl[k] >> 5) * (UM_KT * 128) + within;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = 8 * kq + i;
-                        const float v = *reinterpret_cast<const float *>(
-                            raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                        const float as = (FULL || r < valid) ? fmaf(v, sc, nsh) : 0.f;
-                        s8 += as;
-                        h[i] = __uint_as_float((__float_as_uint(as) + h_add) & h_mask);
-                        l[i] = as - h[i];
+                        const int r = 8 * u_kq[k] + i;
+                        v[k][i] = *reinterpret_cast<const float *>(raw + r * 128 + ((chunk ^ (r & 7)) << 4));
                     }
-                    uint4 hw, lw;
-                    hw.x = pack_f16(h[0], h[1]); hw.y = pack_f16(h[2], h[3]);
-                    hw.z = pack_f16(h[4], h[5]); hw.w = pack_f16(h[6], h[7]);
-                    lw.x = pack_f16(l[0], l[1]); lw.y = pack_f16(l[2], l[3]);
-                    lw.z = pack_f16(l[4], l[5]); lw.w = pack_f16(l[6], l[7]);
-                    *reinterpret_cast<uint4 *>(h_buf + kq * UM_LBO) = hw;
-                    *reinterpret_cast<uint4 *>(l_buf + kq * UM_LBO) = lw;
-                    if (op == 0) {
-                        tsA += s8;
-                        // h / 2 (one exact fp16 multiply per pair): the second factor of the C_00 product
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!u_on[k]) continue;
+                    const uint64_t sc2 = f2_pack(u_sc[k], u_sc[k]);
+                    const uint64_t nsh2 = f2_pack(u_nsh[k], u_nsh[k]);
+                    uint32_t hw[4], lw[4];
+                    uint64_t sum2 = 0ull;                           // (+0.f, +0.f)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // (v - shift) * scale in one rounding: the scale is a power of two, so this is
+                        // exactly scale * fl32(v - shift), the x' of the float64 edge kernel
+                        uint64_t as2 = f2_fma(f2_pack(v[k][2 * i], v[k][2 * i + 1]), sc2, nsh2);
+                        if (!FULL) {
+                            float a0, a1;
+                            f2_unpack(as2, a0, a1);
+                            const int r = 8 * u_kq[k] + 2 * i;
+                            as2 = f2_pack(r < valid ? a0 : 0.f, r + 1 < valid ? a1 : 0.f);
+                        }
+                        sum2 = f2_add(sum2, as2);
+                        float a0, a1;
+                        f2_unpack(as2, a0, a1);
+                        hw[i] = pack_f16(a0, a1);                   // h: round to nearest fp16 (Inf beyond 65504)
+                        const uint64_t l2 = f2_sub(as2, h2_to_f2(hw[i]));   // exact in fp32
+                        float l0, l1;
+                        f2_unpack(l2, l0, l1);
+                        lw[i] = pack_f16(l0, l1);
+                    }
+                    unsigned char *dst = st + u_fl[k] * 16 + u_kq[k] * UM_LBO;
+                    if (u_op[k] == 0) {
+                        *reinterpret_cast<uint4 *>(dst + V2_T_A * V2_TILE) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4 *>(dst + V2_T_AL * V2_TILE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        // h / 2 (one exact fp16 multiply per pair): the second factor of the G product
                         uint4 hh;
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.x) : "r"(hw.x), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.y) : "r"(hw.y), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.z) : "r"(hw.z), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.w) : "r"(hw.w), "r"(0x38003800u));
-                        *reinterpret_cast<uint4 *>(st + V2_T_AH * V2_TILE + f_local * 16 + kq * UM_LBO) = hh;
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.x) : "r"(hw[0]), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.y) : "r"(hw[1]), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.z) : "r"(hw[2]), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.w) : "r"(hw[3]), "r"(0x38003800u));
+                        *reinterpret_cast<uint4 *>(dst + V2_T_AH * V2_TILE) = hh;
+                        // column sum: TwoSum of the tile's 8-frame sum into the float pair
+                        float s0, s1;
+                        f2_unpack(sum2, s0, s1);
+                        const float ts = s0 + s1;
+                        const float tt = sAh[k] + ts, bp = tt - sAh[k];
+                        sAl[k] += (sAh[k] - (tt - bp)) + (ts - bp);
+                        sAh[k] = tt;
+                    } else {
+                        *reinterpret_cast<uint4 *>(dst + V2_T_B * V2_TILE) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4 *>(dst + V2_T_BL * V2_TILE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                 }
             };
             if (P.dbg_mode & 1) { /* timing experiment: no conversion traffic */ }
             else if (valid == UM_KT) convert_tile(std::true_type());
             else convert_tile(std::false_type());
-            {   // TwoSum: (sAh, sAl) += tsA without losing the rounding error
-                const float tt = sAh + tsA, bp = tt - sAh;
-                sAl += (sAh - (tt - bp)) + (tsA - bp);
-                sAh = tt;
-            }
             long long q3 = dbg_on ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
-            if (tid == 128) {
+            if (tid == V2_CONV_TID0) {
                 mbar_arrive_local(&ctl->raw_empty[stage]);
                 if constexpr (CG == 2) mbar_arrive_cluster(&ctl->conv[ostage], 0);
                 else mbar_arrive_local(&ctl->conv[ostage]);
@@ -431,16 +553,20 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             if (++ostage == S) { ostage = 0; ophase ^= 1; }
         }
         if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync; }
-        // column sums: the 4 warps that share a feature combine through shared memory in a fixed
-        // order (the raw ring is idle: every TMA load has landed and been converted); the doubles
-        // appear only here, after this CTA's last tile
+        // column sums: the 4 threads (one per K chunk) that share a feature combine through shared
+        // memory in a fixed order (the raw ring is idle: every TMA load has landed and been
+        // converted); the doubles appear only here, after this CTA's last tile
         {
             double *s_sum = reinterpret_cast<double *>(raw_ring);        // [4][UM_F]
-            s_sum[kq * UM_F + f_local] = ((double)sAh + (double)sAl) / (double)sc;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (u_on[k] && u_op[k] == 0)
+                    s_sum[u_kq[k] * UM_F + u_fl[k]] = ((double)sAh[k] + (double)sAl[k]) / (double)u_sc[k];
             asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
-            if (kq == 0)
-                P.sums[(size_t)group * UM_D + UM_F * cta_rank + f_local] =
-                    ((s_sum[f_local] + s_sum[UM_F + f_local]) + s_sum[2 * UM_F + f_local]) + s_sum[3 * UM_F + f_local];
+            const int f = tid - V2_CONV_TID0;
+            if (f < UM_F)
+                P.sums[(size_t)group * UM_D + UM_F * cta_rank + f] = f < d_local
+                    ? ((s_sum[f] + s_sum[UM_F + f]) + s_sum[2 * UM_F + f]) + s_sum[3 * UM_F + f] : 0.0;
         }
     } else if (warp >= V2_FIRST_DRAIN_WARP) {
         // ================================ drain warps (one per TMEM lane quarter, every CTA) ======
@@ -468,7 +594,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const int e = next_end[q];
             if (e == 0x7fffffff) break;
             const bool last = e == my_tiles - 1;
-            const bool fold = last || ((slabs_done[q] + 1) % P.fold_every) == 0;
             const long long c0 = dbg_on ? clock64() : 0;
             mbar_wait(&ctl->acc_full[q], full_ph[q]);
             full_ph[q] ^= 1;
@@ -511,30 +636,29 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 }
             }
             const long long c2 = dbg_on ? clock64() : 0;
-            if (fold) {
-                // float32 level -> float-float pair, error-free (TwoSum), then clear the level.  This
-                // warp is the only one that ever touches these addresses; its own reductions above
-                // are ordered before these loads (same thread, same address, gpu scope).
+            if (!last && !(P.dbg_mode & 2)) {
+                // one 16-column group of this region: float32 level -> float-float pair, error-free
+                // (TwoSum), then clear the level.  This warp is the only one that ever touches these
+                // addresses; its own reductions above are ordered before these loads (same thread,
+                // same address, gpu scope).  The finalize path adds whatever is left in the level.
+                const int c = 16 * (slabs_done[q] % NG);
                 float *hi = P.hi + cta_base + (size_t)q * RW * UM_F + row;
                 float *lo = P.lo + cta_base + (size_t)q * RW * UM_F + row;
-#pragma unroll 1
-                for (int c = 0; c < RW; c += 16) {
-                    float s[16], H[16], L[16];
+                float s[16], H[16], L[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];"
-                                     : "=f"(s[j]) : "l"(l1 + (size_t)(c + j) * UM_F) : "memory");
-                        H[j] = __ldcg(hi + (size_t)(c + j) * UM_F);
-                        L[j] = __ldcg(lo + (size_t)(c + j) * UM_F);
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];"
+                                 : "=f"(s[j]) : "l"(l1 + (size_t)(c + j) * UM_F) : "memory");
+                    H[j] = __ldcg(hi + (size_t)(c + j) * UM_F);
+                    L[j] = __ldcg(lo + (size_t)(c + j) * UM_F);
+                }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float t = H[j] + s[j], bp = t - H[j];
-                        const float err = (H[j] - (t - bp)) + (s[j] - bp);
-                        __stcg(hi + (size_t)(c + j) * UM_F, t);
-                        __stcg(lo + (size_t)(c + j) * UM_F, L[j] + err);
-                        __stcg(l1 + (size_t)(c + j) * UM_F, 0.f);
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    const float t = H[j] + s[j], bp = t - H[j];
+                    const float err = (H[j] - (t - bp)) + (s[j] - bp);
+                    __stcg(hi + (size_t)(c + j) * UM_F, t);
+                    __stcg(lo + (size_t)(c + j) * UM_F, L[j] + err);
+                    __stcg(l1 + (size_t)(c + j) * UM_F, 0.f);
                 }
             }
             if (dbg_on) {
@@ -553,7 +677,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if constexpr (CG == 2) cluster_sync_all();
-    if (warp == 2) {
+    if (warp == 0) {
         if constexpr (CG == 2)
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(TMEM_COLS));
         else
@@ -561,56 +685,57 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     }
 }
 
-// reduce the CTA partials (float-float pairs -> double), symmetrise C_00, add the float64 edge
-// terms, undo scale and shift, add into `acc`.  When the fp16 range check tripped (*rescued != 0)
-// the v1 bf16 kernel rewrote the SAME memory as its float64 partials ([pair][2][col][row], unscaled).
+// Sum the CTA-level accumulators (float32 level + float-float pair) over the groups, in group order:
+// R[cta_rank][region][col][row] in float64 (1 MB at most).  Coalesced: consecutive threads read
+// consecutive rows.  Skipped when the fp16 range check tripped (the v1 rescue owns the memory then).
 template <int CG>
 __global__ void __launch_bounds__(256)
-tica_umma_v2_finalize_kernel(const float *__restrict__ hi, const float *__restrict__ lo,
-                             const double *__restrict__ v1_partials, int n_groups, int v1_pairs,
-                             const double *__restrict__ sums, int n_sum_groups_v1,
-                             const double *__restrict__ E, const double *__restrict__ es,
+tica_umma_v2_reduce_kernel(const float *__restrict__ lvl1, const float *__restrict__ hi,
+                           const float *__restrict__ lo, int n_groups,
+                           const int *__restrict__ rescued, double *__restrict__ R)
+{
+    constexpr int RW = 64 * CG;
+    constexpr size_t PER_CTA = (size_t)V2_REGIONS * RW * UM_F;
+    if (*rescued != 0) return;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= CG * PER_CTA) return;
+    const size_t rank = idx / PER_CTA, within = idx % PER_CTA;
+    double s = 0.0;
+    for (int g = 0; g < n_groups; ++g) {
+        const size_t a = ((size_t)g * CG + rank) * PER_CTA + within;
+        s += ((double)hi[a] + (double)lo[a]) + (double)lvl1[a];
+    }
+    R[idx] = s;
+}
+
+// symmetrise C_00 = G + G^T, add the float64 edge terms, undo scale and shift, add into `acc`
+template <int CG>
+__global__ void __launch_bounds__(256)
+tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restrict__ sums,
+                             int n_groups, const double *__restrict__ E, const double *__restrict__ es,
                              const float *__restrict__ shift, const float *__restrict__ scale,
                              const int *__restrict__ rescued, double n_pairs_total, double n_obs,
                              double n_seq, int Dr, double *__restrict__ acc)
 {
     constexpr int D = UM_D;
     constexpr int RW = 64 * CG;
+    if (*rescued != 0) return;
     const size_t DD = (size_t)D * D;
     const size_t RR = (size_t)Dr * Dr;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int)RR) return;
     const int i = idx / Dr, j = idx % Dr;
-    const bool resc = *rescued != 0;
-    double ctau = 0.0, c00 = 0.0;
-    int n_sum_groups;
-    if (!resc) {
-        // element (row i, feature column j) of matrix m: CTA i / 128 of the group, region 2 m + half,
-        // column (j / 128) * 64 + j % 64 of the region (half = (j % 128) / 64), row i % 128
-        auto at = [&](int g, int m, int r, int cidx) -> double {
-            const int cta = g * CG + r / UM_F;
-            const int half = (cidx % UM_F) / 64;
-            const int col = (cidx / UM_F) * 64 + (cidx % 64);
-            const size_t a = ((size_t)cta * V2_REGIONS + (size_t)(2 * m + half)) * RW * UM_F
-                             + (size_t)col * UM_F + (size_t)(r % UM_F);
-            return (double)hi[a] + (double)lo[a];
-        };
-        for (int g = 0; g < n_groups; ++g) {
-            ctau += at(g, 0, i, j);
-            c00 += at(g, 1, i, j) + at(g, 1, j, i);      // C_00 = G + G^T
-        }
-        const double inv = 1.0 / ((double)scale[i] * (double)scale[j]);
-        ctau *= inv;
-        c00 *= inv;
-        n_sum_groups = n_groups;
-    } else {
-        const size_t tidx = (size_t)j * D + i;
-        for (int p = 0; p < v1_pairs; ++p) {
-            ctau += v1_partials[(size_t)p * 2 * DD + tidx];
-            c00 += v1_partials[(size_t)p * 2 * DD + DD + tidx];
-        }
-        n_sum_groups = n_sum_groups_v1;
-    }
+    // element (row r, feature column c) of matrix m (0 = C_tau, 1 = G): CTA r / 128 of the group,
+    // region 2 m + half, column (c / 128) * 64 + c % 64 of the region (half = (c % 128) / 64), row r % 128
+    auto at = [&](int m, int r, int c) -> double {
+        const int half = (c % UM_F) / 64;
+        const int col = (c / UM_F) * 64 + (c % 64);
+        return R[(((size_t)(r / UM_F) * V2_REGIONS + (size_t)(2 * m + half)) * RW + (size_t)col) * UM_F
+                 + (size_t)(r % UM_F)];
+    };
+    const double inv = 1.0 / ((double)scale[i] * (double)scale[j]);
+    double ctau = at(0, i, j) * inv;
+    double c00 = (at(1, i, j) + at(1, j, i)) * inv;        // C_00 = G + G^T
     const size_t pidx = (size_t)i * D + j;
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
     double esi[2] = {0.0, 0.0}, esj[3] = {0.0, 0.0, 0.0};
@@ -628,7 +753,7 @@ tica_umma_v2_finalize_kernel(const float *__restrict__ hi, const float *__restri
         esj[2] += ec[2 * D + j];
     }
     double sum_i = 0.0, sum_j = 0.0;
-    for (int p = 0; p < n_sum_groups; ++p) {
+    for (int p = 0; p < n_groups; ++p) {
         sum_i += sums[(size_t)p * D + i];
         sum_j += sums[(size_t)p * D + j];
     }
@@ -653,14 +778,6 @@ tica_umma_v2_finalize_kernel(const float *__restrict__ hi, const float *__restri
             acc[3 * RR + 3 * Dr + 1] += n_seq;
         }
     }
-}
-
-__global__ void tica_umma_rescue_clear32_kernel(const int *__restrict__ flag, float *__restrict__ buf, size_t n)
-{
-    if (*flag == 0) return;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x)
-        buf[i] = 0.f;
 }
 
 }  // namespace msmb
