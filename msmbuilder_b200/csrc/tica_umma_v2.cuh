@@ -40,9 +40,12 @@ constexpr int V2_RAW_STAGES = 2;
 constexpr int V2_OP_STAGES = 4;
 constexpr int V2_CONV_WARPS = 16;
 constexpr int V2_DRAIN_WARPS = 4;
-constexpr int V2_FIRST_CONV_WARP = 2;               // w0 TMA producer (+ TMEM allocation), w1 MMA issuer
-constexpr int V2_FIRST_DRAIN_WARP = V2_FIRST_CONV_WARP + V2_CONV_WARPS;   // 18..21: four distinct lane quarters
-constexpr int V2_THREADS = 32 * (V2_FIRST_DRAIN_WARP + V2_DRAIN_WARPS);   // 704 (93 -> 88 registers per thread)
+// w0 TMA producer (+ TMEM allocation), w1 MMA issuer, w2-3 idle, w4-19 converters, w20-23 drain.
+// Registers are allocated to warps in groups of 4, so 22 warps would cost as much as 24: 768 threads
+// at 80 registers (the issuer and the converters do not spill at 80; the drain warps' fold does, into L1).
+constexpr int V2_FIRST_CONV_WARP = 4;
+constexpr int V2_FIRST_DRAIN_WARP = V2_FIRST_CONV_WARP + V2_CONV_WARPS;   // 20..23: four distinct lane quarters
+constexpr int V2_THREADS = 32 * (V2_FIRST_DRAIN_WARP + V2_DRAIN_WARPS);   // 768
 constexpr int V2_CONV_TID0 = 32 * V2_FIRST_CONV_WARP;
 constexpr int V2_REGIONS = 4;                       // (C_tau, G) x (column half 0, 1)
 constexpr int V2_T_A = 0, V2_T_AL = 1, V2_T_AH = 2, V2_T_B = 3, V2_T_BL = 4;
@@ -186,7 +189,7 @@ __device__ __forceinline__ uint64_t h2_to_f2(uint32_t h)
 
 // ---------------------------------------------------------------------------------------
 template <int CG>
-__global__ void __maxnreg__(88) tica_umma_v2_kernel(const V2Params P)
+__global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Params P)
 {
     constexpr int RW = 64 * CG;                      // columns of a region = N of every UMMA
     constexpr int TMEM_COLS = V2_REGIONS * RW;       // 512 (CG = 2) or 256 (CG = 1)

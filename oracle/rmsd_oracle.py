@@ -122,3 +122,76 @@ def cdist_rmsd(XA, XB):
     a, ga = center_and_trace(XA)
     b, gb = center_and_trace(XB)
     return rmsd_qcp(a, b, ga, gb)
+
+
+# ---------------------------------------------------------------------------------------
+# float32 restatement of the arithmetic the reference CALLS (libdistance.pyx:350-351):
+#   rmsd = sqrtf(msd_atom_major(n, n, x, y, G_x, G_y, 0, NULL))
+# msd_atom_major is mdtraj's libtheobald (absent here).  Its published structure (Haque, Beauchamp &
+# Pande's IRMSD / mdtraj `theobald_rmsd.c`, built on Theobald's qcprot.c) is: the 3x3 inner-product
+# matrix M is accumulated in FLOAT32 four atoms at a time (one SSE register per entry: a separate
+# multiply and add per 4-atom group, a horizontal add at the end); the quartic's coefficients and
+# the Newton iteration from E0 = (G_x + G_y) / 2 run in double (evalprec 1e-11, at most 50 steps);
+# the msd comes back as a float.  The order of the float32 additions inside the SSE code cannot be
+# checked without the source, so this restatement pins the PRECISION CLASS (float32 products and
+# sums of M, float32 traces, float result), not the bits: parity for 'rmsd' stays unpinned at the
+# bit level, and the GPU tests compare within the float32 envelope measured here.
+# ---------------------------------------------------------------------------------------
+
+# Known answer published with the method: the 7-atom fragments of Theobald's qcprot `main.c`
+# (Liu, Agrafiotis & Theobald 2010, supplementary code), "QCP rmsd: 0.719106" and its rotation matrix.
+QCPROT_FRAG_A = np.array([[-2.803, -15.373, 24.556], [0.893, -16.062, 25.147], [1.368, -12.371, 25.885],
+                          [-1.651, -12.153, 28.177], [-0.440, -15.218, 30.068], [2.551, -13.273, 31.372],
+                          [0.105, -11.330, 33.567]])
+QCPROT_FRAG_B = np.array([[-14.739, -18.673, 15.040], [-12.473, -15.810, 16.074], [-14.802, -13.307, 14.408],
+                          [-17.782, -14.852, 16.171], [-16.124, -14.617, 19.584], [-15.029, -11.037, 18.902],
+                          [-18.577, -10.001, 17.996]])
+QCPROT_RMSD = 0.719106
+QCPROT_ROTATION = np.array([[0.72216358, 0.69118937, -0.0271479],
+                            [-0.52038257, 0.51700833, -0.67963547],
+                            [-0.45572112, 0.50493528, 0.73304748]])
+
+
+def inner_products_f32_sse(x, y):
+    """M[p, q] = sum_a x[a, p] * y[a, q] the way a 4-wide float32 SIMD loop forms it: lane a % 4 adds
+    fl32(x * y) in atom order (separate multiply and add), then (s0 + s1) + (s2 + s3)."""
+    x = np.asarray(x, dtype=np.float32)
+    y = np.asarray(y, dtype=np.float32)
+    n = x.shape[0]
+    lanes = np.zeros((4, 3, 3), dtype=np.float32)
+    for a in range(n):
+        prod = (x[a][:, None] * y[a][None, :]).astype(np.float32)
+        lanes[a & 3] = (lanes[a & 3] + prod).astype(np.float32)
+    return ((lanes[0] + lanes[1]).astype(np.float32) + (lanes[2] + lanes[3]).astype(np.float32)).astype(np.float32)
+
+
+def msd_from_M_and_G(M, Ga, Gb, n_atoms, evalprec=1e-11):
+    """Published QCP Newton iteration (qcprot.c FastCalcRMSDAndRotation) in double on a given M."""
+    M = np.asarray(M, dtype=np.float64)
+    c2 = -2.0 * float((M * M).sum())
+    c1 = -8.0 * float(np.linalg.det(M))
+    c0 = float(np.linalg.det(key_matrix(M)))
+    e0 = 0.5 * (float(Ga) + float(Gb))
+    lam = e0
+    for _ in range(50):
+        old = lam
+        x2 = lam * lam
+        b = (x2 + c2) * lam
+        a = b + c1
+        lam -= (a * lam + c0) / (2.0 * x2 * lam + b + a)
+        if abs(lam - old) < abs(evalprec * lam):
+            break
+    return abs(2.0 * (e0 - lam) / n_atoms)
+
+
+def rmsd_theobald_f32(X, Y, GX, GY):
+    """All pairs, float32 accumulation of M (SIMD order), double Newton, float msd, float sqrt."""
+    X = np.asarray(X, dtype=np.float32)
+    Y = np.asarray(Y, dtype=np.float32)
+    out = np.empty((len(X), len(Y)), dtype=np.float32)
+    for i in range(len(X)):
+        for j in range(len(Y)):
+            msd = np.float32(msd_from_M_and_G(inner_products_f32_sse(X[i], Y[j]), np.float32(GX[i]),
+                                              np.float32(GY[j]), X.shape[1]))
+            out[i, j] = np.sqrt(msd, dtype=np.float32)
+    return out
