@@ -27,8 +27,10 @@ static constexpr int kChunk = 4096;
 template <typename T>
 __global__ void __launch_bounds__(256)
 tica_outer_kernel(const TicaItem *__restrict__ items, int D, long long ld, int lag,
-                  double *__restrict__ acc)
+                  double *__restrict__ acc, const int *__restrict__ run_if)
 {
+    // rescue launch of the tensor-core engine: uniform over the grid
+    if (run_if != nullptr && *reinterpret_cast<const volatile int *>(run_if) == 0) return;
     __shared__ double sA0[RS][TS], sB0[RS][TS], sAt[RS][TS], sBt[RS][TS];
     const TicaItem it = items[blockIdx.x];
     const T *X = reinterpret_cast<const T *>(it.base);
@@ -102,8 +104,9 @@ tica_outer_kernel(const TicaItem *__restrict__ items, int D, long long ld, int l
 template <typename T>
 __global__ void __launch_bounds__(256)
 tica_sums_kernel(const TicaItem *__restrict__ items, int D, long long ld, int lag,
-                 double *__restrict__ acc)
+                 double *__restrict__ acc, const int *__restrict__ run_if)
 {
+    if (run_if != nullptr && *reinterpret_cast<const volatile int *>(run_if) == 0) return;
     const TicaItem it = items[blockIdx.x];
     const T *X = reinterpret_cast<const T *>(it.base);
     double *S0 = acc + 3 * (size_t)D * D;
@@ -130,18 +133,20 @@ tica_sums_kernel(const TicaItem *__restrict__ items, int D, long long ld, int la
     }
 }
 
-__global__ void tica_counts_kernel(double *acc, int D, double n_obs, double n_seq)
+__global__ void tica_counts_kernel(double *acc, int D, double n_obs, double n_seq, const int *run_if)
 {
+    if (run_if != nullptr && *reinterpret_cast<const volatile int *>(run_if) == 0) return;
     double *tail = acc + 3 * (size_t)D * D + 3 * (size_t)D;
     tail[0] += n_obs;
     tail[1] += n_seq;
 }
 
-template <typename T>
-static int run_simt(const void *const *seq_ptrs, const int64_t *seq_rows, int n_seq, int D,
-                    int64_t ld, int lag, double *acc, cudaStream_t st)
+// host side of the item table: one item per <= kChunk pair indices of a usable sequence
+size_t tica_simt_items(const void *const *seq_ptrs, const int64_t *seq_rows, int n_seq, int lag,
+                       void *items_out /* NULL: count only */, double *n_obs_out, double *n_used_out)
 {
-    std::vector<TicaItem> items;
+    TicaItem *out = reinterpret_cast<TicaItem *>(items_out);
+    size_t n_items = 0;
     double n_obs = 0.0, n_used = 0.0;
     for (int s = 0; s < n_seq; ++s) {
         const long long n = seq_rows[s];
@@ -150,39 +155,63 @@ static int run_simt(const void *const *seq_ptrs, const int64_t *seq_rows, int n_
         n_used += 1.0;
         const long long pairs = n - lag;
         for (long long t0 = 0; t0 < pairs; t0 += kChunk) {
-            TicaItem it;
-            it.base = seq_ptrs[s];
-            it.t0 = t0;
-            it.count = (int)((pairs - t0) < kChunk ? (pairs - t0) : kChunk);
-            it.pad = 0;
-            items.push_back(it);
+            if (out) {
+                TicaItem it;
+                it.base = seq_ptrs[s];
+                it.t0 = t0;
+                it.count = (int)((pairs - t0) < kChunk ? (pairs - t0) : kChunk);
+                it.pad = 0;
+                out[n_items] = it;
+            }
+            ++n_items;
         }
     }
-    if (items.empty()) return MSMB200_OK;
-    TicaItem *d_items = nullptr;
-    MSMB_CUDA(cudaMallocAsync(&d_items, sizeof(TicaItem) * items.size(), st));
-    MSMB_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(TicaItem) * items.size(),
-                              cudaMemcpyHostToDevice, st));
-    // the host vector must outlive the (pageable => staged) copy
-    MSMB_CUDA(cudaStreamSynchronize(st));
+    if (n_obs_out) *n_obs_out = n_obs;
+    if (n_used_out) *n_used_out = n_used;
+    return n_items;
+}
+size_t tica_simt_item_bytes() { return sizeof(TicaItem); }
+
+// the three launches on a device-resident item table; with `run_if` they only work when *run_if != 0
+int tica_simt_launch(const void *d_items, size_t n_items, int D, int64_t ld, int dtype, int lag,
+                     double n_obs, double n_used, double *acc, const int *run_if, cudaStream_t st)
+{
+    if (n_items == 0) return MSMB200_OK;
+    const TicaItem *items = reinterpret_cast<const TicaItem *>(d_items);
     const int tiles = (D + TS - 1) / TS;
-    dim3 grid((unsigned)items.size(), tiles, tiles);
-    tica_outer_kernel<T><<<grid, 256, 0, st>>>(d_items, D, ld, lag, acc);
+    dim3 grid((unsigned)n_items, tiles, tiles);
+    if (dtype == MSMB200_F64) {
+        tica_outer_kernel<double><<<grid, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
+        MSMB_LAUNCH_CHECK();
+        tica_sums_kernel<double><<<(unsigned)n_items, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
+    } else {
+        tica_outer_kernel<float><<<grid, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
+        MSMB_LAUNCH_CHECK();
+        tica_sums_kernel<float><<<(unsigned)n_items, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
+    }
     MSMB_LAUNCH_CHECK();
-    tica_sums_kernel<T><<<(unsigned)items.size(), 256, 0, st>>>(d_items, D, ld, lag, acc);
+    tica_counts_kernel<<<1, 1, 0, st>>>(acc, D, n_obs, n_used, run_if);
     MSMB_LAUNCH_CHECK();
-    tica_counts_kernel<<<1, 1, 0, st>>>(acc, D, n_obs, n_used);
-    MSMB_LAUNCH_CHECK();
-    MSMB_CUDA(cudaFreeAsync(d_items, st));
     return MSMB200_OK;
 }
 
 int tica_simt_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, int n_seq,
                          int D, int64_t ld, int dtype, int lag, double *acc, cudaStream_t st)
 {
-    if (dtype == MSMB200_F64)
-        return run_simt<double>(seq_ptrs, seq_rows, n_seq, D, ld, lag, acc, st);
-    return run_simt<float>(seq_ptrs, seq_rows, n_seq, D, ld, lag, acc, st);
+    double n_obs = 0.0, n_used = 0.0;
+    const size_t n_items = tica_simt_items(seq_ptrs, seq_rows, n_seq, lag, nullptr, nullptr, nullptr);
+    if (n_items == 0) return MSMB200_OK;
+    std::vector<TicaItem> items(n_items);
+    tica_simt_items(seq_ptrs, seq_rows, n_seq, lag, items.data(), &n_obs, &n_used);
+    TicaItem *d_items = nullptr;
+    MSMB_CUDA(cudaMallocAsync(&d_items, sizeof(TicaItem) * n_items, st));
+    MSMB_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(TicaItem) * n_items,
+                              cudaMemcpyHostToDevice, st));
+    // the host vector must outlive the (pageable => staged) copy
+    MSMB_CUDA(cudaStreamSynchronize(st));
+    const int rc = tica_simt_launch(d_items, n_items, D, ld, dtype, lag, n_obs, n_used, acc, nullptr, st);
+    MSMB_CUDA(cudaFreeAsync(d_items, st));
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

@@ -1082,6 +1082,13 @@ tica_umma_finalize_kernel(const double *__restrict__ partials, int n_pairs,
 #include "tica_umma_v2.cuh"
 namespace msmb {
 
+// float64 engine (tica_simt.cu): the rescue of the second-generation fp16 engine
+size_t tica_simt_items(const void *const *seq_ptrs, const int64_t *seq_rows, int n_seq, int lag,
+                       void *items_out, double *n_obs_out, double *n_used_out);
+size_t tica_simt_item_bytes();
+int tica_simt_launch(const void *d_items, size_t n_items, int D, int64_t ld, int dtype, int lag,
+                     double n_obs, double n_used, double *acc, const int *run_if, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -1230,6 +1237,14 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const size_t o_blocks = off; off = align_up(off + sizeof(int) * n_seq, 128);
     const size_t o_eseq = off; off = align_up(off + sizeof(EdgeSeq) * n_seq, 128);
     const size_t o_sample = off; off = align_up(off + sizeof(const float *) * UM_SAMPLE_ROWS, 128);
+    // item table of the float64 engine (the v2 engine's rescue runs on the stream, guarded by the flag)
+    const bool f16 = passes == 23;                  // 23 = 3xF16 (see lib.cu)
+    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16: 2-byte operands, K = 16
+    // second-generation fp16 engine (tica_umma_v2.cuh): single-CTA tiles for D <= 128, CTA pairs above
+    const bool v2 = f16 && env_int("MSMB200_UMMA_V1", 0) == 0;
+    const int v2_cg = D <= UM_F ? 1 : 2;
+    const size_t n_items = v2 ? tica_simt_items(seq_ptrs, seq_rows, n_seq_in, lag, nullptr, nullptr, nullptr) : 0;
+    const size_t o_items = off; off = align_up(off + tica_simt_item_bytes() * n_items, 128);
     int dev = 0;
     MSMB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= UM_MAX_DEVICES) {
@@ -1248,6 +1263,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     int *tile_prefix = reinterpret_cast<int *>(hb + o_prefix);
     int *seq_pairs = reinterpret_cast<int *>(hb + o_blocks);
     memcpy(hb + o_eseq, seqs.data(), sizeof(EdgeSeq) * n_seq);
+    double simt_n_obs = 0.0, simt_n_used = 0.0;
+    if (n_items) tica_simt_items(seq_ptrs, seq_rows, n_seq_in, lag, hb + o_items, &simt_n_obs, &simt_n_used);
     {
         // sample row j = frame floor(j * total / rows) of the concatenated call
         const float **sample = reinterpret_cast<const float **>(hb + o_sample);
@@ -1302,13 +1319,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     }
     tile_prefix[n_seq] = (int)tiles;
 
-    const bool f16 = passes == 23;                  // 23 = 3xF16 (see lib.cu)
-    const bool bf16 = passes >= 10;                 // 13 = 3xBF16, 16 = 6xBF16: 2-byte operands, K = 16
-    // second-generation fp16 engine (tica_umma_v2.cuh): single-CTA tiles for D <= 128, CTA pairs above
-    const bool v2 = f16 && env_int("MSMB200_UMMA_V1", 0) == 0;
-    const int v2_cg = D <= UM_F ? 1 : 2;
-
-    // v1 CTA pairs (also the rescue engine of v2)
+    // v1 CTA pairs
     int n_pairs = sm_count() / 2;
     n_pairs = env_int("MSMB200_UMMA_PAIRS", n_pairs);
     if (n_pairs > UM_MAX_PAIRS) n_pairs = UM_MAX_PAIRS;
@@ -1323,7 +1334,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const size_t v1_part_bytes = (sizeof(double) + sizeof(float)) * 2 * DD * n_pairs;
     const size_t v2_per_cta = (size_t)V2_REGIONS * (64 * v2_cg) * UM_F;            // floats per array
     const size_t v2_part_bytes = v2 ? 3 * sizeof(float) * v2_per_cta * (size_t)(n_groups * v2_cg) : 0;
-    const size_t part_bytes = v1_part_bytes > v2_part_bytes ? v1_part_bytes : v2_part_bytes;
+    const size_t part_bytes = v2 ? v2_part_bytes : v1_part_bytes;
     const size_t need = ws_fixed_bytes(UM_D) + part_bytes;
     if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u)) {
         set_error("tica_accumulate: workspace too small or misaligned (%zu < %zu); size it with "
@@ -1481,22 +1492,23 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                 tica_umma_kernel<UM_KIND_F16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
             }
             MSMB_LAUNCH_CHECK();
-            // Range rescue, all on the stream (no host round trip): if a scaled value left fp16's
-            // range the two launches below wipe the partials and redo the call with the 6xBF16
-            // engine (full fp32 exponent range); otherwise both exit at once.
-            tica_umma_rescue_clear_kernel<<<2, 256, 0, st>>>(
-                d_flag, reinterpret_cast<double *>(wsb + w_sums), (w_E - w_sums) / sizeof(double));
-            MSMB_LAUNCH_CHECK();
-            tica_umma_rescue_clear_kernel<<<4 * sm_count(), 256, 0, st>>>(
-                d_flag, P.partials, (v2 ? (v1_part_bytes > v2_part_bytes ? v2_part_bytes : v1_part_bytes)
-                                        : v1_part_bytes) / sizeof(double));
-            MSMB_LAUNCH_CHECK();
-            UmmaParams Q = P;
-            Q.passes = 6;
-            Q.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", 2 * UM_SLAB_TILES_DEFAULT);
-            Q.run_if = d_flag;
-            Q.dbg = nullptr;
-            tica_umma_kernel<UM_KIND_BF16><<<2 * n_pairs, UM_THREADS, smem, st>>>(Q);
+            if (!v2) {
+                // Range rescue, all on the stream (no host round trip): if a scaled value left fp16's
+                // range the two launches below wipe the partials and redo the call with the 6xBF16
+                // engine (full fp32 exponent range); otherwise both exit at once.
+                tica_umma_rescue_clear_kernel<<<2, 256, 0, st>>>(
+                    d_flag, reinterpret_cast<double *>(wsb + w_sums), (w_E - w_sums) / sizeof(double));
+                MSMB_LAUNCH_CHECK();
+                tica_umma_rescue_clear_kernel<<<4 * sm_count(), 256, 0, st>>>(
+                    d_flag, P.partials, v1_part_bytes / sizeof(double));
+                MSMB_LAUNCH_CHECK();
+                UmmaParams Q = P;
+                Q.passes = 6;
+                Q.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", 2 * UM_SLAB_TILES_DEFAULT);
+                Q.run_if = d_flag;
+                Q.dbg = nullptr;
+                tica_umma_kernel<UM_KIND_BF16><<<2 * n_pairs, UM_THREADS, smem, st>>>(Q);
+            }
         } else if (bf16) tica_umma_kernel<UM_KIND_BF16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
         else tica_umma_kernel<UM_KIND_TF32><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
         MSMB_LAUNCH_CHECK();
@@ -1528,13 +1540,19 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                 n_pairs_total, n_obs, (double)n_seq, D, acc);
         }
         MSMB_LAUNCH_CHECK();
+        // Range rescue, all on the stream (no host round trip): when a converter raised the flag the
+        // two kernels above left `acc` untouched and the float64 engine (exact reference arithmetic,
+        // tica_simt.cu) does the whole call; otherwise its three launches exit at once.
+        const int rc = tica_simt_launch(scratch + o_items, n_items, D, ld, MSMB200_F32, lag, simt_n_obs,
+                                        simt_n_used, acc, d_flag, st);
+        if (rc != MSMB200_OK) return rc;
+    } else {
+        tica_umma_finalize_kernel<<<fin_blocks, 256, 0, st>>>(
+            P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(wsb + w_E),
+            reinterpret_cast<const double *>(wsb + w_es), d_shift, f16 ? d_scale : nullptr, d_flag,
+            0, n_pairs_total, n_obs, (double)n_seq, D, acc);
+        MSMB_LAUNCH_CHECK();
     }
-    // v1 engines, and the rescued call of v2 (the bf16 kernel wrote v1's float64 partials)
-    tica_umma_finalize_kernel<<<fin_blocks, 256, 0, st>>>(
-        P.partials, n_pairs, P.sums, reinterpret_cast<const double *>(wsb + w_E),
-        reinterpret_cast<const double *>(wsb + w_es), d_shift, f16 ? d_scale : nullptr, d_flag,
-        v2 ? 1 : 0, n_pairs_total, n_obs, (double)n_seq, D, acc);
-    MSMB_LAUNCH_CHECK();
     if (d_dbg) {
         long long h[16];
         MSMB_CUDA(cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -50,6 +50,7 @@ constexpr int V2_CONV_TID0 = 32 * V2_FIRST_CONV_WARP;
 constexpr int V2_REGIONS = 4;                       // (C_tau, G) x (column half 0, 1)
 constexpr int V2_T_A = 0, V2_T_AL = 1, V2_T_AH = 2, V2_T_B = 3, V2_T_BL = 4;
 constexpr int V2_MAX_GROUPS = 192;                  // CTA pairs (CG = 2) or CTAs (CG = 1)
+constexpr uint32_t V2_RANGE_LIMIT = 0x5400u;        // fp16 bit pattern of 64.0 = 2^6
 
 struct V2Params {
     const CUtensorMap *mapsA;     // [n_seq] unlagged
@@ -64,7 +65,7 @@ struct V2Params {
     int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
-    int *overflow;                // set to 1 when an accumulator went non-finite (fp16 range)
+    int *overflow;                // set to 1 when a scaled value reached 2^6 (or was not finite): float64 rescue
     float *lvl1;                  // [n_ctas][4][RW][128] float32 level (red.add target)
     float *hi, *lo;               // same shape: float-float second level
     double *sums;                 // [n_groups][UM_D] column sums of x' (unscaled)
@@ -177,6 +178,21 @@ __device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b)
     uint64_t r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
+}
+// explicit shared-state-space accesses with 32-bit addresses: the ring pointers come out of an
+// integer round-up, so the compiler only sees generic pointers (LD / ST instead of LDS / STS)
+template <int IMM>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0+%1], {%2, %3, %4, %5};"
+                 :: "r"(addr), "n"(IMM), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 // fp16 pair -> the two floats it holds (exact)
 __device__ __forceinline__ uint64_t h2_to_f2(uint32_t h)
@@ -448,6 +464,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         int u_op[2], u_kq[2], u_fl[2];
         float u_sc[2], u_nsh[2];
         bool u_on[2];
+        uint32_t u_src[2], u_dst[2];       // byte offsets of the unit inside a raw stage / an operand stage
+        const int chunk = lane >> 2, within = (lane & 3) * 4;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int u = cw + 16 * k;
@@ -459,9 +477,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             u_fl[k] = 32 * (uu % nf) + lane;
             u_sc[k] = ctl->sc[u_fl[k]];
             u_nsh[k] = ctl->nsh[u_fl[k]];
+            // raw tile of block fb: [frame][128 B], 16-byte chunks XOR-swizzled by frame & 7.  Frame
+            // 8 kq + i sits at  base + i * 128  with the chunk bits flipped by i: one XOR with an
+            // immediate per load, the row offset folds into the instruction
+            u_src[k] = (uint32_t)(u_op[k] * UM_TILE_BYTES + (u_fl[k] >> 5) * (UM_KT * 128)
+                                  + u_kq[k] * 1024 + (chunk << 4) + within);
+            u_dst[k] = (uint32_t)((u_op[k] == 0 ? V2_T_A : V2_T_B) * V2_TILE + u_fl[k] * 16 + u_kq[k] * UM_LBO);
         }
-        const int chunk = lane >> 2, within = (lane & 3) * 4;
+        const uint32_t raw_s = smem_u32(raw_ring), op_s = smem_u32(op_ring);
         float sAh[2] = {0.f, 0.f}, sAl[2] = {0.f, 0.f};   // column sums (operand 0 units) as float pairs
+        uint32_t hmax = 0;                               // largest |h| seen, as two fp16 bit patterns
         int stage = 0, ostage = 0;
         uint32_t phase = 0, ophase = 0;
         const bool dbg_on = P.dbg != nullptr && group == 0 && tid == V2_CONV_TID0 && cta_rank == 0;
@@ -473,21 +498,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             mbar_wait(&ctl->empty[ostage], ophase ^ 1);
             long long q2 = dbg_on ? clock64() : 0;
             const int valid = ctl->valid_rows[stage];
-            const unsigned char *rawst = raw_ring + stage * UM_RAW_BYTES;
-            unsigned char *st = op_ring + ostage * V2_STAGE_BYTES;
+            const uint32_t rawst = raw_s + (uint32_t)stage * UM_RAW_BYTES;
+            const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
             auto convert_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
                 float v[2][8];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     if (!u_on[k]) continue;
-                    const unsigned char *raw = rawst + u_op[k] * UM_TILE_BYTES
-                                               + (u_fl[k] >> 5) * (UM_KT * 128) + within;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 8 * u_kq[k] + i;
-                        v[k][i] = *reinterpret_cast<const float *>(raw + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    }
+                    const uint32_t b = rawst + u_src[k];
+                    v[k][0] = lds_f32<0 * 128>(b);
+                    v[k][1] = lds_f32<1 * 128>(b ^ (1u << 4));
+                    v[k][2] = lds_f32<2 * 128>(b ^ (2u << 4));
+                    v[k][3] = lds_f32<3 * 128>(b ^ (3u << 4));
+                    v[k][4] = lds_f32<4 * 128>(b ^ (4u << 4));
+                    v[k][5] = lds_f32<5 * 128>(b ^ (5u << 4));
+                    v[k][6] = lds_f32<6 * 128>(b ^ (6u << 4));
+                    v[k][7] = lds_f32<7 * 128>(b ^ (7u << 4));
                 }
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
@@ -516,17 +543,25 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                         f2_unpack(l2, l0, l1);
                         lw[i] = pack_f16(l0, l1);
                     }
-                    unsigned char *dst = st + u_fl[k] * 16 + u_kq[k] * UM_LBO;
+                    // range check: largest |h| of this thread (Inf and NaN sort above every finite value)
+                    {
+                        uint32_t m01, m23;
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(hw[0] & 0x7FFF7FFFu), "r"(hw[1] & 0x7FFF7FFFu));
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(m23) : "r"(hw[2] & 0x7FFF7FFFu), "r"(hw[3] & 0x7FFF7FFFu));
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(m01), "r"(m23));
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
+                    }
+                    const uint32_t dst = st + u_dst[k];
                     if (u_op[k] == 0) {
-                        *reinterpret_cast<uint4 *>(dst + V2_T_A * V2_TILE) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4 *>(dst + V2_T_AL * V2_TILE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // a
+                        sts_v4<(V2_T_AL - V2_T_A) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // al
                         // h / 2 (one exact fp16 multiply per pair): the second factor of the G product
-                        uint4 hh;
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.x) : "r"(hw[0]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.y) : "r"(hw[1]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.z) : "r"(hw[2]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hh.w) : "r"(hw[3]), "r"(0x38003800u));
-                        *reinterpret_cast<uint4 *>(dst + V2_T_AH * V2_TILE) = hh;
+                        uint32_t h0, h1, h2, h3;
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h0) : "r"(hw[0]), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h1) : "r"(hw[1]), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h2) : "r"(hw[2]), "r"(0x38003800u));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h3) : "r"(hw[3]), "r"(0x38003800u));
+                        sts_v4<(V2_T_AH - V2_T_A) * V2_TILE>(dst, h0, h1, h2, h3);              // ah
                         // column sum: TwoSum of the tile's 8-frame sum into the float pair
                         float s0, s1;
                         f2_unpack(sum2, s0, s1);
@@ -535,8 +570,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                         sAl[k] += (sAh[k] - (tt - bp)) + (ts - bp);
                         sAh[k] = tt;
                     } else {
-                        *reinterpret_cast<uint4 *>(dst + V2_T_B * V2_TILE) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4 *>(dst + V2_T_BL * V2_TILE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // b
+                        sts_v4<(V2_T_BL - V2_T_B) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // bl
                     }
                 }
             };
@@ -556,6 +591,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             if (++ostage == S) { ostage = 0; ophase ^= 1; }
         }
         if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync; }
+        // Range check.  The scale puts the largest magnitude of the sample into [1, 2).  A value 2^6
+        // times larger still fits fp16, but its 22-bit split is then coarse next to everything else
+        // (the bulk of the feature drowns in the rounding of the outlier's square), and beyond 65504
+        // h is Inf.  Either way the whole call is redone by the float64 engine (guarded launches
+        // behind this kernel; non-finite input takes the same detour and comes out as in float64).
+        if (max(hmax & 0xFFFFu, hmax >> 16) >= V2_RANGE_LIMIT) atomicOr(P.overflow, 1);
         // column sums: the 4 threads (one per K chunk) that share a feature combine through shared
         // memory in a fixed order (the raw ring is idle: every TMA load has landed and been
         // converted); the doubles appear only here, after this CTA's last tile
@@ -578,7 +619,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         const size_t cta_base = (size_t)cta_global * V2_REGIONS * RW * UM_F;
         int next_end[V2_REGIONS], slabs_done[V2_REGIONS];
         uint32_t full_ph[V2_REGIONS];
-        uint32_t absmax = 0;
         const bool dbg_on = P.dbg != nullptr && group == 0 && cta_rank == 0 && quarter == 0 && lane == 0;
         long long d_wait = 0, d_ld = 0, d_red = 0, d_fold = 0, n_events = 0;
 #pragma unroll
@@ -625,7 +665,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     float *dst = l1 + (size_t)(32 * c) * UM_F;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        absmax = max(absmax, v[j] & 0x7FFFFFFFu);     // Inf / NaN sort above every finite value
                         asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;"
                                      :: "l"(dst + (size_t)j * UM_F), "f"(__uint_as_float(v[j])) : "memory");
                     }
@@ -672,7 +711,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             if (last) next_end[q] = 0x7fffffff;
             else next_end[q] = e + ST < my_tiles - 1 ? e + ST : my_tiles - 1;
         }
-        if (absmax >= 0x7F800000u) atomicOr(P.overflow, 1);
         if (dbg_on) { P.dbg[8] = d_wait; P.dbg[9] = d_ld; P.dbg[10] = d_red; P.dbg[11] = d_fold; P.dbg[12] = n_events; }
     }
 
