@@ -233,6 +233,19 @@ int msmb200_rmsd_kcenters_pass(const float *xyz, const float *traces, int64_t n,
                                int32_t *labels, int64_t row_offset,
                                msmb200_candidate *out, void *workspace,
                                size_t workspace_bytes, void *stream);
+/* The same pass, skipping the frames the triangle inequality rules out (RMSD is a metric):
+ * a frame whose centre c satisfies d(c, new) >= 2 d(frame, c) + margin cannot move to the new
+ * centre, so only its 16 bytes of (distance, label, trace) are read.  centre_slots: candidate
+ * slots 0 .. center_label, slot_stride bytes apart (slot j = centre j as written by pass j - 1;
+ * payload n_atoms*3 coords + G at byte 16); labels must hold the centre index of every frame
+ * (true after pass 0).  Writes exactly what msmb200_rmsd_kcenters_pass writes (kcenters.py:91-97).
+ * workspace: msmb200_rmsd_pass_workspace_bytes(n, k) bytes, zeroed once before the first pass. */
+int msmb200_rmsd_kcenters_pass_pruned(const float *xyz, const float *traces, int64_t n,
+                                      int n_atoms, const void *centre_slots, size_t slot_stride,
+                                      int32_t center_label, double *distances, int32_t *labels,
+                                      int64_t row_offset, msmb200_candidate *out, void *workspace,
+                                      size_t workspace_bytes, void *stream);
+size_t msmb200_rmsd_pass_workspace_bytes(int64_t n, int32_t max_centres);
 int msmb200_rmsd_assign_nearest(const float *xyz, const float *traces, int64_t n,
                                 int n_atoms, const float *Y, const float *Y_traces,
                                 int k, const int64_t *rows, int64_t n_rows,

@@ -4,6 +4,7 @@ Everything here launches on torch's current stream and returns without
 synchronising unless a Python scalar is requested.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -27,7 +28,7 @@ class KCentersState(object):
     """Per-shard state of a k-centers run on a (n, d) device tensor (vector
     metrics) or a centred (n, n_atoms, 3) tensor + traces (rmsd)."""
 
-    def __init__(self, data, metric, traces=None, row_offset=0):
+    def __init__(self, data, metric, traces=None, row_offset=0, max_centres=0):
         _lib.require_gpu()
         self.data = data
         self.rmsd = (metric == "rmsd")
@@ -47,8 +48,12 @@ class KCentersState(object):
         self.cand_bytes = int(lib.msmb200_candidate_bytes(self.row_elems, self.dtype))
         self.distances = torch.full((self.n,), float("inf"), dtype=torch.float64, device="cuda")
         self.labels = torch.zeros((self.n,), dtype=torch.int32, device="cuda")
-        self.ws = torch.zeros(int(lib.msmb200_kcenters_workspace_bytes(0)), dtype=torch.uint8,
-                              device="cuda")
+        ws_bytes = int(lib.msmb200_kcenters_workspace_bytes(0))
+        if self.rmsd:
+            # the pruned RMSD pass keeps a compact list of the frames it has to look at
+            ws_bytes = max(ws_bytes, int(lib.msmb200_rmsd_pass_workspace_bytes(self.n, int(max_centres))))
+        self.max_centres = int(max_centres)
+        self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
         self.local = torch.zeros(self.cand_bytes, dtype=torch.uint8, device="cuda")
 
     def payload_ptr(self, cand):
@@ -68,10 +73,13 @@ class KCentersState(object):
             _lib.call("msmb200_candidate_from_row", dev.ptr(self.data), int(local_row), self.d,
                       self.d, self.dtype, self.row_offset, dev.ptr(cand), dev.stream_ptr())
 
-    def run_pass(self, center_cand, label, out_cand=None, start=0):
+    def run_pass(self, center_cand, label, out_cand=None, start=0, ring=None):
         """One pass against the centre stored in `center_cand`; this shard's
         farthest frame is written to `out_cand` (default: self.local).  `start`
-        restricts the pass to rows [start, n) (RegularSpatial never looks back)."""
+        restricts the pass to rows [start, n) (RegularSpatial never looks back).
+        `ring` (RMSD only): the (k + 1, cand_bytes) tensor whose slot j holds centre j and whose
+        slot `label` is `center_cand` -- the pass then skips the frames the triangle inequality
+        rules out (same result, see msmb200_rmsd_kcenters_pass_pruned)."""
         out = self.local if out_cand is None else out_cand
         start = int(start)
         n = self.n - start
@@ -80,7 +88,13 @@ class KCentersState(object):
         data = self.data[start:]
         dist = self.distances[start:]
         lab = self.labels[start:]
-        if self.rmsd:
+        if (self.rmsd and ring is not None and start == 0 and 0 < int(label) <= self.max_centres
+                and not os.environ.get("MSMB200_RMSD_NO_PRUNE")):
+            _lib.call("msmb200_rmsd_kcenters_pass_pruned", dev.ptr(data), dev.ptr(self.traces),
+                      n, self.n_atoms, dev.ptr(ring), int(ring.stride(0)), int(label),
+                      dev.ptr(dist), dev.ptr(lab), self.row_offset,
+                      dev.ptr(out), dev.ptr(self.ws), self.ws.numel(), dev.stream_ptr())
+        elif self.rmsd:
             _lib.call("msmb200_rmsd_kcenters_pass", dev.ptr(data), dev.ptr(self.traces[start:]),
                       n, self.n_atoms, self.payload_ptr(center_cand), int(label),
                       dev.ptr(dist), dev.ptr(lab), self.row_offset + start,
@@ -108,15 +122,15 @@ def kcenters_fit(data, n_clusters, metric, seed_index, traces=None, lookahead=Tr
         ids, _, distances, labels = kcenters_fit_lookahead(data, n_clusters, metric, seed_index,
                                                            stats=stats)
         return ids, distances, labels
-    st = KCentersState(data, metric, traces=traces)
     k = int(n_clusters)
+    st = KCentersState(data, metric, traces=traces, max_centres=k)
     if stats is not None:
         stats["passes"] = k
     # ring of k candidate slots: slot i holds centre i (its index is cluster_ids_[i])
     ring = torch.zeros((k + 1, st.cand_bytes), dtype=torch.uint8, device="cuda")
     st.seed(ring[0], int(seed_index))
     for i in range(k):
-        st.run_pass(ring[i], i, out_cand=ring[i + 1])
+        st.run_pass(ring[i], i, out_cand=ring[i + 1], ring=ring)
     ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
     return ids, st.distances, st.labels
 

@@ -63,6 +63,9 @@ SIGNATURES = {
     "msmb200_rmsd_center": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "msmb200_rmsd_kcenters_pass": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i32, c_vp, c_vp,
                                            c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "msmb200_rmsd_kcenters_pass_pruned": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_sz, c_i32, c_vp,
+                                                  c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "msmb200_rmsd_pass_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "msmb200_rmsd_assign_nearest": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp,
                                             c_i64, c_vp, c_vp, c_vp, c_vp]),
     "msmb200_rmsd_dist": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_flt, c_vp, c_i64, c_vp,

@@ -102,14 +102,14 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t *bar)
 // One UMMA (kind::f16, fp16 x fp16 -> fp32).  MODE picks the collector hint for the A operand:
 // 0 none, 1 fill, 2 use, 3 lastuse -- the caller strings together the MMAs that share A.
 #define V2_MMA_ASM(CGS, VEC, QUAL) asm volatile( \
-    "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t" \
-    "@q tcgen05.mma.cta_group::" CGS ".kind::f16" QUAL " [%0], %1, %2, %3, " VEC ", p;\n\t}" \
-    :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(leader) : "memory")
+    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" \
+    "tcgen05.mma.cta_group::" CGS ".kind::f16" QUAL " [%0], %1, %2, %3, " VEC ", p;\n\t}" \
+    :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory")
 #define V2_VEC8 "{%5, %5, %5, %5, %5, %5, %5, %5}"
 #define V2_VEC4 "{%5, %5, %5, %5}"
 template <int CG, int MODE>
 __device__ __forceinline__ void v2_mma(uint32_t tmem_d, uint64_t da, uint64_t db,
-                                       uint32_t idesc, uint32_t acc, uint32_t leader)
+                                       uint32_t idesc, uint32_t acc)
 {
     if constexpr (CG == 2) {
         if constexpr (MODE == 1) V2_MMA_ASM("2", V2_VEC8, ".collector::a::fill");
@@ -123,20 +123,34 @@ __device__ __forceinline__ void v2_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         else V2_MMA_ASM("1", V2_VEC4, "");
     }
 }
+// The MMA warp runs its bookkeeping warp-uniformly and issues the tcgen05 instructions from ONE lane
+// inside `if (elect_one_sync())`: nvcc recognises this form (it is CUTLASS's), knows that a single
+// lane is active in the region and moves the operands to uniform registers without a waterfall.  A
+// per-instruction lane predicate instead gave an ELECT / BRA.U.ANY loop around every UTCHMMA (~120
+// cycles of issue per MMA, r2c profile).
+__device__ __forceinline__ uint32_t elect_one_sync()
+{
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t}"
+        : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
 // arrive on `bar` (in every CTA of the group) when all MMAs issued so far have completed
 template <int CG>
-__device__ __forceinline__ void v2_commit(uint64_t *bar, uint32_t leader)
+__device__ __forceinline__ void v2_commit(uint64_t *bar)
 {
     if constexpr (CG == 2) {
         asm volatile(
-            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
-            "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-            :: "r"(smem_u32(bar)), "h"((uint16_t)3), "r"(leader) : "memory");
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
     } else {
         asm volatile(
-            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-            "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-            :: "r"(smem_u32(bar)), "r"(leader) : "memory");
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+            :: "r"(smem_u32(bar)) : "memory");
     }
 }
 // (fp16 x fp16) -> f32, K-major A and B, M = 128 * CG, N = 64 * CG
@@ -322,9 +336,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA; warp-uniform, one elected lane issues)
         if (cta_rank == 0 && my_tiles > 0) {
-            const uint32_t leader = elect_one();
             const uint32_t idesc = v2_idesc<CG>();
-            const uint32_t ring_addr = smem_u32(op_ring);
+            // provably warp-uniform operands (a value loaded from shared memory is not, to the compiler:
+            // every UTCHMMA would be wrapped in an ELECT / R2UR.BROADCAST waterfall loop)
+            const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+            const uint32_t ring_addr = __shfl_sync(0xffffffffu, smem_u32(op_ring), 0);
             const bool dbg_on = P.dbg != nullptr && group == 0;
             const long long d_start = clock64();
             long long d_idle = 0;
@@ -378,9 +394,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t st = ring_addr + (uint32_t)(tt % S) * V2_STAGE_BYTES;
                     const uint32_t base_lo = ((st >> 4) & 0x3FFFu) | ((uint32_t)((UM_LBO >> 4) & 0x3FFF) << 16);
+                    if (mask == 15u) ++d_fast;
+                    if (elect_one_sync()) {
                     if (mask == 15u) {
                         // all four regions: 10 UMMAs per K step, A = h kept in the collector for 8 of them
-                        ++d_fast;
 #pragma unroll
                         for (int ks = 0; ks < UM_KT / 16; ++ks) {
                             const uint32_t off = ks * 2 * UM_LBO;
@@ -390,16 +407,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                             const uint32_t f1 = (ks == 0 && (firsts & 2u)) ? 0u : 1u;
                             const uint32_t f2 = (ks == 0 && (firsts & 4u)) ? 0u : 1u;
                             const uint32_t f3 = (ks == 0 && (firsts & 8u)) ? 0u : 1u;
-                            v2_mma<CG, 1>(tmem + 0 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off), idesc, f0, leader);
-                            v2_mma<CG, 2>(tmem + 0 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u, leader);
-                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, f1, leader);
-                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off + HB), idesc, 1u, leader);
-                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, f2, leader);
-                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u, leader);
-                            v2_mma<CG, 2>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off + HB), idesc, f3, leader);
-                            v2_mma<CG, 3>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off + HB), idesc, 1u, leader);
-                            v2_mma<CG, 1>(tmem + 0 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off), idesc, 1u, leader);
-                            v2_mma<CG, 3>(tmem + 1 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, 1u, leader);
+                            v2_mma<CG, 1>(tmem + 0 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off), idesc, f0);
+                            v2_mma<CG, 2>(tmem + 0 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u);
+                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, f1);
+                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off + HB), idesc, 1u);
+                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, f2);
+                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u);
+                            v2_mma<CG, 2>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off + HB), idesc, f3);
+                            v2_mma<CG, 3>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off + HB), idesc, 1u);
+                            v2_mma<CG, 1>(tmem + 0 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off), idesc, 1u);
+                            v2_mma<CG, 3>(tmem + 1 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, 1u);
                         }
                     } else {
                         // some regions only (one is being drained, or is catching up): no collector hints
@@ -415,29 +432,37 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                                 const uint32_t first = (ks == 0 && (firsts & (1u << q))) ? 0u : 1u;
                                 if (q < 2) {
                                     const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off + hb);
-                                    v2_mma<CG, 0>(d, dA, dB, idesc, first, leader);
-                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_BL * V2_TILE + off + hb), idesc, 1u, leader);
-                                    v2_mma<CG, 0>(d, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u, leader);
+                                    v2_mma<CG, 0>(d, dA, dB, idesc, first);
+                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_BL * V2_TILE + off + hb), idesc, 1u);
+                                    v2_mma<CG, 0>(d, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u);
                                 } else {
-                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AH * V2_TILE + off + hb), idesc, first, leader);
-                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AL * V2_TILE + off + hb), idesc, 1u, leader);
+                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AH * V2_TILE + off + hb), idesc, first);
+                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AL * V2_TILE + off + hb), idesc, 1u);
                                 }
                             }
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < V2_REGIONS; ++q) {
-                        if (!(mask & (1u << q))) continue;
-                        nt[q] = tt + 1;
-                        if (tt + 1 == nf[q] || tt + 1 == my_tiles) v2_commit<CG>(&ctl->acc_full[q], leader);
-                    }
+                    for (int q = 0; q < V2_REGIONS; ++q)
+                        if ((mask & (1u << q)) && (tt + 1 == nf[q] || tt + 1 == my_tiles))
+                            v2_commit<CG>(&ctl->acc_full[q]);
+                    }   // elected lane
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < V2_REGIONS; ++q)
+                        if (mask & (1u << q)) nt[q] = tt + 1;
                     if (mask != full_mask) break;    // re-evaluate from `released`: a deferred region comes first
                 }
                 int low = my_tiles;
 #pragma unroll
                 for (int q = 0; q < V2_REGIONS; ++q)
                     if (region_active(q) && nt[q] < low) low = nt[q];
-                for (; released < low; ++released) v2_commit<CG>(&ctl->empty[released % S], leader);
+                if (released < low) {
+                    if (elect_one_sync())
+                        for (int r = released; r < low; ++r) v2_commit<CG>(&ctl->empty[r % S]);
+                    __syncwarp();
+                    released = low;
+                }
                 if (!progressed) {
                     if (dbg_on) { const long long c = clock64(); __nanosleep(20); d_idle += clock64() - c; }
                     else __nanosleep(20);

@@ -101,7 +101,7 @@ def select_candidate_host(gathered, n_cand, cand_bytes):
 
 
 def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn, alloc_fn,
-                             group=None):
+                             group=None, pass_ring=False):
     """Rank-collective Gonzalez loop.
 
     seed_fn(cand)                      fill `cand` with the seed centre on the rank
@@ -111,6 +111,8 @@ def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn
                                        frame into `out`
     select_fn(gathered, n, out)        choose the winner among n gathered slots
     alloc_fn(n_bytes)                  zeroed uint8 buffer on the compute device
+    pass_ring                          also hand the ring of chosen centres to pass_fn
+                                       (pass_fn(center_cand, label, out, ring): the pruned RMSD pass)
 
     Returns the (k, cand_bytes) ring of chosen centres (slot i = centre i).
     """
@@ -130,7 +132,10 @@ def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn
     seed_fn(local)
     exchange(ring[0])
     for i in range(k):
-        pass_fn(ring[i], i, local)
+        if pass_ring:
+            pass_fn(ring[i], i, local, ring)
+        else:
+            pass_fn(ring[i], i, local)
         exchange(ring[i + 1])
     return ring
 
@@ -195,7 +200,8 @@ def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, tr
         return ids, distances, labels, ring
     if stats is not None:
         stats["passes"] = int(n_clusters)
-    st = K.KCentersState(data_local, metric, traces=traces, row_offset=row_offset)
+    st = K.KCentersState(data_local, metric, traces=traces, row_offset=row_offset,
+                         max_centres=int(n_clusters))
 
     def alloc(nbytes):
         return torch.zeros(int(nbytes), dtype=torch.uint8, device="cuda")
@@ -208,11 +214,11 @@ def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, tr
             cand.zero_()
             cand[:8].view(torch.float64)[0] = float("-inf")
 
-    def pass_fn(center_cand, label, out):
-        st.run_pass(center_cand, label, out_cand=out)
+    def pass_fn(center_cand, label, out, ring):
+        st.run_pass(center_cand, label, out_cand=out, ring=ring)
 
     ring = kcenters_fit_distributed(n_clusters, st.cand_bytes, seed_fn, pass_fn, st.select,
-                                    alloc, group=group)
+                                    alloc, group=group, pass_ring=True)
     k = int(n_clusters)
     ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
     return ids, st.distances, st.labels, ring

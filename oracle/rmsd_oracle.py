@@ -165,12 +165,37 @@ def inner_products_f32_sse(x, y):
     return ((lanes[0] + lanes[1]).astype(np.float32) + (lanes[2] + lanes[3]).astype(np.float32)).astype(np.float32)
 
 
+def _det3(a, b, c, d, e, f, g, h, i):
+    # (a (e i - f h) - b (d i - f g)) + c (d h - e g): plain Python floats, one IEEE rounding per operation
+    return (a * (e * i - f * h) - b * (d * i - f * g)) + c * (d * h - e * g)
+
+
 def msd_from_M_and_G(M, Ga, Gb, n_atoms, evalprec=1e-11):
-    """Published QCP Newton iteration (qcprot.c FastCalcRMSDAndRotation) in double on a given M."""
-    M = np.asarray(M, dtype=np.float64)
-    c2 = -2.0 * float((M * M).sum())
-    c1 = -8.0 * float(np.linalg.det(M))
-    c0 = float(np.linalg.det(key_matrix(M)))
+    """Published QCP Newton iteration (qcprot.c FastCalcRMSDAndRotation) in double on a given M.
+    Written operation by operation (no fused multiply-add, fixed order) so that
+    msmbuilder_b200/csrc/rmsd.cu:qcp_rmsd_strict can be compared with it bit for bit."""
+    m = [float(v) for v in np.asarray(M, dtype=np.float64).reshape(9)]
+    Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz = m
+    fro = 0.0
+    for v in m:
+        fro = fro + v * v
+    c2 = -2.0 * fro
+    c1 = -8.0 * _det3(Sxx, Sxy, Sxz, Syx, Syy, Syz, Szx, Szy, Szz)
+    k00 = (Sxx + Syy) + Szz
+    k01 = Syz - Szy
+    k02 = Szx - Sxz
+    k03 = Sxy - Syx
+    k11 = (Sxx - Syy) - Szz
+    k12 = Sxy + Syx
+    k13 = Szx + Sxz
+    k22 = (Syy - Sxx) - Szz
+    k23 = Syz + Szy
+    k33 = Szz - (Sxx + Syy)
+    d0 = _det3(k11, k12, k13, k12, k22, k23, k13, k23, k33)
+    d1 = _det3(k01, k12, k13, k02, k22, k23, k03, k23, k33)
+    d2 = _det3(k01, k11, k13, k02, k12, k23, k03, k13, k33)
+    d3 = _det3(k01, k11, k12, k02, k12, k22, k03, k13, k23)
+    c0 = ((k00 * d0 - k01 * d1) + k02 * d2) - k03 * d3
     e0 = 0.5 * (float(Ga) + float(Gb))
     lam = e0
     for _ in range(50):
@@ -178,10 +203,12 @@ def msd_from_M_and_G(M, Ga, Gb, n_atoms, evalprec=1e-11):
         x2 = lam * lam
         b = (x2 + c2) * lam
         a = b + c1
-        lam -= (a * lam + c0) / (2.0 * x2 * lam + b + a)
+        num = a * lam + c0
+        den = ((2.0 * x2) * lam + b) + a
+        lam = lam - num / den
         if abs(lam - old) < abs(evalprec * lam):
             break
-    return abs(2.0 * (e0 - lam) / n_atoms)
+    return abs((2.0 * (e0 - lam)) / float(n_atoms))
 
 
 def rmsd_theobald_f32(X, Y, GX, GY):

@@ -1,6 +1,11 @@
-"""GPU: metric='rmsd' (QCP kernels) vs the float64 oracle.  PARITY UNPINNED against
-the reference (mdtraj's libtheobald is absent): tolerance 1e-5 is what the
-reference's own RMSD tests accept (msmbuilder/tests/test_libdistance.py:155,163)."""
+"""GPU: metric='rmsd' (QCP kernels).  The arithmetic lives in mdtraj's libtheobald, absent here, so
+bit-level parity with the reference stays UNPINNED; what is pinned:
+  * the kernels agree BIT FOR BIT with oracle/rmsd_oracle.py:rmsd_theobald_f32, the restatement of
+    the published structure of that code (float32 M in SIMD order, double Newton of qcprot.c);
+  * the oracle and the kernels reproduce the known answer published with the method (qcprot main.c);
+  * against the float64 routes the difference is the float32 rounding of M: 1e-5 on the msd scale,
+    what the reference's own RMSD tests accept (msmbuilder/tests/test_libdistance.py:155,163);
+  * the pruned k-centers pass writes exactly what the plain pass writes."""
 import numpy as np
 import pytest
 
@@ -17,7 +22,7 @@ def assert_rmsd_close(got, ref, G_scale, n_atoms):
     the reference, libdistance.pyx:336-341), so the ERROR lives in msd: about
     6e-8 * (G_a + G_b) / n.  Near-zero distances therefore carry an absolute error
     of ~sqrt(that) (1e-4) in both implementations; compare squared distances."""
-    tol_msd = 4e-7 * G_scale / n_atoms
+    tol_msd = 2e-6 * G_scale / n_atoms
     np.testing.assert_allclose(np.asarray(got) ** 2, np.asarray(ref) ** 2, rtol=2e-5, atol=tol_msd)
 
 
@@ -62,3 +67,83 @@ def test_minibatch_kmedoids_rmsd_runs():
     # frames of one template share a label
     for t in range(4):
         assert len(set(lab[which == t])) == 1
+
+
+def _device_frames(c, G):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(c)).cuda(), torch.from_numpy(np.ascontiguousarray(G)).cuda()
+
+
+@pytest.mark.parametrize("n_atoms", [7, 20, 37, 100])
+def test_bit_for_bit_with_the_float32_restatement(n_atoms):
+    # oracle-centred frames and traces go straight to the kernels (C ABI): dist, assign and pdist
+    # must reproduce rmsd_theobald_f32 exactly -- same float32 sums of M, same double Newton steps
+    from msmbuilder_b200 import _kernels as K
+    xyz, _ = rmsd_conformations_numpy(70, n_atoms=n_atoms, n_templates=5, seed=10 + n_atoms)
+    c, G = ro.center_and_trace(xyz)
+    ref = ro.rmsd_theobald_f32(c, c[:6], G, G[:6]).astype(np.float64)
+    X, T = _device_frames(c, G)
+    for j in range(6):
+        got = K.rmsd_dist(X, T, X[j], float(G[j])).cpu().numpy()
+        np.testing.assert_array_equal(got, ref[:, j])
+    labels, mind, inertia = K.rmsd_assign_nearest(X, T, X[:6].contiguous(), T[:6].contiguous(),
+                                                  want_min_dist=True)
+    np.testing.assert_array_equal(labels.cpu().numpy(), ref.argmin(1))
+    np.testing.assert_array_equal(mind.cpu().numpy(), ref.min(1))
+    rows = np.array([3, 0, 5, 1])
+    got = K.rmsd_pdist(X, T, rows).cpu().numpy()
+    full = ro.rmsd_theobald_f32(c[rows], c[rows], G[rows], G[rows]).astype(np.float64)
+    np.testing.assert_array_equal(got, full[np.triu_indices(4, k=1)])
+
+
+def test_published_qcp_known_answer_on_the_device():
+    from msmbuilder_b200 import libdistance as ld
+    a = ro.QCPROT_FRAG_A.astype(np.float32)[None]
+    b = ro.QCPROT_FRAG_B.astype(np.float32)[None]
+    assert abs(float(ld.cdist(a, b, "rmsd")[0, 0]) - ro.QCPROT_RMSD) < 5e-6
+
+
+def test_pruned_pass_writes_what_the_plain_pass_writes(monkeypatch):
+    # k = 60 on 8 tight templates: from the ninth centre on almost every frame is ruled out by the
+    # triangle inequality; ids, labels and distances must not change by a bit
+    from msmbuilder_b200.cluster import KCenters
+    xyz, which = rmsd_conformations_numpy(6000, n_atoms=24, n_templates=8, seed=5, noise=0.03)
+    a = KCenters(n_clusters=60, metric="rmsd", random_state=3).fit([xyz[:2500], xyz[2500:]])
+    monkeypatch.setenv("MSMB200_RMSD_NO_PRUNE", "1")
+    b = KCenters(n_clusters=60, metric="rmsd", random_state=3).fit([xyz[:2500], xyz[2500:]])
+    assert a.cluster_ids_ == b.cluster_ids_
+    for x, y in zip(a.labels_, b.labels_):
+        np.testing.assert_array_equal(x, y)
+    for x, y in zip(a.distances_, b.distances_):
+        np.testing.assert_array_equal(x, y)
+    assert len(set(a.cluster_ids_)) == 60
+
+
+def test_kcenters_rmsd_vs_float32_oracle_loop():
+    # the reference's loop (kcenters.py:79-102) driven by the float32 restatement: same centres,
+    # labels and distances, bit for bit
+    from sklearn.utils import check_random_state
+    from msmbuilder_b200.cluster import KCenters
+    from msmbuilder_b200 import _kernels as K
+    import torch
+    xyz, which = rmsd_conformations_numpy(400, n_atoms=16, n_templates=5, seed=6, noise=0.05)
+    m = KCenters(n_clusters=12, metric="rmsd", random_state=1).fit([xyz])
+    # centre on the device the way the estimator does, then run the reference loop on those frames
+    X = torch.from_numpy(xyz.copy()).cuda()
+    T = K.rmsd_center(X)
+    c, G = X.cpu().numpy(), T.cpu().numpy()
+    n = len(c)
+    nxt = check_random_state(1).randint(0, n)
+    labels = np.zeros(n, dtype=int)
+    distances = np.full(n, np.inf)
+    ids = []
+    for i in range(12):
+        d = ro.rmsd_theobald_f32(c, c[nxt:nxt + 1], G, G[nxt:nxt + 1])[:, 0].astype(np.float64)
+        closer = d < distances
+        distances[closer] = d[closer]
+        labels[closer] = i
+        ids.append(int(nxt))
+        nxt = int(np.argmax(distances))
+    assert m.cluster_ids_ == ids
+    np.testing.assert_array_equal(m.labels_[0], labels)
+    np.testing.assert_array_equal(m.distances_[0], distances)

@@ -237,10 +237,11 @@ def test_umma_f16_engine_feature_scales():
 
 
 def test_umma_f16_engine_range_rescue():
-    # an excursion 10^7 times the spread of the shift/scale sample leaves fp16's range: the call
-    # must redo itself with the bf16 engine on the stream and still match float64.  The sample is
-    # frame floor(j * 8000 / 1024) of the concatenated call (tica_shift_kernel), so the excursions
-    # sit on frames between two sample points (global 7001..7005 and 7501).
+    # an excursion 10^7 times the spread of the shift/scale sample: beyond 2^6 times the sample's
+    # largest magnitude the converters raise the range flag and the call redoes itself with the
+    # float64 engine on the stream (no host round trip).  The sample is frame floor(j * 8000 / 1024)
+    # of the concatenated call (host side of tica_umma_accumulate), so the excursions sit on frames
+    # between two sample points (global 7001..7005 and 7501).
     seqs = ar1_numpy(2, 4000, 256, seed=26)
     seqs[1] = seqs[1].copy()
     sampled = {(j * 8000) // 1024 for j in range(1024)}
@@ -248,15 +249,22 @@ def test_umma_f16_engine_range_rescue():
     seqs[1][3001:3006, 5] += 3.0e7
     seqs[1][3501, 200] = -8.0e6
     a, b = _umma_vs_simt(seqs, 10, engine="umma_3xf16")
-    c = _umma_vs_simt(seqs, 10, engine="umma_6xbf16")[1]
     assert a.n_observations_ == b.n_observations_
-    # the rescue IS the 6xBF16 engine: same accumulators (up to the order of the column-sum atomics)
-    np.testing.assert_allclose(b._outer_0_to_T_lagged, c._outer_0_to_T_lagged, rtol=1e-12)
-    np.testing.assert_allclose(b._outer_0_to_TminusTau, c._outer_0_to_TminusTau, rtol=1e-12)
-    _assert_moments_close(b, a, 5e-6)
+    # the rescue IS the float64 engine: same accumulators up to the order of its atomic adds
+    for name in ("_outer_0_to_T_lagged", "_outer_0_to_TminusTau", "_outer_offset_to_T",
+                 "_sum_0_to_TminusTau", "_sum_tau_to_T", "_sum_0_to_T"):
+        np.testing.assert_allclose(getattr(b, name), getattr(a, name), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(b.eigenvalues_, a.eigenvalues_, rtol=0, atol=1e-9)
+    # a milder outlier (100 x the sample's range) takes the same exact route
+    seqs2 = ar1_numpy(2, 4000, 256, seed=28)
+    seqs2[0] = seqs2[0].copy()
+    seqs2[0][3, ::4] += 400.0
+    a2, b2 = _umma_vs_simt(seqs2, 10, engine="umma_3xf16")
+    np.testing.assert_allclose(b2.eigenvalues_, a2.eigenvalues_, rtol=0, atol=1e-9)
     # and the next call on the same estimator is clean again (flag is per call)
     d = _umma_vs_simt(seqs[:1], 10, engine="umma_3xf16")
     _assert_moments_close(d[1], d[0], 5e-6)
+    assert np.abs(d[1].eigenvalues_ - d[0].eigenvalues_).max() > 0     # the tensor-core engine again
 
 
 @pytest.mark.parametrize("engine", ["umma_3xf16", "umma_6xbf16"])

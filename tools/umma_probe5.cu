@@ -69,7 +69,13 @@ rate_kernel(int N, int variant, int n_iter, long long *cycles)
     if (CG == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
-    if (cta_rank == 0 && tid == 32) {
+    uint32_t elected = 0;
+    if (cta_rank == 0 && warp == 1) {
+        uint32_t laneid = 0;
+        asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}"
+                     : "+r"(laneid), "+r"(elected) : "r"(0xFFFFFFFFu));
+    }
+    if (elected) {
         const uint32_t idesc = make_idesc(128 * CG, N);
         const uint32_t base = smem_u32(ops);
         const int n_acc = variant == 0 ? 1 : 512 / N;
@@ -112,7 +118,7 @@ rate_kernel(int N, int variant, int n_iter, long long *cycles)
         long long t1 = clock64();
         if (blockIdx.x == 0) cycles[0] = t1 - t0;
     }
-    if (!(cta_rank == 0 && tid == 32)) mbar_wait(&bars[0], 0);
+    if (!elected) mbar_wait(&bars[0], 0);
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (CG == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
