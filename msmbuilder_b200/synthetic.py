@@ -120,12 +120,18 @@ def rmsd_conformations_numpy(n_frames, n_atoms=100, n_templates=20, seed=0, nois
     return xyz.astype(np.float32), which
 
 
-def rmsd_conformations_device(n_frames, n_atoms=100, n_templates=2000, seed=0, noise=0.05):
+def rmsd_conformations_device(n_frames, n_atoms=100, n_templates=2000, seed=0, noise=0.05,
+                              templates=None):
+    """Device twin of rmsd_conformations_numpy.  `templates` (n_templates, n_atoms, 3): reuse one
+    template bank for several calls (chunks of one data set, each with its own `seed`)."""
     import torch
     dev = torch.device("cuda")
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    templates = torch.randn((n_templates, n_atoms, 3), generator=g, device=dev) * 0.3
+    if templates is None:
+        templates = torch.randn((n_templates, n_atoms, 3), generator=g, device=dev) * 0.3
+    else:
+        n_templates = int(templates.shape[0])
     which = torch.randint(0, n_templates, (n_frames,), generator=g, device=dev)
     xyz = templates[which] + torch.randn((n_frames, n_atoms, 3), generator=g, device=dev) * noise
     q = torch.randn((n_frames, 4), generator=g, device=dev)

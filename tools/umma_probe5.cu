@@ -25,6 +25,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
     d |= (uint64_t)1 << 46;
     return d;
 }
+// K-major SWIZZLE_128B: rows of 128 bytes (64 fp16 along K), 8-row atoms of 1024 bytes
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((16 >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __host__ __device__ inline uint32_t make_idesc(int M, int N)
 {
     uint32_t d = 0;
@@ -78,8 +89,12 @@ rate_kernel(int N, int variant, int n_iter, long long *cycles)
     if (elected) {
         const uint32_t idesc = make_idesc(128 * CG, N);
         const uint32_t base = smem_u32(ops);
-        const int n_acc = variant == 0 ? 1 : 512 / N;
-        const uint64_t dA = make_desc(base), dA2 = make_desc(base + TILE);
+        const int n_acc = (variant == 0 || variant == 3) ? 1 : 512 / N;
+        const bool sw = variant == 3;
+        // SWIZZLE_128B tiles: 128 rows x 128 B = 16 KB each (A at 0, A2 at 16 KB, B at 32 KB; the three
+        // "tiles" of the no-swizzle variants alias the same memory, contents do not matter here)
+        const uint64_t dA = sw ? make_desc_sw128(base) : make_desc(base);
+        const uint64_t dA2 = sw ? make_desc_sw128(base + 32) : make_desc(base + TILE);
         long long t0 = clock64();
         for (int it = 0; it < n_iter; ++it) {
             // 8 MMAs per iteration: two groups of four that share A
@@ -90,7 +105,8 @@ rate_kernel(int N, int variant, int n_iter, long long *cycles)
                 for (int j = 0; j < 4; ++j) {
                     const int m = g * 4 + j;
                     const uint32_t d = tmem + (uint32_t)((m % n_acc) * N);
-                    const uint64_t db = make_desc(base + (2 + (j % 3)) * TILE + (j & 1) * 4096);
+                    const uint64_t db = sw ? make_desc_sw128(base + 16384 + (j & 3) * 32)
+                                           : make_desc(base + (2 + (j % 3)) * TILE + (j & 1) * 4096);
                     const uint32_t acc = it ? 1u : 0u;
                     if (CG == 2) {
                         if (variant == 2) {
@@ -147,7 +163,8 @@ static void run(int N, int variant, int grid, long long *d_cyc)
     CK(cudaMemcpy(&c, d_cyc, sizeof(c), cudaMemcpyDeviceToHost));
     const double ideal = 128.0 * N / 256.0;
     printf("cta_group::%d M=%d N=%3d %-28s grid %3d: %.1f cycles/MMA (ideal %.0f)\n", CG, 128 * CG, N,
-           variant == 0 ? "one accumulator" : variant == 1 ? "round-robin accumulators" : "round robin + A collector",
+           variant == 0 ? "one accumulator" : variant == 1 ? "round-robin accumulators"
+           : variant == 2 ? "round robin + A collector" : "one accumulator, SWIZZLE_128B",
            grid, (double)c / (n_iter * 8.0), ideal);
 }
 
@@ -159,7 +176,8 @@ int main()
     CK(cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * TILE + 1024));
     const int Ns[3] = {256, 128, 64};
     for (int n = 0; n < 3; ++n)
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < 4; ++v) {
+            if (v == 1) continue;
             run<2>(Ns[n], v, 2, d_cyc);
             run<1>(Ns[n], v, 1, d_cyc);
         }
