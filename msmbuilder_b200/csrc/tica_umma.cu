@@ -1332,7 +1332,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (tiles < n_groups) n_groups = (int)(tiles > 0 ? tiles : 1);
     const size_t DD = (size_t)UM_D * UM_D;          // scratch is always 256 wide
     const size_t v1_part_bytes = (sizeof(double) + sizeof(float)) * 2 * DD * n_pairs;
-    const size_t v2_per_cta = (size_t)V2_REGIONS * (64 * v2_cg) * UM_F;            // floats per array
+    const size_t v2_per_cta = (size_t)V2_REGIONS * (128 * v2_cg) * UM_F;           // floats per array
     const size_t v2_part_bytes = v2 ? 3 * sizeof(float) * v2_per_cta * (size_t)(n_groups * v2_cg) : 0;
     const size_t part_bytes = v2 ? v2_part_bytes : v1_part_bytes;
     const size_t need = ws_fixed_bytes(UM_D) + part_bytes;

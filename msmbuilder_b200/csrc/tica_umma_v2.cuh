@@ -9,25 +9,27 @@
 //    accumulated and C_00 = G + G^T (= h h^T + h l^T + l h^T) is formed by the finalize kernel.
 //    C_tau keeps its three products h b^T + h bl^T + l b^T.  Operand tiles per stage:
 //    a = h, al = l, ah = h / 2 (exact), b, bl  (8 KB each, K-major, no swizzle).
-//  * The drain is hidden.  TMEM holds FOUR accumulator regions (C_tau | G) x (column half 0 | 1);
-//    every UMMA is M x (N = RW) into one region.  The regions' slab boundaries are staggered by a
-//    quarter slab, so at most one region is being drained at a time; its MMAs are deferred (the
-//    operand ring is 4 deep) while the tensor pipe keeps working on the other three, and the region
-//    catches up as soon as its accumulators have been read out.
-//  * Dedicated drain warps (4: one per TMEM lane quarter), so the converters never stop:
-//    tcgen05.ld -> fire-and-forget red.global.add.f32 into this CTA's float32 level (L2 resident);
-//    the region is released as soon as its last column chunk is in registers.  After every drain the
-//    warp moves ONE 16-column group of the region from the float32 level into a float-float (hi, lo)
-//    pair with an error-free TwoSum (round robin: a group is folded every RW/16 slabs), so the float32
-//    level never sums more than RW/16 slabs and no drain event takes long.  The finalize path adds
-//    hi + lo + level in float64.  No FP64 instruction runs in this kernel while the tensor pipe is
-//    busy (FP64 issued under a busy tensor pipe stalls for hundreds of cycles, profiles/r1_k1_issue.txt).
+//  * The drain is hidden.  TMEM holds TWO accumulator regions, C_tau and G (N columns each: every UMMA
+//    is the full M x N, the only shape that amortises the ~40 cycles a tcgen05.mma costs on top of
+//    N / 2, profiles/r2d_probe5_mma_shapes.log).  Their slab boundaries are half a slab apart, so
+//    at most one region is being drained at a time; its MMAs are deferred (the operand ring is 4
+//    deep) while the tensor pipe keeps working on the other one, and the region catches up as soon
+//    as its accumulators have been read out.
+//  * Dedicated drain warps (8: two per TMEM lane quarter, half of a region's columns each), so the
+//    converters never stop: tcgen05.ld of 64 columns at a time -> fire-and-forget
+//    red.global.add.f32 into this CTA's float32 level (L2 resident); the region is released as soon
+//    as its last columns are in registers.  After every drain the warp moves ONE 16-column group
+//    from the float32 level into a float-float (hi, lo) pair with an error-free TwoSum (round
+//    robin: a group is folded every 8 (4) slabs), so the float32 level never sums more than that
+//    and no drain event takes long.  The finalize path adds hi + lo + level in float64.  No FP64
+//    instruction runs in this kernel while the tensor pipe is busy (it stalls for hundreds of
+//    cycles there, profiles/r1_k1_issue.txt).
 //  * Converters: a thread owns one feature and the 8 frames of one K chunk of one operand; packed
 //    f32x2 math (FFMA2 / FADD2 of sm_100), h = cvt.rn.f16x2, l = fp16(x' - h): ~40 instructions per
 //    8 values instead of ~70.  Only the feature blocks that exist are converted (D < 128 per CTA).
-//  * template <CG>: CG = 2 is the CTA-pair kernel (cta_group::2, M = 256, D in (128, 256]);
-//    CG = 1 is the single-CTA kernel for D <= 128 (cta_group::1, M = 128, regions of 64 columns,
-//    148 independent CTAs): narrow inputs no longer pay 256-wide tiles (config 2, 10M x 64).
+//  * template <CG>: CG = 2 is the CTA-pair kernel (cta_group::2, M = 256, N = 256, D in (128, 256]);
+//    CG = 1 is the single-CTA kernel for D <= 128 (cta_group::1, M = 128, N = 128 or 64, 148
+//    independent CTAs): narrow inputs no longer pay 256-wide tiles (config 2, 10M x 64).
 //  * Bit-reproducible like v1: every address has one writer, all sums are taken in a fixed order.
 #pragma once
 
@@ -38,16 +40,16 @@ constexpr int V2_NTILES = 5;                        // a, al, ah, b, bl
 constexpr int V2_STAGE_BYTES = V2_NTILES * V2_TILE; // 40 KB
 constexpr int V2_RAW_STAGES = 2;
 constexpr int V2_OP_STAGES = 4;
-constexpr int V2_CONV_WARPS = 16;
-constexpr int V2_DRAIN_WARPS = 4;
-// w0 TMA producer (+ TMEM allocation), w1 MMA issuer, w2-3 idle, w4-19 converters, w20-23 drain.
-// Registers are allocated to warps in groups of 4, so 22 warps would cost as much as 24: 768 threads
-// at 80 registers (the issuer and the converters do not spill at 80; the drain warps' fold does, into L1).
+constexpr int V2_CONV_WARPS = 8;
+constexpr int V2_DRAIN_WARPS = 8;
+constexpr int V2_UNITS_PER_WARP = 4;                // 8 * 4 feature blocks = 32 units per tile at most
+// w0 TMA producer (+ TMEM allocation), w1 MMA issuer, w2-3 idle, w4-11 converters, w12-19 drain.
+// Registers are allocated to warps in groups of 4: 20 warps = 640 threads at 96 registers.
 constexpr int V2_FIRST_CONV_WARP = 4;
-constexpr int V2_FIRST_DRAIN_WARP = V2_FIRST_CONV_WARP + V2_CONV_WARPS;   // 20..23: four distinct lane quarters
-constexpr int V2_THREADS = 32 * (V2_FIRST_DRAIN_WARP + V2_DRAIN_WARPS);   // 768
+constexpr int V2_FIRST_DRAIN_WARP = V2_FIRST_CONV_WARP + V2_CONV_WARPS;   // 12..19: two warps per lane quarter
+constexpr int V2_THREADS = 32 * (V2_FIRST_DRAIN_WARP + V2_DRAIN_WARPS);   // 640
 constexpr int V2_CONV_TID0 = 32 * V2_FIRST_CONV_WARP;
-constexpr int V2_REGIONS = 4;                       // (C_tau, G) x (column half 0, 1)
+constexpr int V2_REGIONS = 2;                       // C_tau, G
 constexpr int V2_T_A = 0, V2_T_AL = 1, V2_T_AH = 2, V2_T_B = 3, V2_T_BL = 4;
 constexpr int V2_MAX_GROUPS = 192;                  // CTA pairs (CG = 2) or CTAs (CG = 1)
 constexpr uint32_t V2_RANGE_LIMIT = 0x5400u;        // fp16 bit pattern of 64.0 = 2^6
@@ -66,7 +68,7 @@ struct V2Params {
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
     int *overflow;                // set to 1 when a scaled value reached 2^6 (or was not finite): float64 rescue
-    float *lvl1;                  // [n_ctas][4][RW][128] float32 level (red.add target)
+    float *lvl1;                  // [n_ctas][2][RW][128] float32 level (red.add target), RW = 128 * CG
     float *hi, *lo;               // same shape: float-float second level
     double *sums;                 // [n_groups][UM_D] column sums of x' (unscaled)
     long long *dbg;
@@ -78,7 +80,7 @@ struct V2Smem {
     uint64_t conv[V2_OP_STAGES];       // leader's copy is used; CG arrivals
     uint64_t empty[V2_OP_STAGES];      // local; one commit arrival
     uint64_t acc_full[V2_REGIONS];     // local; one commit arrival
-    uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 4 * CG arrivals
+    uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 8 * CG arrivals
     uint32_t tmem_base;
     int valid_rows[V2_RAW_STAGES];
     float sc[UM_F];                    // this CTA's per-feature scale and -shift * scale
@@ -153,13 +155,13 @@ __device__ __forceinline__ void v2_commit(uint64_t *bar)
             :: "r"(smem_u32(bar)) : "memory");
     }
 }
-// (fp16 x fp16) -> f32, K-major A and B, M = 128 * CG, N = 64 * CG
+// (fp16 x fp16) -> f32, K-major A and B, M = 128 * CG, N = n_cols
 template <int CG>
-__device__ __forceinline__ uint32_t v2_idesc()
+__device__ __forceinline__ uint32_t v2_idesc(int n_cols)
 {
     uint32_t d = 0;
     d |= 1u << 4;                                   // D format F32; A, B format F16 = 0
-    d |= (uint32_t)((64 * CG) >> 3) << 17;          // N
+    d |= (uint32_t)(n_cols >> 3) << 17;             // N
     d |= (uint32_t)((128 * CG) >> 4) << 24;         // M
     return d;
 }
@@ -221,10 +223,11 @@ __device__ __forceinline__ uint64_t h2_to_f2(uint32_t h)
 template <int CG>
 __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Params P)
 {
-    constexpr int RW = 64 * CG;                      // columns of a region = N of every UMMA
+    constexpr int RW = 128 * CG;                     // columns reserved per region (N <= RW)
     constexpr int TMEM_COLS = V2_REGIONS * RW;       // 512 (CG = 2) or 256 (CG = 1)
     constexpr int S = V2_OP_STAGES;
-    constexpr int NG = RW / 16;                      // 16-column fold groups of a region
+    constexpr int CW = RW / 2;                       // columns of a region one drain warp owns
+    constexpr int NG = CW / 16;                      // its 16-column fold groups
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *ring = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -248,15 +251,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     int d_local = P.D - UM_F * (int)cta_rank;
     d_local = d_local < 0 ? 0 : (d_local > UM_F ? UM_F : d_local);
     const int nfb = d_local / 32;
-    // column halves in use: the upper half only exists when some CTA has more than 64 features
-    const int n_halves = (CG == 2 || P.D > 64) ? 2 : 1;
+    // N of every UMMA: all the columns the group has (a single CTA with <= 64 features runs N = 64)
+    const int n_cols = CG == 2 ? 256 : (P.D > 64 ? 128 : 64);
     // slab boundaries: staggered across groups (so the drains of the whole chip do not coincide)
-    // and by a quarter slab across the four regions of a group
+    // and by half a slab between the two regions of a group
     const int slab_off = (int)(((long long)group * ST) / P.n_groups);
     auto region_off = [&](int q) { return (slab_off + (q * ST) / V2_REGIONS) % ST; };
-    auto slab_first = [&](int q, int t) { return t == 0 || ((t + region_off(q)) % ST) == 0; };
-    auto slab_last = [&](int q, int t) { return ((t + region_off(q) + 1) % ST) == 0 || t + 1 == my_tiles; };
-    auto region_active = [&](int q) { return (q & 1) < n_halves; };
 
     if (tid == 0) {
         for (int s = 0; s < V2_RAW_STAGES; ++s) {
@@ -336,9 +336,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA; warp-uniform, one elected lane issues)
         if (cta_rank == 0 && my_tiles > 0) {
-            const uint32_t idesc = v2_idesc<CG>();
-            // provably warp-uniform operands (a value loaded from shared memory is not, to the compiler:
-            // every UTCHMMA would be wrapped in an ELECT / R2UR.BROADCAST waterfall loop)
+            const uint32_t idesc = v2_idesc<CG>(n_cols);
+            // provably warp-uniform operands (a value loaded from shared memory is not, to the compiler)
             const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
             const uint32_t ring_addr = __shfl_sync(0xffffffffu, smem_u32(op_ring), 0);
             const bool dbg_on = P.dbg != nullptr && group == 0;
@@ -350,10 +349,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             uint32_t acc_ph = 0;                     // phase bit of acc_empty[q] in bit q
 #pragma unroll
             for (int q = 0; q < V2_REGIONS; ++q) {
-                nt[q] = region_active(q) ? 0 : my_tiles;
+                nt[q] = 0;
                 nf[q] = ST - region_off(q);
             }
-            const uint32_t full_mask = n_halves == 2 ? 15u : 5u;
             // descriptor of (tile, byte offset) in the stage whose low word is `base_lo`: only the
             // 14-bit start-address field changes (shared addresses stay below 2^18: no carry)
             auto desc = [](uint32_t base_lo, uint32_t byte_off) -> uint64_t {
@@ -362,7 +360,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     : "r"(base_lo + (byte_off >> 4)), "r"((uint32_t)((UM_SBO >> 4) | (1u << 14))));
                 return d;
             };
-            constexpr uint32_t HB = 64 * 16;         // byte offset of the upper column half in a B tile
             int conv_done = 0;                       // tiles whose conversion has been observed
             int released = 0;                        // tiles whose operand stage has been handed back
             while (released < my_tiles) {
@@ -394,69 +391,55 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     const uint32_t st = ring_addr + (uint32_t)(tt % S) * V2_STAGE_BYTES;
                     const uint32_t base_lo = ((st >> 4) & 0x3FFFu) | ((uint32_t)((UM_LBO >> 4) & 0x3FFF) << 16);
-                    if (mask == 15u) ++d_fast;
+                    if (mask == 3u) ++d_fast;
                     if (elect_one_sync()) {
-                    if (mask == 15u) {
-                        // all four regions: 10 UMMAs per K step, A = h kept in the collector for 8 of them
+                        const uint32_t f0 = (firsts & 1u) ? 0u : 1u, f1 = (firsts & 2u) ? 0u : 1u;
+                        if (mask == 3u) {
+                            // both regions: 5 UMMAs per K step, A = h kept in the collector for 4 of them
 #pragma unroll
-                        for (int ks = 0; ks < UM_KT / 16; ++ks) {
-                            const uint32_t off = ks * 2 * UM_LBO;
-                            const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
-                            const uint64_t dAl = desc(base_lo, V2_T_AL * V2_TILE + off);
-                            const uint32_t f0 = (ks == 0 && (firsts & 1u)) ? 0u : 1u;
-                            const uint32_t f1 = (ks == 0 && (firsts & 2u)) ? 0u : 1u;
-                            const uint32_t f2 = (ks == 0 && (firsts & 4u)) ? 0u : 1u;
-                            const uint32_t f3 = (ks == 0 && (firsts & 8u)) ? 0u : 1u;
-                            v2_mma<CG, 1>(tmem + 0 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off), idesc, f0);
-                            v2_mma<CG, 2>(tmem + 0 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u);
-                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, f1);
-                            v2_mma<CG, 2>(tmem + 1 * RW, dA, desc(base_lo, V2_T_BL * V2_TILE + off + HB), idesc, 1u);
-                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, f2);
-                            v2_mma<CG, 2>(tmem + 2 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u);
-                            v2_mma<CG, 2>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off + HB), idesc, f3);
-                            v2_mma<CG, 3>(tmem + 3 * RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off + HB), idesc, 1u);
-                            v2_mma<CG, 1>(tmem + 0 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off), idesc, 1u);
-                            v2_mma<CG, 3>(tmem + 1 * RW, dAl, desc(base_lo, V2_T_B * V2_TILE + off + HB), idesc, 1u);
-                        }
-                    } else {
-                        // some regions only (one is being drained, or is catching up): no collector hints
+                            for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                                const uint32_t off = ks * 2 * UM_LBO;
+                                const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
+                                const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off);
+                                v2_mma<CG, 1>(tmem, dA, dB, idesc, ks == 0 ? f0 : 1u);
+                                v2_mma<CG, 2>(tmem, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u);
+                                v2_mma<CG, 2>(tmem + RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, ks == 0 ? f1 : 1u);
+                                v2_mma<CG, 3>(tmem + RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u);
+                                v2_mma<CG, 0>(tmem, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u);
+                            }
+                        } else if (mask == 1u) {
+                            // C_tau alone (G is being drained, or C_tau is catching up)
 #pragma unroll
-                        for (int ks = 0; ks < UM_KT / 16; ++ks) {
-                            const uint32_t off = ks * 2 * UM_LBO;
-                            const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
+                            for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                                const uint32_t off = ks * 2 * UM_LBO;
+                                const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
+                                const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off);
+                                v2_mma<CG, 1>(tmem, dA, dB, idesc, ks == 0 ? f0 : 1u);
+                                v2_mma<CG, 3>(tmem, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u);
+                                v2_mma<CG, 0>(tmem, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u);
+                            }
+                        } else {
+                            // G alone
 #pragma unroll
-                            for (int q = 0; q < V2_REGIONS; ++q) {
-                                if (!(mask & (1u << q))) continue;
-                                const uint32_t hb = (uint32_t)(q & 1) * HB;
-                                const uint32_t d = tmem + (uint32_t)(RW * q);
-                                const uint32_t first = (ks == 0 && (firsts & (1u << q))) ? 0u : 1u;
-                                if (q < 2) {
-                                    const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off + hb);
-                                    v2_mma<CG, 0>(d, dA, dB, idesc, first);
-                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_BL * V2_TILE + off + hb), idesc, 1u);
-                                    v2_mma<CG, 0>(d, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u);
-                                } else {
-                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AH * V2_TILE + off + hb), idesc, first);
-                                    v2_mma<CG, 0>(d, dA, desc(base_lo, V2_T_AL * V2_TILE + off + hb), idesc, 1u);
-                                }
+                            for (int ks = 0; ks < UM_KT / 16; ++ks) {
+                                const uint32_t off = ks * 2 * UM_LBO;
+                                const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
+                                v2_mma<CG, 1>(tmem + RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, ks == 0 ? f1 : 1u);
+                                v2_mma<CG, 3>(tmem + RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u);
                             }
                         }
-                    }
 #pragma unroll
-                    for (int q = 0; q < V2_REGIONS; ++q)
-                        if ((mask & (1u << q)) && (tt + 1 == nf[q] || tt + 1 == my_tiles))
-                            v2_commit<CG>(&ctl->acc_full[q]);
+                        for (int q = 0; q < V2_REGIONS; ++q)
+                            if ((mask & (1u << q)) && (tt + 1 == nf[q] || tt + 1 == my_tiles))
+                                v2_commit<CG>(&ctl->acc_full[q]);
                     }   // elected lane
                     __syncwarp();
 #pragma unroll
                     for (int q = 0; q < V2_REGIONS; ++q)
                         if (mask & (1u << q)) nt[q] = tt + 1;
-                    if (mask != full_mask) break;    // re-evaluate from `released`: a deferred region comes first
+                    if (mask != 3u) break;           // re-evaluate from `released`: a deferred region comes first
                 }
-                int low = my_tiles;
-#pragma unroll
-                for (int q = 0; q < V2_REGIONS; ++q)
-                    if (region_active(q) && nt[q] < low) low = nt[q];
+                const int low = nt[0] < nt[1] ? nt[0] : nt[1];
                 if (released < low) {
                     if (elect_one_sync())
                         for (int r = released; r < low; ++r) v2_commit<CG>(&ctl->empty[r % S]);
@@ -485,19 +468,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         // this is the transpose), centres / scales / splits them and stores 16-byte K-major chunks
         // (512 contiguous bytes per warp store).
         const int cw = warp - V2_FIRST_CONV_WARP;
+        constexpr int U = V2_UNITS_PER_WARP;
         const int n_units = 8 * nfb;
-        int u_op[2], u_kq[2], u_fl[2];
-        float u_sc[2], u_nsh[2];
-        bool u_on[2];
-        uint32_t u_src[2], u_dst[2];       // byte offsets of the unit inside a raw stage / an operand stage
+        int u_kq[U], u_fl[U];
+        float u_sc[U], u_nsh[U];
+        bool u_on[U], u_a[U];              // unit exists / belongs to operand 0 (the unlagged frames)
+        uint32_t u_src[U], u_dst[U];       // byte offsets of the unit inside a raw stage / an operand stage
         const int chunk = lane >> 2, within = (lane & 3) * 4;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int u = cw + 16 * k;
+        for (int k = 0; k < U; ++k) {
+            const int u = cw + V2_CONV_WARPS * k;
             u_on[k] = u < n_units;
             const int uu = u_on[k] ? u : 0;
             const int nf = nfb > 0 ? nfb : 1;
-            u_op[k] = uu / (4 * nf);
+            const int op = uu / (4 * nf);
+            u_a[k] = op == 0;
             u_kq[k] = (uu / nf) & 3;
             u_fl[k] = 32 * (uu % nf) + lane;
             u_sc[k] = ctl->sc[u_fl[k]];
@@ -505,12 +490,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             // raw tile of block fb: [frame][128 B], 16-byte chunks XOR-swizzled by frame & 7.  Frame
             // 8 kq + i sits at  base + i * 128  with the chunk bits flipped by i: one XOR with an
             // immediate per load, the row offset folds into the instruction
-            u_src[k] = (uint32_t)(u_op[k] * UM_TILE_BYTES + (u_fl[k] >> 5) * (UM_KT * 128)
+            u_src[k] = (uint32_t)(op * UM_TILE_BYTES + (u_fl[k] >> 5) * (UM_KT * 128)
                                   + u_kq[k] * 1024 + (chunk << 4) + within);
-            u_dst[k] = (uint32_t)((u_op[k] == 0 ? V2_T_A : V2_T_B) * V2_TILE + u_fl[k] * 16 + u_kq[k] * UM_LBO);
+            u_dst[k] = (uint32_t)((op == 0 ? V2_T_A : V2_T_B) * V2_TILE + u_fl[k] * 16 + u_kq[k] * UM_LBO);
         }
         const uint32_t raw_s = smem_u32(raw_ring), op_s = smem_u32(op_ring);
-        float sAh[2] = {0.f, 0.f}, sAl[2] = {0.f, 0.f};   // column sums (operand 0 units) as float pairs
+        float sAh[U], sAl[U];                            // column sums (operand 0 units) as float pairs
+#pragma unroll
+        for (int k = 0; k < U; ++k) sAh[k] = sAl[k] = 0.f;
         uint32_t hmax = 0;                               // largest |h| seen, as two fp16 bit patterns
         int stage = 0, ostage = 0;
         uint32_t phase = 0, ophase = 0;
@@ -527,76 +514,85 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
             auto convert_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
-                float v[2][8];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (!u_on[k]) continue;
-                    const uint32_t b = rawst + u_src[k];
-                    v[k][0] = lds_f32<0 * 128>(b);
-                    v[k][1] = lds_f32<1 * 128>(b ^ (1u << 4));
-                    v[k][2] = lds_f32<2 * 128>(b ^ (2u << 4));
-                    v[k][3] = lds_f32<3 * 128>(b ^ (3u << 4));
-                    v[k][4] = lds_f32<4 * 128>(b ^ (4u << 4));
-                    v[k][5] = lds_f32<5 * 128>(b ^ (5u << 4));
-                    v[k][6] = lds_f32<6 * 128>(b ^ (6u << 4));
-                    v[k][7] = lds_f32<7 * 128>(b ^ (7u << 4));
-                }
+                for (int k0 = 0; k0 < U; k0 += 2) {
+                    // two units at a time: 16 loads in flight, then the arithmetic
+                    float v[2][8];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    if (!u_on[k]) continue;
-                    const uint64_t sc2 = f2_pack(u_sc[k], u_sc[k]);
-                    const uint64_t nsh2 = f2_pack(u_nsh[k], u_nsh[k]);
-                    uint32_t hw[4], lw[4];
-                    uint64_t sum2 = 0ull;                           // (+0.f, +0.f)
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int k = k0 + kk;
+                        if (!u_on[k]) continue;
+                        const uint32_t b = rawst + u_src[k];
+                        v[kk][0] = lds_f32<0 * 128>(b);
+                        v[kk][1] = lds_f32<1 * 128>(b ^ (1u << 4));
+                        v[kk][2] = lds_f32<2 * 128>(b ^ (2u << 4));
+                        v[kk][3] = lds_f32<3 * 128>(b ^ (3u << 4));
+                        v[kk][4] = lds_f32<4 * 128>(b ^ (4u << 4));
+                        v[kk][5] = lds_f32<5 * 128>(b ^ (5u << 4));
+                        v[kk][6] = lds_f32<6 * 128>(b ^ (6u << 4));
+                        v[kk][7] = lds_f32<7 * 128>(b ^ (7u << 4));
+                    }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        // (v - shift) * scale in one rounding: the scale is a power of two, so this is
-                        // exactly scale * fl32(v - shift), the x' of the float64 edge kernel
-                        uint64_t as2 = f2_fma(f2_pack(v[k][2 * i], v[k][2 * i + 1]), sc2, nsh2);
-                        if (!FULL) {
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int k = k0 + kk;
+                        if (!u_on[k]) continue;
+                        const uint64_t sc2 = f2_pack(u_sc[k], u_sc[k]);
+                        const uint64_t nsh2 = f2_pack(u_nsh[k], u_nsh[k]);
+                        uint32_t hw[4], lw[4];
+                        uint64_t as2[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            // (v - shift) * scale in one rounding: the scale is a power of two, so this is
+                            // exactly scale * fl32(v - shift), the x' of the float64 edge kernel
+                            as2[i] = f2_fma(f2_pack(v[kk][2 * i], v[kk][2 * i + 1]), sc2, nsh2);
+                            if (!FULL) {
+                                float a0, a1;
+                                f2_unpack(as2[i], a0, a1);
+                                const int r = 8 * u_kq[k] + 2 * i;
+                                as2[i] = f2_pack(r < valid ? a0 : 0.f, r + 1 < valid ? a1 : 0.f);
+                            }
                             float a0, a1;
-                            f2_unpack(as2, a0, a1);
-                            const int r = 8 * u_kq[k] + 2 * i;
-                            as2 = f2_pack(r < valid ? a0 : 0.f, r + 1 < valid ? a1 : 0.f);
+                            f2_unpack(as2[i], a0, a1);
+                            hw[i] = pack_f16(a0, a1);               // h: round to nearest fp16 (Inf beyond 65504)
+                            // l = x' - h, exact in fp32: one mixed-precision FMA per value (h * -1 + x'),
+                            // full rate -- the unpack + packed subtract it replaces ran at half rate
+                            // (profiles/r2e_probe6_instruction_rates.log)
+                            float l0, l1;
+                            asm("{\n\t.reg .f16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+                                "fma.rn.f32.f16 %0, lo, m1, %3;\n\tfma.rn.f32.f16 %1, hi, m1, %4;\n\t}"
+                                : "=f"(l0), "=f"(l1) : "r"(hw[i]), "f"(a0), "f"(a1));
+                            lw[i] = pack_f16(l0, l1);
                         }
-                        sum2 = f2_add(sum2, as2);
-                        float a0, a1;
-                        f2_unpack(as2, a0, a1);
-                        hw[i] = pack_f16(a0, a1);                   // h: round to nearest fp16 (Inf beyond 65504)
-                        const uint64_t l2 = f2_sub(as2, h2_to_f2(hw[i]));   // exact in fp32
-                        float l0, l1;
-                        f2_unpack(l2, l0, l1);
-                        lw[i] = pack_f16(l0, l1);
-                    }
-                    // range check: largest |h| of this thread (Inf and NaN sort above every finite value)
-                    {
-                        uint32_t m01, m23;
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(hw[0] & 0x7FFF7FFFu), "r"(hw[1] & 0x7FFF7FFFu));
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(m23) : "r"(hw[2] & 0x7FFF7FFFu), "r"(hw[3] & 0x7FFF7FFFu));
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(m01), "r"(m23));
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
-                    }
-                    const uint32_t dst = st + u_dst[k];
-                    if (u_op[k] == 0) {
-                        sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // a
-                        sts_v4<(V2_T_AL - V2_T_A) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // al
-                        // h / 2 (one exact fp16 multiply per pair): the second factor of the G product
-                        uint32_t h0, h1, h2, h3;
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h0) : "r"(hw[0]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h1) : "r"(hw[1]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h2) : "r"(hw[2]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h3) : "r"(hw[3]), "r"(0x38003800u));
-                        sts_v4<(V2_T_AH - V2_T_A) * V2_TILE>(dst, h0, h1, h2, h3);              // ah
-                        // column sum: TwoSum of the tile's 8-frame sum into the float pair
-                        float s0, s1;
-                        f2_unpack(sum2, s0, s1);
-                        const float ts = s0 + s1;
-                        const float tt = sAh[k] + ts, bp = tt - sAh[k];
-                        sAl[k] += (sAh[k] - (tt - bp)) + (ts - bp);
-                        sAh[k] = tt;
-                    } else {
-                        sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // b
-                        sts_v4<(V2_T_BL - V2_T_B) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // bl
+                        // range check: largest |h| of this thread (Inf and NaN sort above every finite value)
+                        {
+                            uint32_t m01, m23;
+                            asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(hw[0] & 0x7FFF7FFFu), "r"(hw[1] & 0x7FFF7FFFu));
+                            asm("max.u16x2 %0, %1, %2;" : "=r"(m23) : "r"(hw[2] & 0x7FFF7FFFu), "r"(hw[3] & 0x7FFF7FFFu));
+                            asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(m01), "r"(m23));
+                            asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
+                        }
+                        const uint32_t dst = st + u_dst[k];
+                        if (u_a[k]) {
+                            sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // a
+                            sts_v4<(V2_T_AL - V2_T_A) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // al
+                            // h / 2 (one exact fp16 multiply per pair): the second factor of the G product
+                            uint32_t h0, h1, h2, h3;
+                            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h0) : "r"(hw[0]), "r"(0x38003800u));
+                            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h1) : "r"(hw[1]), "r"(0x38003800u));
+                            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h2) : "r"(hw[2]), "r"(0x38003800u));
+                            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h3) : "r"(hw[3]), "r"(0x38003800u));
+                            sts_v4<(V2_T_AH - V2_T_A) * V2_TILE>(dst, h0, h1, h2, h3);              // ah
+                            // column sum (operand 0 only): TwoSum of the 8-frame sum into the float pair
+                            float s0, s1;
+                            f2_unpack(f2_add(f2_add(as2[0], as2[1]), f2_add(as2[2], as2[3])), s0, s1);
+                            const float ts = s0 + s1;
+                            const float tt = sAh[k] + ts, bp = tt - sAh[k];
+                            sAl[k] += (sAh[k] - (tt - bp)) + (ts - bp);
+                            sAh[k] = tt;
+                        } else {
+                            sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // b
+                            sts_v4<(V2_T_BL - V2_T_B) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // bl
+                        }
                     }
                 }
             };
@@ -628,8 +624,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         {
             double *s_sum = reinterpret_cast<double *>(raw_ring);        // [4][UM_F]
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-                if (u_on[k] && u_op[k] == 0)
+            for (int k = 0; k < U; ++k)
+                if (u_on[k] && u_a[k])
                     s_sum[u_kq[k] * UM_F + u_fl[k]] = ((double)sAh[k] + (double)sAl[k]) / (double)u_sc[k];
             asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
             const int f = tid - V2_CONV_TID0;
@@ -638,27 +634,27 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     ? ((s_sum[f] + s_sum[UM_F + f]) + s_sum[2 * UM_F + f]) + s_sum[3 * UM_F + f] : 0.0;
         }
     } else if (warp >= V2_FIRST_DRAIN_WARP) {
-        // ================================ drain warps (one per TMEM lane quarter, every CTA) ======
-        const int quarter = warp & 3;
+        // ================================ drain warps (two per TMEM lane quarter, every CTA) ======
+        const int quarter = warp & 3;                            // TMEM lanes this warp may touch
+        const int half = (warp - V2_FIRST_DRAIN_WARP) >> 2;      // its half of a region's columns
         const int row = quarter * 32 + lane;                     // accumulator row = feature in this CTA
         const size_t cta_base = (size_t)cta_global * V2_REGIONS * RW * UM_F;
+        // columns [c_lo, c_hi) of the region are this warp's; none when the UMMAs are narrower
+        const int c_lo = half * CW, c_hi = min(n_cols, (half + 1) * CW);
         int next_end[V2_REGIONS], slabs_done[V2_REGIONS];
         uint32_t full_ph[V2_REGIONS];
-        const bool dbg_on = P.dbg != nullptr && group == 0 && cta_rank == 0 && quarter == 0 && lane == 0;
+        const bool dbg_on = P.dbg != nullptr && group == 0 && cta_rank == 0 && warp == V2_FIRST_DRAIN_WARP && lane == 0;
         long long d_wait = 0, d_ld = 0, d_red = 0, d_fold = 0, n_events = 0;
 #pragma unroll
         for (int q = 0; q < V2_REGIONS; ++q) {
             int e = ST - 1 - region_off(q);
             if (e > my_tiles - 1) e = my_tiles - 1;
-            next_end[q] = (region_active(q) && my_tiles > 0) ? e : 0x7fffffff;
+            next_end[q] = my_tiles > 0 ? e : 0x7fffffff;
             slabs_done[q] = 0;
             full_ph[q] = 0;
         }
         while (true) {
-            int q = 0;
-#pragma unroll
-            for (int r = 1; r < V2_REGIONS; ++r)
-                if (next_end[r] < next_end[q]) q = r;
+            const int q = next_end[1] < next_end[0] ? 1 : 0;
             const int e = next_end[q];
             if (e == 0x7fffffff) break;
             const bool last = e == my_tiles - 1;
@@ -669,15 +665,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const long long c1 = dbg_on ? clock64() : 0;
             float *l1 = P.lvl1 + cta_base + (size_t)q * RW * UM_F + row;
             long long t_ld = 0;
+            bool released = false;
             if (!(P.dbg_mode & 2)) {
 #pragma unroll 1
-                for (int c = 0; c < RW / 32; ++c) {
-                    uint32_t v[32];
+                for (int c = c_lo; c < c_hi; c += 64) {
+                    uint32_t v0[32], v1[32];
                     const long long a0 = dbg_on ? clock64() : 0;
-                    UM_TMEM_LD32(v, tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RW * q + 32 * c));
+                    UM_TMEM_LD32(v0, tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RW * q + c));
+                    if (c + 32 < c_hi)
+                        UM_TMEM_LD32(v1, tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(RW * q + c + 32));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c == RW / 32 - 1) {
-                        // the region's accumulators are in registers: hand TMEM back before the
+                    if (c + 64 >= c_hi) {
+                        // the warp's share of the region is in registers: hand TMEM back before the
                         // reductions are issued
                         asm volatile("tcgen05.fence::before_thread_sync;");
                         __syncwarp();
@@ -685,16 +684,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                             if constexpr (CG == 2) mbar_arrive_cluster(&ctl->acc_empty[q], 0);
                             else mbar_arrive_local(&ctl->acc_empty[q]);
                         }
+                        released = true;
                     }
                     if (dbg_on) t_ld += clock64() - a0;
-                    float *dst = l1 + (size_t)(32 * c) * UM_F;
+                    float *dst = l1 + (size_t)c * UM_F;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 32; ++j)
                         asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;"
-                                     :: "l"(dst + (size_t)j * UM_F), "f"(__uint_as_float(v[j])) : "memory");
+                                     :: "l"(dst + (size_t)j * UM_F), "f"(__uint_as_float(v0[j])) : "memory");
+                    if (c + 32 < c_hi) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;"
+                                         :: "l"(dst + (size_t)(32 + j) * UM_F), "f"(__uint_as_float(v1[j])) : "memory");
                     }
                 }
-            } else {
+            }
+            if (!released) {
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
                 if (lane == 0 && !last) {
@@ -703,12 +709,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 }
             }
             const long long c2 = dbg_on ? clock64() : 0;
-            if (!last && !(P.dbg_mode & 2)) {
-                // one 16-column group of this region: float32 level -> float-float pair, error-free
-                // (TwoSum), then clear the level.  This warp is the only one that ever touches these
-                // addresses; its own reductions above are ordered before these loads (same thread,
-                // same address, gpu scope).  The finalize path adds whatever is left in the level.
-                const int c = 16 * (slabs_done[q] % NG);
+            if (!last && !(P.dbg_mode & 2) && c_lo + 16 * (slabs_done[q] % NG) < c_hi) {
+                // one 16-column group of this warp's columns: float32 level -> float-float pair,
+                // error-free (TwoSum), then clear the level.  This warp is the only one that ever
+                // touches these addresses; its own reductions above are ordered before these loads
+                // (same thread, same address, gpu scope).  The finalize path adds what is left in the level.
+                const int c = c_lo + 16 * (slabs_done[q] % NG);
                 float *hi = P.hi + cta_base + (size_t)q * RW * UM_F + row;
                 float *lo = P.lo + cta_base + (size_t)q * RW * UM_F + row;
                 float s[16], H[16], L[16];
@@ -760,7 +766,7 @@ tica_umma_v2_reduce_kernel(const float *__restrict__ lvl1, const float *__restri
                            const float *__restrict__ lo, int n_groups,
                            const int *__restrict__ rescued, double *__restrict__ R)
 {
-    constexpr int RW = 64 * CG;
+    constexpr int RW = 128 * CG;
     constexpr size_t PER_CTA = (size_t)V2_REGIONS * RW * UM_F;
     if (*rescued != 0) return;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -784,7 +790,7 @@ tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restr
                              double n_seq, int Dr, double *__restrict__ acc)
 {
     constexpr int D = UM_D;
-    constexpr int RW = 64 * CG;
+    constexpr int RW = 128 * CG;
     if (*rescued != 0) return;
     const size_t DD = (size_t)D * D;
     const size_t RR = (size_t)Dr * Dr;
@@ -792,12 +798,9 @@ tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restr
     if (idx >= (int)RR) return;
     const int i = idx / Dr, j = idx % Dr;
     // element (row r, feature column c) of matrix m (0 = C_tau, 1 = G): CTA r / 128 of the group,
-    // region 2 m + half, column (c / 128) * 64 + c % 64 of the region (half = (c % 128) / 64), row r % 128
+    // region m, column c (UMMA column n = CTA n / 128, feature n % 128 = global feature n), row r % 128
     auto at = [&](int m, int r, int c) -> double {
-        const int half = (c % UM_F) / 64;
-        const int col = (c / UM_F) * 64 + (c % 64);
-        return R[(((size_t)(r / UM_F) * V2_REGIONS + (size_t)(2 * m + half)) * RW + (size_t)col) * UM_F
-                 + (size_t)(r % UM_F)];
+        return R[(((size_t)(r / UM_F) * V2_REGIONS + (size_t)m) * RW + (size_t)c) * UM_F + (size_t)(r % UM_F)];
     };
     const double inv = 1.0 / ((double)scale[i] * (double)scale[j]);
     double ctau = at(0, i, j) * inv;
