@@ -433,23 +433,54 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
     best = s_best;
     maxv2 = s_v2[0];
 
-    // (2) key of the t_cap-th largest lane maximum (bitwise binary search; 0 if fewer are positive)
+    // (2) key of the t_cap-th largest lane maximum (0 if fewer than t_cap are positive): radix select,
+    //     8 bits per round from the top -- 8 passes over the lane records instead of the 63 of a
+    //     bitwise search (this block is the serial section between two fused passes)
     unsigned long long K = 0;
-    for (int bit = 62; bit >= 0; --bit) {
-        const unsigned long long trial = K | (1ull << bit);
+    {
+        __shared__ unsigned s_hist[256];
+        __shared__ unsigned long long s_prefix;
+        __shared__ unsigned s_rank;
+        // positive keys in all
         unsigned long long cnt = 0;
-        for (long long s = tid; s < n_slots; s += blockDim.x) cnt += cand_key(lc[s].v1) >= trial;
+        for (long long s = tid; s < n_slots; s += blockDim.x) cnt += cand_key(lc[s].v1) != 0ull;
         for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-        __syncthreads();                 // s_cnt / s_total of the previous round are consumed
         if (lane == 0) s_cnt[warp] = cnt;
         __syncthreads();
         if (warp == 0) {
             unsigned long long c = s_cnt[lane];
             for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-            if (lane == 0) s_total = c;
+            if (lane == 0) { s_total = c; s_prefix = 0ull; s_rank = (unsigned)t_cap; }
         }
         __syncthreads();
-        if (s_total >= (unsigned long long)t_cap) K = trial;
+        if (s_total >= (unsigned long long)t_cap) {
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                if (tid < 256) s_hist[tid] = 0u;
+                __syncthreads();
+                const unsigned long long prefix = s_prefix;
+                for (long long s = tid; s < n_slots; s += blockDim.x) {
+                    const unsigned long long key = cand_key(lc[s].v1);
+                    // keys that agree with the digits chosen so far
+                    if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                        atomicAdd(&s_hist[(unsigned)(key >> shift) & 0xFFu], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    // the digit whose bin holds the s_rank-th largest of the remaining keys
+                    unsigned rank = s_rank, above = 0u;
+                    int b = 255;
+                    for (; b > 0; --b) {
+                        if (above + s_hist[b] >= rank) break;
+                        above += s_hist[b];
+                    }
+                    s_prefix = prefix | ((unsigned long long)b << shift);
+                    s_rank = rank - above;
+                }
+                __syncthreads();
+            }
+            K = s_prefix;
+        }
+        __syncthreads();
     }
 
     // (3) candidates: lane maxima strictly above that value (< t_cap of them), plus the arg-max

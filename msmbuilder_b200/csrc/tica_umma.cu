@@ -1147,14 +1147,18 @@ static int env_int(const char *name, int dflt)
 struct MapKey {
     const void *base;
     long long rows, ld;
-    int D;
-    bool operator==(const MapKey &o) const { return base == o.base && rows == o.rows && ld == o.ld && D == o.D; }
+    int D, box_blocks;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && rows == o.rows && ld == o.ld && D == o.D && box_blocks == o.box_blocks;
+    }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey &k) const
     {
         size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
-        h ^= (size_t)k.rows * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.D;
+        h ^= (size_t)k.rows * 0xC2B2AE3D27D4EB4Full + (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.D
+             + ((size_t)k.box_blocks << 20);
         return h ^ (h >> 29);
     }
 };
@@ -1278,6 +1282,9 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         for (int j = sample_rows; j < UM_SAMPLE_ROWS; ++j) sample[j] = nullptr;
     }
     if (g_map_cache.size() > (1u << 16)) g_map_cache.clear();
+    // 32-feature blocks per TMA box: the single-CTA v2 kernel only brings the blocks that exist (the
+    // zero-filled ones would still cost shared-memory write bandwidth, the kernel's scarcest resource)
+    const int box_blocks = (v2 && v2_cg == 1) ? D / 32 : 4;
     long long tiles = 0;
     for (int s = 0; s < n_seq; ++s) {
         const long long Pn = seqs[s].n - lag;           // pair indices (>= 1)
@@ -1296,7 +1303,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
             // (32 features, Pn rows, D/32 blocks); rows >= Pn read as zeros
             void *base = (void *)(seqs[s].base + (which ? (size_t)lag * ld : 0));
             CUtensorMap *dst = which ? &mapsB[s] : &mapsA[s];
-            const MapKey key{base, Pn, (long long)ld, D};
+            const MapKey key{base, Pn, (long long)ld, D, box_blocks};
             auto hit = g_map_cache.find(key);
             if (hit != g_map_cache.end()) {
                 *dst = hit->second;
@@ -1304,7 +1311,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
             }
             cuuint64_t dims[3] = {32, (cuuint64_t)Pn, (cuuint64_t)(D / 32)};
             cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-            cuuint32_t box[3] = {32, UM_KT, 4};
+            cuuint32_t box[3] = {32, UM_KT, (cuuint32_t)box_blocks};
             cuuint32_t es[3] = {1, 1, 1};
             CUresult r = enc(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                              dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1442,6 +1449,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     V.slab_tiles = env_int("MSMB200_UMMA_SLAB_TILES", UM_SLAB_TILES_DEFAULT);
     if (V.slab_tiles < 1) V.slab_tiles = 1;
     V.D = D;
+    V.box_blocks = box_blocks;
     V.dbg_mode = P.dbg_mode;
     V.shift = d_shift;
     V.scale = d_scale;

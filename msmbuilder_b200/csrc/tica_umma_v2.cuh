@@ -64,6 +64,7 @@ struct V2Params {
     int n_groups;                 // CTA pairs (CG = 2) or CTAs (CG = 1)
     int slab_tiles;               // 32-frame tiles per TMEM slab
     int D;                        // real feature count (32k)
+    int box_blocks;               // 32-feature blocks one TMA box brings (4; D / 32 for the single-CTA kernel)
     int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 if (valid > UM_KT) valid = UM_KT;
                 mbar_wait(&ctl->raw_empty[stage], phase ^ 1);
                 ctl->valid_rows[stage] = valid;
-                mbar_expect_tx(&ctl->raw_full[stage], 2 * UM_TILE_BYTES);
+                mbar_expect_tx(&ctl->raw_full[stage], 2 * P.box_blocks * (UM_KT * 128));
                 unsigned char *st = raw_ring + stage * UM_RAW_BYTES;
                 tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
                 tma_load_3d(st + UM_TILE_BYTES, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
