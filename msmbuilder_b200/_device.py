@@ -147,14 +147,34 @@ class HostUploader(object):
         events[-1].synchronize()
 
 
-_UPLOADER = None
+_UPLOADERS = {}
 
 
 def uploader():
-    global _UPLOADER
-    if _UPLOADER is None:
-        _UPLOADER = HostUploader()
-    return _UPLOADER
+    """One uploader (pinned ring, copy threads, side stream) per device: the worker threads of a
+    multi-GPU fit (`devices=`) upload to their own GPU at the same time."""
+    d = torch.cuda.current_device()
+    up = _UPLOADERS.get(d)
+    if up is None:
+        up = _UPLOADERS.setdefault(d, HostUploader())
+    return up
+
+
+def resolve_devices(devices):
+    """`devices` of the estimators -> list of CUDA ordinals, or None for "the current device".
+    None / a single device keep the one-GPU path; 'all' = every visible GPU."""
+    if devices is None:
+        return None
+    if isinstance(devices, str):
+        if devices != 'all':
+            raise ValueError("devices must be None, 'all' or a sequence of CUDA ordinals")
+        devs = list(range(torch.cuda.device_count()))
+    else:
+        devs = [int(d) for d in devices]
+    if len(set(devs)) != len(devs) or any(d < 0 or d >= torch.cuda.device_count() for d in devs):
+        raise ValueError("devices=%r: need distinct ordinals below torch.cuda.device_count()=%d"
+                         % (devices, torch.cuda.device_count()))
+    return devs if len(devs) > 1 else None
 
 
 def host_array(a):

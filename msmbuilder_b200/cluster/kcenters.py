@@ -53,6 +53,10 @@ class _KCenters(ClusterMixin, TransformerMixin):
         Distance. 'rmsd' takes trajectories / (n, n_atoms, 3) coordinates.
     random_state : integer or numpy.RandomState, optional
         Draws the first centre; an integer fixes the seed.
+    devices : None, 'all' or list of CUDA ordinals, optional (``KCenters`` only)
+        GPUs to shard the frames over from ONE process (a thread per GPU, candidate exchange by
+        peer copies): ``fit`` then uses the whole box without torchrun.  None = current device.
+        Same centres, labels and distances as on one GPU.
 
     Attributes
     ----------
@@ -129,6 +133,10 @@ class KCenters(MultiSequenceClusterMixin, _KCenters, BaseEstimator):
         Distance of each frame to its centre, one array per sequence.
     '''
 
+    def __init__(self, n_clusters=8, metric='euclidean', random_state=None, devices=None):
+        _KCenters.__init__(self, n_clusters=n_clusters, metric=metric, random_state=random_state)
+        self.devices = devices
+
     def fit(self, sequences, y=None):
         """Fit the kcenters clustering on the data
 
@@ -142,8 +150,96 @@ class KCenters(MultiSequenceClusterMixin, _KCenters, BaseEstimator):
         -------
         self
         """
+        from .._device import resolve_devices
+        devs = resolve_devices(self.devices)
+        if devs is not None:
+            return self._fit_on_devices(sequences, devs)
         MultiSequenceClusterMixin.fit(self, sequences)
         self.distances_ = self._split(self.distances_)
+        return self
+
+    def _fit_on_devices(self, sequences, devs):
+        """One process, one thread per GPU: contiguous row ranges of the concatenated frames go to
+        the devices (no host concatenation: every thread uploads slices of the caller's arrays into
+        its own FrameStore), then the rank-collective loop of parallel.kcenters_fit_gpu runs over a
+        thread communicator -- the protocol torchrun + NCCL would run, minus the processes."""
+        import threading
+        import torch
+        from ..utils import check_iter_of_sequences
+        from .base import _frames_of
+        from .. import parallel as P
+        from .. import _kernels as K
+        from .._device import FrameStore, to_host
+        check_iter_of_sequences(sequences, allow_trajectory=self._allow_trajectory)
+        seqs = [_frames_of(s) for s in sequences]
+        if len(seqs) == 0:
+            raise TypeError('sequences must be a list of numpy arrays or ``md.Trajectory``s')
+        lengths = [int(len(s)) for s in seqs]
+        n_total = int(sum(lengths))
+        # a device needs a few thousand frames to be worth a thread
+        n_dev = max(1, min(len(devs), n_total // 4096))
+        devs = devs[:n_dev]
+        if n_dev == 1:
+            with torch.cuda.device(devs[0]):
+                MultiSequenceClusterMixin.fit(self, sequences)
+                self.distances_ = self._split(self.distances_)
+            return self
+        starts = np.concatenate([[0], np.cumsum(lengths)])
+        ranges = P.shard_rows(n_total, n_dev)
+        seed = check_random_state(self.random_state).randint(0, n_total)      # kcenters.py:84
+        k, metric = int(self.n_clusters), self.metric
+        group = P.ThreadGroup(n_dev)
+        results, errors = [None] * n_dev, []
+
+        def work(r):
+            try:
+                lo, hi = ranges[r]
+                with torch.cuda.device(devs[r]):
+                    parts = []
+                    for s, a in zip(seqs, starts[:-1]):
+                        b0, b1 = max(lo, int(a)) - int(a), min(hi, int(a) + len(s)) - int(a)
+                        if b1 > b0:
+                            parts.append(s[b0:b1])
+                    store = FrameStore(parts)
+                    data, traces = store.data, None
+                    if metric == 'rmsd':
+                        if data.ndim != 3 or data.shape[2] != 3:
+                            raise ValueError("metric='rmsd' needs coordinates of shape (n_frames, n_atoms, 3)")
+                        data = data.to(torch.float32).clone()
+                        traces = K.rmsd_center(data)
+                    elif data.ndim != 2:
+                        raise ValueError("expected a 2-D array of shape (n_samples, n_features)")
+                    ids, distances, labels, ring = P.kcenters_fit_gpu(
+                        data, lo, k, metric, seed, traces=traces, comm=group.comm(r))
+                    row_elems = int(np.prod(data.shape[1:]))
+                    es = data.element_size()
+                    cent = None
+                    if r == 0:
+                        cent = ring[:k, P.CAND_HEADER:P.CAND_HEADER + row_elems * es].contiguous() \
+                            .view(data.dtype).reshape((k,) + tuple(data.shape[1:])).cpu().numpy()
+                    results[r] = (ids.cpu().numpy(), to_host(labels, torch.int64), to_host(distances),
+                                  float(distances.sum().item()), cent)
+            except BaseException as e:        # noqa: B902 -- the other threads must not wait for this one
+                errors.append(e)
+                group.abort()
+
+        threads = [threading.Thread(target=work, args=(r,), name="msmb200-kcenters-%d" % devs[r])
+                   for r in range(n_dev)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            first = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+            raise (first or errors)[0]
+        self.cluster_ids_ = [int(c) for c in results[0][0]]
+        self.cluster_centers_ = results[0][4]
+        labels = np.concatenate([res[1] for res in results])
+        distances = np.concatenate([res[2] for res in results])
+        self.inertia_ = float(sum(res[3] for res in results))
+        self._MultiSequenceClusterMixin__lengths = lengths
+        self.labels_ = self._split(labels)
+        self.distances_ = self._split(distances)
         return self
 
     def summarize(self):

@@ -585,8 +585,41 @@ rmsd_scan_kernel(const double *__restrict__ dist, const int *__restrict__ labels
 
 // The pass proper.  list == NULL: every frame (dense: tiles of 32 consecutive frames); otherwise the
 // frames named by list[0 .. ps->list_count).  block_cands[0 .. scan_blocks) were written by the scan.
+//
+// Two kinds of warps (r2f ncu: with the Newton iteration behind the float32 sums in one warp, the
+// single warp a scheduler could hold -- 38 KB of tile each -- issued 1 cycle in 4, waiting on its own
+// dependent float64 chain):
+//   tile warps (kTileWarps)   stage 32 frames with cp.async, every lane forms the float32 M of its
+//                             frame and hands {M, G_x, frame} to its solver warp through a
+//                             double-buffered record in shared memory (mbarrier full / empty);
+//   solver warps (kTileWarps) one per tile warp, no tile of their own: the double Newton iteration,
+//                             the strict running minimum and the arg-max, while the tile warp is
+//                             already copying / summing the next 32 frames.
+struct SolveRecord { float M[9]; float Gx; long long f; };          // 48 bytes per lane
+
+__device__ __forceinline__ void mbar_init_(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 template <bool VEC4>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(2 * kTileThreads)
 rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ traces, long long n,
                       int n_atoms, const float *__restrict__ center, int label,
                       double *__restrict__ dist, int *__restrict__ labels, long long row_offset,
@@ -594,50 +627,85 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
                       BlockCandR *__restrict__ block_cands, msmb200_candidate *__restrict__ out)
 {
     extern __shared__ __align__(16) float s_tile[];
+    __shared__ uint64_t s_full[kTileWarps][2], s_empty[kTileWarps][2];
+    __shared__ ArgMax s_warp[kTileWarps];
+    __shared__ bool s_is_last;
     const int n3 = n_atoms * 3;
     const int stride = tile_stride(n_atoms, VEC4);
     float *s_center = s_tile;                                  // n3 floats (padded to 16 bytes)
     const int c_pad = (n3 + 3) & ~3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *my_tile = s_tile + c_pad + (size_t)warp * 32 * stride;
+    const bool solver = warp >= kTileWarps;
+    const int pair = solver ? warp - kTileWarps : warp;
+    float *my_tile = s_tile + c_pad + (size_t)pair * 32 * stride;
+    SolveRecord *records = reinterpret_cast<SolveRecord *>(s_tile + c_pad + (size_t)kTileWarps * 32 * stride)
+                           + (size_t)pair * 2 * 32;
     for (int j = threadIdx.x; j < n3; j += blockDim.x) s_center[j] = center[j];
+    if (threadIdx.x < kTileWarps * 2) {
+        mbar_init_(&s_full[threadIdx.x >> 1][threadIdx.x & 1], 1);
+        mbar_init_(&s_empty[threadIdx.x >> 1][threadIdx.x & 1], 1);
+    }
     __syncthreads();
     const float Gc = center[n3];
     const long long total = list ? (long long)ps->list_count : n;
     const long long n_chunks = (total + 31) / 32;
     ArgMax best{-INFINITY, 0x7fffffffffffffffLL};
-    for (long long ch = (long long)blockIdx.x * kTileWarps + warp; ch < n_chunks;
-         ch += (long long)gridDim.x * kTileWarps) {
-        const long long e = ch * 32 + lane;
-        const bool valid = e < total;
-        const long long f = valid ? (list ? (long long)list[e] : e) : -1;
-        // stage the chunk's frames: the warp copies frame after frame (coalesced)
-        for (int j = 0; j < 32; ++j) {
-            const long long fj = __shfl_sync(0xffffffffu, f, j);
-            if (fj < 0) break;
-            tile_copy_frame<VEC4>(my_tile + (size_t)j * stride, xyz + fj * (long long)n3, n3, lane);
-        }
-        double cur = INFINITY;
-        float Gx = 0.f;
-        if (valid) { cur = __ldcg(dist + f); Gx = traces[f]; }
-        tile_copy_wait();
-        if (valid) {
+    if (!solver) {
+        // ------------------------------------------------ tile warp: copy, float32 sums, hand over
+        long long it = 0;
+        for (long long ch = (long long)blockIdx.x * kTileWarps + pair; ; ch += (long long)gridDim.x * kTileWarps, ++it) {
+            const bool more = ch < n_chunks;
+            long long f = -2;                                  // -2: no more chunks (every lane)
             float M[9];
-            inner_products_simd4<VEC4>(my_tile + (size_t)lane * stride, s_center, n_atoms, M);
-            const double dv = (double)qcp_rmsd_strict(M, Gx, Gc, n_atoms);
-            if (dv < cur) {
-                cur = dv;
-                dist[f] = dv;
-                labels[f] = label;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) M[q] = 0.f;
+            float Gx = 0.f;
+            if (more) {
+                const long long e = ch * 32 + lane;
+                f = e < total ? (list ? (long long)list[e] : e) : -1;
+                for (int j = 0; j < 32; ++j) {
+                    const long long fj = __shfl_sync(0xffffffffu, f, j);
+                    if (fj < 0) break;
+                    tile_copy_frame<VEC4>(my_tile + (size_t)j * stride, xyz + fj * (long long)n3, n3, lane);
+                }
+                if (f >= 0) Gx = traces[f];
+                tile_copy_wait();
+                if (f >= 0) inner_products_simd4<VEC4>(my_tile + (size_t)lane * stride, s_center, n_atoms, M);
             }
-            if (cur > best.v || (cur == best.v && f < best.i)) { best.v = cur; best.i = f; }
+            const int b = (int)(it & 1);
+            mbar_wait_(&s_empty[pair][b], (uint32_t)(((it >> 1) & 1) ^ 1));
+            SolveRecord &r = records[b * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) r.M[q] = M[q];
+            r.Gx = Gx;
+            r.f = f;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&s_full[pair][b]);
+            if (!more) break;
         }
-        __syncwarp();                                          // the tile is rewritten by the next chunk
+    } else {
+        // ------------------------------------------------ solver warp: Newton, minimum, arg-max
+        for (long long it = 0; ; ++it) {
+            const int b = (int)(it & 1);
+            mbar_wait_(&s_full[pair][b], (uint32_t)((it >> 1) & 1));
+            const SolveRecord r = records[b * 32 + lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&s_empty[pair][b]);
+            if (r.f == -2) break;
+            if (r.f >= 0) {
+                double cur = __ldcg(dist + r.f);
+                const double dv = (double)qcp_rmsd_strict(r.M, r.Gx, Gc, n_atoms);
+                if (dv < cur) {
+                    cur = dv;
+                    dist[r.f] = dv;
+                    labels[r.f] = label;
+                }
+                if (cur > best.v || (cur == best.v && r.f < best.i)) { best.v = cur; best.i = r.f; }
+            }
+        }
+        best = argmax_warp(best);
+        if (lane == 0) s_warp[pair] = best;
     }
-    __shared__ ArgMax s_warp[kTileWarps];
-    __shared__ bool s_is_last;
-    best = argmax_warp(best);
-    if (lane == 0) s_warp[warp] = best;
     __syncthreads();
     BlockCandR *mine = block_cands + scan_blocks_cap;          // the scan kernel's slots come first
     if (threadIdx.x == 0) {
@@ -663,193 +731,21 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     }
     w = argmax_warp(w);
     __syncthreads();
-    if (lane == 0) s_warp[warp] = w;
+    if (lane == 0 && warp < kTileWarps) s_warp[warp] = w;
+    __syncthreads();
+    // warps kTileWarps .. 2 kTileWarps - 1 hold the other half of the candidates
+    __shared__ ArgMax s_warp2[kTileWarps];
+    if (lane == 0 && warp >= kTileWarps) s_warp2[warp - kTileWarps] = w;
     __syncthreads();
     if (threadIdx.x == 0) {
         ArgMax b = s_warp[0];
         for (int q = 1; q < kTileWarps; ++q) b = argmax_merge(b, s_warp[q]);
+        for (int q = 0; q < kTileWarps; ++q) b = argmax_merge(b, s_warp2[q]);
         if (b.i == 0x7fffffffffffffffLL) b.i = 0;
         s_warp[0] = b;
         out->value = b.v;
         out->index = row_offset + b.i;
         ps->list_count = 0;                                    // ready for the next pass's scan
-        ps->scan_blocks = 0;
-    }
-    __syncthreads();
-    w = s_warp[0];
-    float *payload = reinterpret_cast<float *>(out + 1);
-    if (n > 0) {
-        for (int j = threadIdx.x; j < n3; j += blockDim.x) payload[j] = xyz[w.i * (long long)n3 + j];
-        if (threadIdx.x == 0) payload[n3] = traces[w.i];
-    }
-}
-
-// ---- K6c', the pipelined pass (frames 16-byte aligned, n_atoms % 4 == 0) ----------------------------
-// Same arithmetic, same results; the copy of a tile no longer waits in front of its arithmetic.  A
-// frame is cut into phases of <= 3 four-atom groups (144 bytes); a warp owns a ring of four
-// sub-buffers (32 frames x one phase each, 18 KB per warp: three blocks per SM) and always has the copies of the next
-// three phases in flight (cp.async groups) while every lane walks the current phase of its own frame,
-// the 4 x 9 float32 accumulators staying in registers from phase to phase.
-static constexpr int kPipeDepth = 4;
-static constexpr int kPipeQuads = 3;          // 144-byte phases: 18 KB of ring per warp, 12 warps per SM (the
-                                              // arithmetic is latency bound with one warp per scheduler, r2f ncu)
-__host__ __device__ inline int pipe_qpp(int n_atoms)
-{
-    const int nq = n_atoms >> 2;
-    return nq < kPipeQuads ? (nq > 0 ? nq : 1) : kPipeQuads;
-}
-__host__ __device__ inline int pipe_stride4(int n_atoms) { return (3 * pipe_qpp(n_atoms)) | 1; }   // odd: conflict-free
-
-__global__ void __launch_bounds__(kTileThreads)
-rmsd_pipe_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ traces, long long n,
-                      int n_atoms, const float *__restrict__ center, int label,
-                      double *__restrict__ dist, int *__restrict__ labels, long long row_offset,
-                      const int *__restrict__ list, PassScratch *__restrict__ ps, int scan_blocks_cap,
-                      BlockCandR *__restrict__ block_cands, msmb200_candidate *__restrict__ out)
-{
-    extern __shared__ __align__(16) float s_tile[];
-    const int n3 = n_atoms * 3;
-    const int n_quads = n_atoms >> 2;
-    const int qpp = pipe_qpp(n_atoms);
-    const int n_ph = (n_quads + qpp - 1) / qpp;
-    const int stride4 = pipe_stride4(n_atoms);
-    float *s_center = s_tile;
-    const int c_pad = (n3 + 3) & ~3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *ring = reinterpret_cast<float4 *>(s_tile + c_pad) + (size_t)warp * kPipeDepth * 32 * stride4;
-    for (int j = threadIdx.x; j < n3; j += blockDim.x) s_center[j] = center[j];
-    __syncthreads();
-    const float Gc = center[n3];
-    const long long total = list ? (long long)ps->list_count : n;
-    const long long n_chunks = (total + 31) / 32;
-    const long long ch0 = (long long)blockIdx.x * kTileWarps + warp;
-    const long long ch_stride = (long long)gridDim.x * kTileWarps;
-    const long long my_chunks = ch0 < n_chunks ? (n_chunks - ch0 + ch_stride - 1) / ch_stride : 0;
-    const long long n_items = my_chunks * n_ph;
-
-    // frame of lane `lane` in the chunk of item i (-1: none)
-    auto frame_of = [&](long long item) -> long long {
-        const long long e = (ch0 + (item / n_ph) * ch_stride) * 32 + lane;
-        if (e >= total) return -1;
-        return list ? (long long)list[e] : e;
-    };
-    // start the copies of item i (one cp.async group, possibly empty)
-    auto issue = [&](long long item) {
-        if (item < n_items) {
-            const int p = (int)(item % n_ph);
-            const int q0 = p * qpp;
-            const int len4 = 3 * (min(qpp, n_quads - q0));          // float4s of this phase per frame
-            const long long f = frame_of(item);
-            float4 *buf = ring + (size_t)(item % kPipeDepth) * 32 * stride4;
-            for (int j = 0; j < 32; ++j) {
-                const long long fj = __shfl_sync(0xffffffffu, f, j);
-                if (fj < 0) break;
-                if (lane < len4)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                 :: "r"((uint32_t)__cvta_generic_to_shared(buf + (size_t)j * stride4 + lane)),
-                                    "l"(reinterpret_cast<const float4 *>(xyz + fj * (long long)n3) + 3 * q0 + lane)
-                                 : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    ArgMax best{-INFINITY, 0x7fffffffffffffffLL};
-    float acc[4][9];
-    double cur = INFINITY;
-    float Gx = 0.f;
-    long long f_cur = -1;
-    for (int i = 0; i < kPipeDepth - 1; ++i) issue(i);
-    for (long long item = 0; item < n_items; ++item) {
-        issue(item + kPipeDepth - 1);
-        asm volatile("cp.async.wait_group %0;" :: "n"(kPipeDepth - 1) : "memory");
-        __syncwarp();
-        const int p = (int)(item % n_ph);
-        if (p == 0) {
-            f_cur = frame_of(item);
-#pragma unroll
-            for (int l = 0; l < 4; ++l)
-#pragma unroll
-                for (int q = 0; q < 9; ++q) acc[l][q] = 0.f;
-            cur = INFINITY;
-            Gx = 0.f;
-            if (f_cur >= 0) { cur = __ldcg(dist + f_cur); Gx = traces[f_cur]; }
-        }
-        if (f_cur >= 0) {
-            const int q0 = p * qpp;
-            const int nq = min(qpp, n_quads - q0);
-            const float4 *x4 = ring + (size_t)(item % kPipeDepth) * 32 * stride4 + (size_t)lane * stride4;
-            const float4 *y4 = reinterpret_cast<const float4 *>(s_center) + 3 * q0;
-            for (int g = 0; g < nq; ++g) {
-                float xs[12], ys[12];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float4 a = x4[3 * g + c], b = y4[3 * g + c];
-                    xs[4 * c] = a.x; xs[4 * c + 1] = a.y; xs[4 * c + 2] = a.z; xs[4 * c + 3] = a.w;
-                    ys[4 * c] = b.x; ys[4 * c + 1] = b.y; ys[4 * c + 2] = b.z; ys[4 * c + 3] = b.w;
-                }
-                RMSD_ATOM(0, xs[0], xs[1], xs[2], ys[0], ys[1], ys[2])
-                RMSD_ATOM(1, xs[3], xs[4], xs[5], ys[3], ys[4], ys[5])
-                RMSD_ATOM(2, xs[6], xs[7], xs[8], ys[6], ys[7], ys[8])
-                RMSD_ATOM(3, xs[9], xs[10], xs[11], ys[9], ys[10], ys[11])
-            }
-            if (p == n_ph - 1) {
-                float M[9];
-#pragma unroll
-                for (int q = 0; q < 9; ++q)
-                    M[q] = __fadd_rn(__fadd_rn(acc[0][q], acc[1][q]), __fadd_rn(acc[2][q], acc[3][q]));
-                const double dv = (double)qcp_rmsd_strict(M, Gx, Gc, n_atoms);
-                if (dv < cur) {
-                    cur = dv;
-                    dist[f_cur] = dv;
-                    labels[f_cur] = label;
-                }
-                if (cur > best.v || (cur == best.v && f_cur < best.i)) { best.v = cur; best.i = f_cur; }
-            }
-        }
-        __syncwarp();                                          // the sub-buffer is refilled by the next issue
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-
-    __shared__ ArgMax s_warp[kTileWarps];
-    __shared__ bool s_is_last;
-    best = argmax_warp(best);
-    if (lane == 0) s_warp[warp] = best;
-    __syncthreads();
-    BlockCandR *mine = block_cands + scan_blocks_cap;
-    if (threadIdx.x == 0) {
-        ArgMax b = s_warp[0];
-        for (int w = 1; w < kTileWarps; ++w) b = argmax_merge(b, s_warp[w]);
-        mine[blockIdx.x].v = b.v;
-        mine[blockIdx.x].i = b.i;
-        __threadfence();
-        const unsigned ticket = atomicInc(&ps->counter, gridDim.x - 1);
-        s_is_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_is_last) return;
-    __threadfence();
-    ArgMax w{-INFINITY, 0x7fffffffffffffffLL};
-    const int n_scan = list ? (int)ps->scan_blocks : 0;
-    for (int b = threadIdx.x; b < n_scan + (int)gridDim.x; b += blockDim.x) {
-        const BlockCandR *src = b < n_scan ? block_cands + b : mine + (b - n_scan);
-        ArgMax c;
-        c.v = __ldcg(&src->v);
-        c.i = __ldcg(&src->i);
-        w = argmax_merge(w, c);
-    }
-    w = argmax_warp(w);
-    __syncthreads();
-    if (lane == 0) s_warp[warp] = w;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        ArgMax b = s_warp[0];
-        for (int q = 1; q < kTileWarps; ++q) b = argmax_merge(b, s_warp[q]);
-        if (b.i == 0x7fffffffffffffffLL) b.i = 0;
-        s_warp[0] = b;
-        out->value = b.v;
-        out->index = row_offset + b.i;
-        ps->list_count = 0;
         ps->scan_blocks = 0;
     }
     __syncthreads();
@@ -1008,13 +904,11 @@ static int rmsd_pass_tiles(const float *xyz, const float *traces, int64_t n, int
     double *dcc = reinterpret_cast<double *>(w + 64 + sizeof(BlockCandR) * (size_t)(kScanBlocksCap + 2 * 1024));
     int *list = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(dcc) + sizeof(double) * (size_t)(n_prev + 1));
     const bool vec4 = (n_atoms & 3) == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15u) == 0;
-    const size_t smem = vec4 ? sizeof(float) * (size_t)((n_atoms * 3 + 3) & ~3)
-                                   + sizeof(float4) * (size_t)kTileWarps * kPipeDepth * 32 * pipe_stride4(n_atoms)
-                             : tile_smem_bytes(n_atoms, false, true);
+    const size_t smem = tile_smem_bytes(n_atoms, vec4, true) + sizeof(SolveRecord) * (size_t)kTileWarps * 2 * 32;
     static bool attr_done[2] = {false, false};
     if (!attr_done[vec4 ? 1 : 0]) {
-        if (vec4) MSMB_CUDA(cudaFuncSetAttribute(rmsd_pipe_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        else MSMB_CUDA(cudaFuncSetAttribute(rmsd_tile_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (vec4) MSMB_CUDA(cudaFuncSetAttribute(rmsd_tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        else MSMB_CUDA(cudaFuncSetAttribute(rmsd_tile_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done[vec4 ? 1 : 0] = true;
     }
     const int *d_list = nullptr;
@@ -1033,11 +927,11 @@ static int rmsd_pass_tiles(const float *xyz, const float *traces, int64_t n, int
     }
     const int grid = tile_grid(n, smem);
     if (vec4)
-        rmsd_pipe_pass_kernel<<<grid, kTileThreads, smem, st>>>(
+        rmsd_tile_pass_kernel<true><<<grid, 2 * kTileThreads, smem, st>>>(
             xyz, traces, n, n_atoms, center, label, distances, labels, row_offset, d_list, ps,
             kScanBlocksCap, cands, out);
     else
-        rmsd_tile_pass_kernel<false><<<grid, kTileThreads, smem, st>>>(
+        rmsd_tile_pass_kernel<false><<<grid, 2 * kTileThreads, smem, st>>>(
             xyz, traces, n, n_atoms, center, label, distances, labels, row_offset, d_list, ps,
             kScanBlocksCap, cands, out);
     MSMB_LAUNCH_CHECK();

@@ -85,8 +85,9 @@ class tICA(BaseEstimator, TransformerMixin):
     """
 
     def __init__(self, n_components=None, lag_time=1, shrinkage=None,
-                 kinetic_mapping=False, commute_mapping=False, engine='auto'):
+                 kinetic_mapping=False, commute_mapping=False, engine='auto', devices=None):
         self.n_components = n_components
+        self.devices = devices
         self.lag_time = lag_time
         self.shrinkage = shrinkage
         self.shrinkage_ = None
@@ -228,7 +229,12 @@ class tICA(BaseEstimator, TransformerMixin):
         """
         self._initialized = False
         check_iter_of_sequences(sequences, max_iter=3)  # input may be lazy
-        self._fit_many(sequences)
+        from .._device import resolve_devices
+        devs = resolve_devices(self.devices)
+        if devs is not None:
+            self._fit_many_on_devices(sequences, devs)
+        else:
+            self._fit_many(sequences)
         if self.n_sequences_ == 0:
             raise ValueError('All sequences were shorter than '
                              'the lag time, %d' % self.lag_time)
@@ -299,6 +305,77 @@ class tICA(BaseEstimator, TransformerMixin):
         flush()
         if state["acc"] is not None:
             self._add_packed(state["acc"].cpu().numpy())       # the one synchronisation of a fit
+
+    def _fit_many_on_devices(self, sequences, devs):
+        """`devices=`: whole sequences are dealt to the GPUs (longest first), one thread per GPU
+        stages and accumulates its share exactly like _fit_many, and the packed float64
+        accumulators are added on the host in device order (the all-reduce of the torchrun path,
+        tica.py:417-422 being a plain sum over sequences)."""
+        import threading
+        import torch
+        from .. import parallel as P
+        good = []
+        for X in sequences:
+            if is_tensor(X):
+                X = X.detach()
+                if X.ndim == 1:
+                    X = X.unsqueeze(0)
+                if X.dtype not in (torch.float32, torch.float64):
+                    X = X.to(torch.float64)
+            else:
+                X = np.atleast_2d(np.asarray(X))
+                if X.dtype not in (np.float32, np.float64):
+                    X = X.astype(np.float64)
+            if X.ndim != 2:
+                raise ValueError('sequences must be a list of sequences')
+            n, d = int(X.shape[0]), int(X.shape[1])
+            if d > n:
+                warnings.warn("The number of features (%d) is greater than the length of the "
+                              "data (%d). The covariance matrix is not guaranteed to be "
+                              "positive definite." % (d, n))
+            self._initialize(d)
+            if d != self.n_features:
+                raise ValueError("sequence has %d features, model has %d" % (d, self.n_features))
+            if not n > self.lag_time:
+                warnings.warn("length of data (%d) is too short for the lag time (%d)"
+                              % (n, self.lag_time))
+                continue
+            good.append(X)
+        if not good:
+            return
+        shares = [sh for sh in P.shard_sequences([int(x.shape[0]) for x in good], len(devs)) if sh]
+        packed, errors = [None] * len(shares), []
+
+        def work(r):
+            try:
+                with torch.cuda.device(devs[r]):
+                    acc, batch, nbytes = None, [], 0
+                    for i in shares[r]:
+                        X = good[i]
+                        b = X.numel() * X.element_size() if is_tensor(X) else X.nbytes
+                        if batch and nbytes + b > self._stage_bytes:
+                            acc = self._accumulate_device(batch, acc=acc)
+                            batch, nbytes = [], 0
+                        batch.append(X)
+                        nbytes += b
+                    if batch:
+                        acc = self._accumulate_device(batch, acc=acc)
+                    packed[r] = acc.cpu().numpy()
+            except BaseException as e:      # noqa: B902
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(r,), name="msmb200-tica-%d" % devs[r])
+                   for r in range(len(shares))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        total = packed[0]
+        for extra in packed[1:]:
+            total = total + extra
+        self._add_packed(total)
 
     def _accumulate_device(self, seqs, acc=None):
         """Run K1 over `seqs` (host arrays are uploaded, device tensors used in

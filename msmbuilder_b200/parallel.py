@@ -41,6 +41,85 @@ def world():
     return 0, 1
 
 
+# ----------------------------------------------------------------------------- communicators
+# The k-centers loops need two collectives on small device blobs: an all-gather of equally sized
+# byte blobs and a SUM all-reduce.  Two back ends provide them:
+#   DistComm    one process per GPU under torchrun (NCCL over NVLink; gloo on CPU in the tests)
+#   ThreadComm  one PROCESS, one Python thread per GPU (`devices=` of the estimators): the blobs are
+#               exchanged with peer copies between two thread barriers.  This is what lets a stock
+#               Pipeline / fit call use every GPU of the box without torchrun.
+class DistComm(object):
+    def __init__(self, group=None):
+        self.group = group
+        self.rank, self.ws = world()
+
+    def all_gather_into(self, out, local):
+        if self.ws == 1:
+            out.copy_(local.reshape(-1))
+            return
+        dist.all_gather_into_tensor(out, local, group=self.group)
+
+    def all_reduce_sum(self, t):
+        if self.ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class ThreadGroup(object):
+    """Shared state of `n` cooperating threads (one per device)."""
+
+    def __init__(self, n):
+        import threading
+        self.n = int(n)
+        self.barrier = threading.Barrier(self.n)
+        self.slots = [None] * self.n
+
+    def comm(self, rank):
+        return ThreadComm(self, rank)
+
+    def abort(self):
+        self.barrier.abort()
+
+
+def _sync_stream(t):
+    if t.is_cuda:
+        torch.cuda.current_stream(t.device).synchronize()
+
+
+class ThreadComm(object):
+    def __init__(self, group, rank):
+        self.g = group
+        self.rank = int(rank)
+        self.ws = group.n
+
+    def all_gather_into(self, out, local):
+        g = self.g
+        if g.n == 1:
+            out.copy_(local.reshape(-1))
+            return
+        _sync_stream(local)                        # my blob is complete before anyone reads it
+        g.slots[self.rank] = local
+        g.barrier.wait()
+        n = local.numel()
+        for r in range(g.n):
+            out[r * n:(r + 1) * n].copy_(g.slots[r].reshape(-1), non_blocking=True)
+        _sync_stream(out)                          # every blob has been read ...
+        g.barrier.wait()                           # ... before its owner may overwrite it
+
+    def all_reduce_sum(self, t):
+        g = self.g
+        if g.n == 1:
+            return
+        _sync_stream(t)
+        g.slots[self.rank] = t
+        g.barrier.wait()
+        total = g.slots[0].to(t.device, copy=True)
+        for r in range(1, g.n):                    # fixed order: every thread gets the same bits
+            total += g.slots[r].to(t.device)
+        _sync_stream(total)
+        g.barrier.wait()
+        t.copy_(total)
+
+
 def _agree_max(values, group=None):
     """Element-wise MAX of a few Python ints over the ranks (device tensor under NCCL, CPU tensor
     under gloo); every rank returns the same list."""
@@ -101,7 +180,7 @@ def select_candidate_host(gathered, n_cand, cand_bytes):
 
 
 def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn, alloc_fn,
-                             group=None, pass_ring=False):
+                             group=None, pass_ring=False, comm=None):
     """Rank-collective Gonzalez loop.
 
     seed_fn(cand)                      fill `cand` with the seed centre on the rank
@@ -116,7 +195,9 @@ def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn
 
     Returns the (k, cand_bytes) ring of chosen centres (slot i = centre i).
     """
-    rank, ws = world()
+    if comm is None:
+        comm = DistComm(group)
+    ws = comm.ws
     k = int(n_clusters)
     ring = alloc_fn((k + 1) * cand_bytes).reshape(k + 1, cand_bytes)
     local = alloc_fn(cand_bytes)
@@ -126,7 +207,7 @@ def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn
         if ws == 1:
             dst.copy_(local)
             return
-        dist.all_gather_into_tensor(gathered, local, group=group)
+        comm.all_gather_into(gathered, local)
         select_fn(gathered, ws, dst)
 
     seed_fn(local)
@@ -140,7 +221,7 @@ def kcenters_fit_distributed(n_clusters, cand_bytes, seed_fn, pass_fn, select_fn
     return ring
 
 
-def lookahead_collectives(group=None):
+def lookahead_collectives(group=None, comm=None):
     """The two collectives of the look-ahead k-centers (_kernels.kcenters_fit_lookahead):
 
     gather_sets(local_set) -> (all_sets, world_size)   ONE all-gather per chain of every rank's
@@ -150,7 +231,9 @@ def lookahead_collectives(group=None):
                                                        all-reduce of the bytes hands it to everyone
 
     Works on whatever device the blobs live on (NCCL: cuda, gloo: cpu)."""
-    _, ws = world()
+    if comm is None:
+        comm = DistComm(group)
+    ws = comm.ws
     gathered = {}
 
     def gather_sets(local_set):
@@ -159,12 +242,12 @@ def lookahead_collectives(group=None):
         if "buf" not in gathered:
             gathered["buf"] = torch.empty(ws * local_set.numel(), dtype=local_set.dtype,
                                           device=local_set.device)
-        dist.all_gather_into_tensor(gathered["buf"], local_set, group=group)
+        comm.all_gather_into(gathered["buf"], local_set)
         return gathered["buf"], ws
 
     def bcast(blob):
         if ws > 1:
-            dist.all_reduce(blob, op=dist.ReduceOp.SUM, group=group)
+            comm.all_reduce_sum(blob)
 
     return gather_sets, bcast
 
@@ -177,18 +260,19 @@ def broadcast_centers(centers, src=0, group=None):
 
 
 def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, traces=None,
-                     group=None, lookahead=True, stats=None):
+                     group=None, lookahead=True, stats=None, comm=None):
     """KCenters over frame shards: `data_local` is this rank's contiguous slice of
     the concatenated frames, starting at global row `row_offset`.
 
     Returns (cluster_ids int64[k] (global indices, device), distances f64[n_local],
     labels i32[n_local], centres ring (k+1, cand_bytes) uint8)."""
     from . import _kernels as K
-    rank, ws = world()
+    if comm is None:
+        comm = DistComm(group)
     # every rank must take the same path: the shape test is a function of (d, dtype, metric) and of
     # the local base address alignment, which FrameStore / torch allocations always satisfy
     if traces is None and lookahead and K.lookahead_supported(data_local, metric):
-        gather_sets, bcast = lookahead_collectives(group=group)
+        gather_sets, bcast = lookahead_collectives(comm=comm)
         ids, rows, distances, labels = K.kcenters_fit_lookahead(
             data_local, n_clusters, metric, seed_global, gather_sets=gather_sets, bcast=bcast,
             row_offset=row_offset, stats=stats)
@@ -218,7 +302,7 @@ def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, tr
         st.run_pass(center_cand, label, out_cand=out, ring=ring)
 
     ring = kcenters_fit_distributed(n_clusters, st.cand_bytes, seed_fn, pass_fn, st.select,
-                                    alloc, group=group, pass_ring=True)
+                                    alloc, comm=comm, pass_ring=True)
     k = int(n_clusters)
     ids = ring[:k, 8:16].contiguous().view(torch.int64).reshape(k)
     return ids, st.distances, st.labels, ring
