@@ -592,10 +592,14 @@ rmsd_scan_kernel(const double *__restrict__ dist, const int *__restrict__ labels
 //   tile warps (kTileWarps)   stage 32 frames with cp.async, every lane forms the float32 M of its
 //                             frame and hands {M, G_x, frame} to its solver warp through a
 //                             double-buffered record in shared memory (mbarrier full / empty);
-//   solver warps (kTileWarps) one per tile warp, no tile of their own: the double Newton iteration,
-//                             the strict running minimum and the arg-max, while the tile warp is
-//                             already copying / summing the next 32 frames.
+//   solver warps (kSolvers per tile warp) no tile of their own: the double Newton iteration (a chain
+//                             of ~400 dependent float64 operations, ~16k cycles per 32 frames: pure
+//                             latency, r2h ncu), the strict running minimum and the arg-max, while
+//                             the tile warp is already copying / summing the next frames.  Records
+//                             go round robin to the tile warp's solvers.
 struct SolveRecord { float M[9]; float Gx; long long f; };          // 48 bytes per lane
+static constexpr int kSolvers = 4;                                  // solver warps per tile warp
+static constexpr int kPassThreads = 32 * kTileWarps * (1 + kSolvers);
 
 __device__ __forceinline__ void mbar_init_(uint64_t *bar, uint32_t count)
 {
@@ -619,7 +623,7 @@ __device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity)
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(2 * kTileThreads)
+__global__ void __launch_bounds__(kPassThreads)
 rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ traces, long long n,
                       int n_atoms, const float *__restrict__ center, int label,
                       double *__restrict__ dist, int *__restrict__ labels, long long row_offset,
@@ -627,8 +631,8 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
                       BlockCandR *__restrict__ block_cands, msmb200_candidate *__restrict__ out)
 {
     extern __shared__ __align__(16) float s_tile[];
-    __shared__ uint64_t s_full[kTileWarps][2], s_empty[kTileWarps][2];
-    __shared__ ArgMax s_warp[kTileWarps];
+    __shared__ uint64_t s_full[kTileWarps][kSolvers], s_empty[kTileWarps][kSolvers];
+    __shared__ ArgMax s_warp[kTileWarps * kSolvers];
     __shared__ bool s_is_last;
     const int n3 = n_atoms * 3;
     const int stride = tile_stride(n_atoms, VEC4);
@@ -636,14 +640,15 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     const int c_pad = (n3 + 3) & ~3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool solver = warp >= kTileWarps;
-    const int pair = solver ? warp - kTileWarps : warp;
+    const int pair = solver ? (warp - kTileWarps) % kTileWarps : warp;     // the tile warp it belongs to
+    const int sk = solver ? (warp - kTileWarps) / kTileWarps : 0;           // which of its solvers
     float *my_tile = s_tile + c_pad + (size_t)pair * 32 * stride;
     SolveRecord *records = reinterpret_cast<SolveRecord *>(s_tile + c_pad + (size_t)kTileWarps * 32 * stride)
-                           + (size_t)pair * 2 * 32;
+                           + (size_t)pair * kSolvers * 32;                 // [solver][lane]
     for (int j = threadIdx.x; j < n3; j += blockDim.x) s_center[j] = center[j];
-    if (threadIdx.x < kTileWarps * 2) {
-        mbar_init_(&s_full[threadIdx.x >> 1][threadIdx.x & 1], 1);
-        mbar_init_(&s_empty[threadIdx.x >> 1][threadIdx.x & 1], 1);
+    if (threadIdx.x < kTileWarps * kSolvers) {
+        mbar_init_(&s_full[threadIdx.x / kSolvers][threadIdx.x % kSolvers], 1);
+        mbar_init_(&s_empty[threadIdx.x / kSolvers][threadIdx.x % kSolvers], 1);
     }
     __syncthreads();
     const float Gc = center[n3];
@@ -653,7 +658,7 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     if (!solver) {
         // ------------------------------------------------ tile warp: copy, float32 sums, hand over
         long long it = 0;
-        for (long long ch = (long long)blockIdx.x * kTileWarps + pair; ; ch += (long long)gridDim.x * kTileWarps, ++it) {
+        for (long long ch = (long long)blockIdx.x * kTileWarps + pair; ; ch += (long long)gridDim.x * kTileWarps) {
             const bool more = ch < n_chunks;
             long long f = -2;                                  // -2: no more chunks (every lane)
             float M[9];
@@ -672,25 +677,27 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
                 tile_copy_wait();
                 if (f >= 0) inner_products_simd4<VEC4>(my_tile + (size_t)lane * stride, s_center, n_atoms, M);
             }
-            const int b = (int)(it & 1);
-            mbar_wait_(&s_empty[pair][b], (uint32_t)(((it >> 1) & 1) ^ 1));
-            SolveRecord &r = records[b * 32 + lane];
+            // round robin over this warp's solvers; the end marker goes to every one of them
+            for (int rep = 0; rep < (more ? 1 : kSolvers); ++rep, ++it) {
+                const int k = (int)(it % kSolvers);
+                mbar_wait_(&s_empty[pair][k], (uint32_t)(((it / kSolvers) & 1) ^ 1));
+                SolveRecord &r = records[k * 32 + lane];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) r.M[q] = M[q];
-            r.Gx = Gx;
-            r.f = f;
-            __syncwarp();
-            if (lane == 0) mbar_arrive_(&s_full[pair][b]);
+                for (int q = 0; q < 9; ++q) r.M[q] = M[q];
+                r.Gx = Gx;
+                r.f = f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_(&s_full[pair][k]);
+            }
             if (!more) break;
         }
     } else {
         // ------------------------------------------------ solver warp: Newton, minimum, arg-max
         for (long long it = 0; ; ++it) {
-            const int b = (int)(it & 1);
-            mbar_wait_(&s_full[pair][b], (uint32_t)((it >> 1) & 1));
-            const SolveRecord r = records[b * 32 + lane];
+            mbar_wait_(&s_full[pair][sk], (uint32_t)(it & 1));
+            const SolveRecord r = records[sk * 32 + lane];
             __syncwarp();
-            if (lane == 0) mbar_arrive_(&s_empty[pair][b]);
+            if (lane == 0) mbar_arrive_(&s_empty[pair][sk]);
             if (r.f == -2) break;
             if (r.f >= 0) {
                 double cur = __ldcg(dist + r.f);
@@ -704,13 +711,13 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
             }
         }
         best = argmax_warp(best);
-        if (lane == 0) s_warp[pair] = best;
+        if (lane == 0) s_warp[warp - kTileWarps] = best;
     }
     __syncthreads();
     BlockCandR *mine = block_cands + scan_blocks_cap;          // the scan kernel's slots come first
     if (threadIdx.x == 0) {
         ArgMax b = s_warp[0];
-        for (int w = 1; w < kTileWarps; ++w) b = argmax_merge(b, s_warp[w]);
+        for (int w = 1; w < kTileWarps * kSolvers; ++w) b = argmax_merge(b, s_warp[w]);
         mine[blockIdx.x].v = b.v;
         mine[blockIdx.x].i = b.i;
         __threadfence();
@@ -731,16 +738,12 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     }
     w = argmax_warp(w);
     __syncthreads();
-    if (lane == 0 && warp < kTileWarps) s_warp[warp] = w;
-    __syncthreads();
-    // warps kTileWarps .. 2 kTileWarps - 1 hold the other half of the candidates
-    __shared__ ArgMax s_warp2[kTileWarps];
-    if (lane == 0 && warp >= kTileWarps) s_warp2[warp - kTileWarps] = w;
+    __shared__ ArgMax s_fin[kTileWarps * (1 + kSolvers)];
+    if (lane == 0) s_fin[warp] = w;
     __syncthreads();
     if (threadIdx.x == 0) {
-        ArgMax b = s_warp[0];
-        for (int q = 1; q < kTileWarps; ++q) b = argmax_merge(b, s_warp[q]);
-        for (int q = 0; q < kTileWarps; ++q) b = argmax_merge(b, s_warp2[q]);
+        ArgMax b = s_fin[0];
+        for (int q = 1; q < kTileWarps * (1 + kSolvers); ++q) b = argmax_merge(b, s_fin[q]);
         if (b.i == 0x7fffffffffffffffLL) b.i = 0;
         s_warp[0] = b;
         out->value = b.v;
@@ -904,7 +907,7 @@ static int rmsd_pass_tiles(const float *xyz, const float *traces, int64_t n, int
     double *dcc = reinterpret_cast<double *>(w + 64 + sizeof(BlockCandR) * (size_t)(kScanBlocksCap + 2 * 1024));
     int *list = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(dcc) + sizeof(double) * (size_t)(n_prev + 1));
     const bool vec4 = (n_atoms & 3) == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15u) == 0;
-    const size_t smem = tile_smem_bytes(n_atoms, vec4, true) + sizeof(SolveRecord) * (size_t)kTileWarps * 2 * 32;
+    const size_t smem = tile_smem_bytes(n_atoms, vec4, true) + sizeof(SolveRecord) * (size_t)kTileWarps * kSolvers * 32;
     static bool attr_done[2] = {false, false};
     if (!attr_done[vec4 ? 1 : 0]) {
         if (vec4) MSMB_CUDA(cudaFuncSetAttribute(rmsd_tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -927,11 +930,11 @@ static int rmsd_pass_tiles(const float *xyz, const float *traces, int64_t n, int
     }
     const int grid = tile_grid(n, smem);
     if (vec4)
-        rmsd_tile_pass_kernel<true><<<grid, 2 * kTileThreads, smem, st>>>(
+        rmsd_tile_pass_kernel<true><<<grid, kPassThreads, smem, st>>>(
             xyz, traces, n, n_atoms, center, label, distances, labels, row_offset, d_list, ps,
             kScanBlocksCap, cands, out);
     else
-        rmsd_tile_pass_kernel<false><<<grid, 2 * kTileThreads, smem, st>>>(
+        rmsd_tile_pass_kernel<false><<<grid, kPassThreads, smem, st>>>(
             xyz, traces, n, n_atoms, center, label, distances, labels, row_offset, d_list, ps,
             kScanBlocksCap, cands, out);
     MSMB_LAUNCH_CHECK();

@@ -60,11 +60,18 @@ class tICA(BaseEstimator, TransformerMixin):
         Scale the projection by regularised timescales (commute map).
     engine : {'auto', 'simt_f64', 'umma_3xf16', 'umma_6xbf16', 'umma_3xbf16', 'umma_3xtf32', 'umma_tf32'}, default='auto'
         Which device kernel accumulates the covariance matrices.  'auto' uses the
-        tcgen05 tensor-core kernel with the error-compensated 3-product fp16 split
-        of the per-feature power-of-two scaled frames (~2^-22 per product; a value
-        outside fp16's range makes the call redo itself as 'umma_6xbf16', ~2^-24,
-        full float32 range) when the shape allows it and the float64 CUDA-core
-        kernel otherwise; 'umma_3xbf16' is ~2^-16 per product, unbiased.
+        tcgen05 tensor-core kernel with the error-compensated fp16 split of the
+        per-feature power-of-two scaled frames (~2^-22 per product) when the shape
+        allows it (float32, n_features a multiple of 32 between 64 and 256) and the
+        float64 CUDA-core kernel otherwise.  A value more than 2^6 times the largest
+        magnitude of the scale sample (1024 frames spread over the call), or a
+        non-finite one, makes the call redo itself on the stream with the float64
+        kernel, so outliers cost time, not accuracy.  'umma_6xbf16' is ~2^-24 per
+        product over the full float32 range, 'umma_3xbf16' ~2^-16, unbiased.
+    devices : None, 'all' or list of CUDA ordinals, default=None
+        GPUs ``fit`` deals whole sequences to from ONE process (a thread per GPU,
+        the packed float64 accumulators added on the host): the whole box without
+        torchrun.  None = the current device.
 
     Attributes
     ----------
