@@ -528,7 +528,10 @@ def run_ours(args):
     # tensor peak for the engine's MMA kind: bf16 = measured sustained cuBLAS bf16; tf32 = half of it
     is_bf16 = args.engine in ("auto", "umma_3xf16", "umma_3xbf16", "umma_6xbf16")   # kind::f16 MMAs
     tf32_peak = peaks["bf16_sustained"] if is_bf16 else peaks["bf16_sustained"] / 2.0
-    issued = {"auto": 3, "umma_3xf16": 3, "umma_6xbf16": 6, "umma_3xbf16": 3, "umma_3xtf32": 3,
+    # tensor-core products issued per algorithmic product: the second-generation fp16 engine issues 5
+    # full-size UMMAs per K step for the 2 algorithmic ones (C_tau: h b + h bl + l b; C_00 = G + G^T
+    # with G = h (h/2) + h l), the bf16 engines 3 or 6 per matrix
+    issued = {"auto": 2.5, "umma_3xf16": 2.5, "umma_6xbf16": 6, "umma_3xbf16": 3, "umma_3xtf32": 3,
               "umma_tf32": 1}.get(args.engine, 1)
     tica_ach = flops_tica / tica_s / 1e12
     roof_k2 = {"kernel": "kcenters_multi_pass_kernel" if pass_ms else "kcenters_pass_fast_kernel",
@@ -545,6 +548,11 @@ def run_ours(args):
                                                    "; TF32 dense taken as 1/2 of the measured sustained bf16"),
                "algorithmic_flops_per_launch": flops_tica, "ms_per_launch": tica_s * 1e3,
                "issued_mma_products": issued, "issued_frac": issued * tica_ach / tf32_peak,
+               "note": "a kind::f16 UMMA M256 x N256 x K16 from shared-memory operands takes 167.6 cycles on "
+                       "this part, not the 128 of the nominal rate (profiles/r2e_probe5_mma_shapes.log): "
+                       "issued_frac tops out at ~0.76 of a peak derived from the nominal rate; the kernel "
+                       "itself is bound by shared-memory bandwidth (operand reads of the UMMAs + conversion "
+                       "traffic, DESIGN.md section 4)",
                "share_of_step": tica_s / (ms_per_step / 1e3)}
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/ncu_traffic.json),
     # only when this run has the captured shape; otherwise null
@@ -559,7 +567,7 @@ def run_ours(args):
             elif args.no_lookahead:
                 roof_k2["traffic"] = tr.get("kcenters_pass_fast_kernel")
             if args.engine in ("auto", "umma_3xf16"):
-                roof_k1["traffic"] = tr.get("tica_umma_kernel_f16")
+                roof_k1["traffic"] = tr.get("tica_umma_v2_kernel", tr.get("tica_umma_kernel_f16"))
             roof_k1["traffic_source"] = roof_k2["traffic_source"] = tr["source"]
     except (OSError, KeyError, ValueError):
         pass
@@ -569,8 +577,8 @@ def run_ours(args):
         "metric": "frames/sec tICA fit + KCenters assign", "value": value, "unit": "frames/s",
         "n_gpus": ws, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": {"auto": "f32 in; fp16x3 split tensor-core products of the scaled frames (~2^-22), fp32 TMEM slabs -> f64 (tICA); f64 distances (KCenters)",
-                  "umma_3xf16": "f32 in; fp16x3 split tensor-core products (~2^-22), fp32 TMEM slabs -> f64; f64 distances",
+        "dtype": {"auto": "f32 in; fp16 h+l split tensor-core products of the scaled frames (~2^-22), fp32 TMEM slabs -> float-float -> f64 (tICA); f64 distances (KCenters)",
+                  "umma_3xf16": "f32 in; fp16 h+l split tensor-core products (~2^-22), fp32 TMEM slabs -> float-float -> f64; f64 distances",
                   "umma_6xbf16": "f32 in; bf16x6 split tensor-core products, fp32 TMEM slabs -> f64; f64 distances",
                   "umma_3xbf16": "f32 in; bf16x3 split tensor-core products (~2^-16), fp32 TMEM slabs -> f64; f64 distances",
                   "umma_3xtf32": "f32 in; tf32x3 split tensor-core products (~2^-21), fp32 TMEM slabs -> f64; f64 distances",

@@ -622,6 +622,23 @@ __device__ __forceinline__ void mbar_wait_(uint64_t *bar, uint32_t parity)
         "DONE_%=:\n\t}" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
+// a waiting solver warp must not compete for issue slots with the tile warp of its scheduler: poll,
+// then sleep (r2j ncu: 136 M spins of the plain try_wait loop took 60 % of all stall samples and the
+// four solvers per tile warp bought nothing)
+__device__ __forceinline__ void mbar_wait_sleep_(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity), "r"(2000u) : "memory");
+        if (ok) break;
+        __nanosleep(500);
+    }
+}
+
 template <bool VEC4>
 __global__ void __launch_bounds__(kPassThreads)
 rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ traces, long long n,
@@ -694,7 +711,7 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     } else {
         // ------------------------------------------------ solver warp: Newton, minimum, arg-max
         for (long long it = 0; ; ++it) {
-            mbar_wait_(&s_full[pair][sk], (uint32_t)(it & 1));
+            mbar_wait_sleep_(&s_full[pair][sk], (uint32_t)(it & 1));
             const SolveRecord r = records[sk * 32 + lane];
             __syncwarp();
             if (lane == 0) mbar_arrive_(&s_empty[pair][sk]);

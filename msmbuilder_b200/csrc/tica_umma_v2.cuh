@@ -515,12 +515,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
             auto convert_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
+                {
+                    // all four units' loads first (32 in flight per thread: with two converter warps
+                    // per scheduler the arithmetic is latency bound otherwise), then the arithmetic
+                    constexpr int k0 = 0;
+                    float v[U][8];
 #pragma unroll
-                for (int k0 = 0; k0 < U; k0 += 2) {
-                    // two units at a time: 16 loads in flight, then the arithmetic
-                    float v[2][8];
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
+                    for (int kk = 0; kk < U; ++kk) {
                         const int k = k0 + kk;
                         if (!u_on[k]) continue;
                         const uint32_t b = rawst + u_src[k];
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                         v[kk][7] = lds_f32<7 * 128>(b ^ (7u << 4));
                     }
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
+                    for (int kk = 0; kk < U; ++kk) {
                         const int k = k0 + kk;
                         if (!u_on[k]) continue;
                         const uint64_t sc2 = f2_pack(u_sc[k], u_sc[k]);
