@@ -499,6 +499,13 @@ __device__ __forceinline__ void tile_copy_frame(float *dst, const float *__restr
                          :: "r"((uint32_t)__cvta_generic_to_shared(dst + c)), "l"(src + c) : "memory");
     }
 }
+// one frame = one TMA bulk copy (16-byte aligned, a multiple of 16 bytes), completion on an mbarrier
+__device__ __forceinline__ void tile_bulk_frame(float *dst, const float *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+                    "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void tile_copy_wait()
 {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -649,6 +656,7 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
 {
     extern __shared__ __align__(16) float s_tile[];
     __shared__ uint64_t s_full[kTileWarps][kSolvers], s_empty[kTileWarps][kSolvers];
+    __shared__ uint64_t s_landed[kTileWarps];                  // the tile warp's frames have arrived (TMA bytes)
     __shared__ ArgMax s_warp[kTileWarps * kSolvers];
     __shared__ bool s_is_last;
     const int n3 = n_atoms * 3;
@@ -666,6 +674,7 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     if (threadIdx.x < kTileWarps * kSolvers) {
         mbar_init_(&s_full[threadIdx.x / kSolvers][threadIdx.x % kSolvers], 1);
         mbar_init_(&s_empty[threadIdx.x / kSolvers][threadIdx.x % kSolvers], 1);
+        if (threadIdx.x < kTileWarps) mbar_init_(&s_landed[threadIdx.x], 1);
     }
     __syncthreads();
     const float Gc = center[n3];
@@ -675,6 +684,7 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
     if (!solver) {
         // ------------------------------------------------ tile warp: copy, float32 sums, hand over
         long long it = 0;
+        uint32_t landed_phase = 0;
         for (long long ch = (long long)blockIdx.x * kTileWarps + pair; ; ch += (long long)gridDim.x * kTileWarps) {
             const bool more = ch < n_chunks;
             long long f = -2;                                  // -2: no more chunks (every lane)
@@ -685,13 +695,30 @@ rmsd_tile_pass_kernel(const float *__restrict__ xyz, const float *__restrict__ t
             if (more) {
                 const long long e = ch * 32 + lane;
                 f = e < total ? (list ? (long long)list[e] : e) : -1;
-                for (int j = 0; j < 32; ++j) {
-                    const long long fj = __shfl_sync(0xffffffffu, f, j);
-                    if (fj < 0) break;
-                    tile_copy_frame<VEC4>(my_tile + (size_t)j * stride, xyz + fj * (long long)n3, n3, lane);
+                if (VEC4) {
+                    // every lane fetches its own frame with ONE bulk copy (the per-chunk cp.async loop
+                    // was half of the warp's instructions, and one warp per scheduler is issue bound)
+                    const uint32_t bytes = (uint32_t)n3 * 4u;
+                    const unsigned have = __ballot_sync(0xffffffffu, f >= 0);
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                     :: "r"((uint32_t)__cvta_generic_to_shared(&s_landed[pair])),
+                                        "r"(bytes * (uint32_t)__popc(have)) : "memory");
+                    __syncwarp();
+                    if (f >= 0)
+                        tile_bulk_frame(my_tile + (size_t)lane * stride, xyz + f * (long long)n3, bytes, &s_landed[pair]);
+                    if (f >= 0) Gx = traces[f];
+                    mbar_wait_(&s_landed[pair], landed_phase);
+                    landed_phase ^= 1;
+                } else {
+                    for (int j = 0; j < 32; ++j) {
+                        const long long fj = __shfl_sync(0xffffffffu, f, j);
+                        if (fj < 0) break;
+                        tile_copy_frame<VEC4>(my_tile + (size_t)j * stride, xyz + fj * (long long)n3, n3, lane);
+                    }
+                    if (f >= 0) Gx = traces[f];
+                    tile_copy_wait();
                 }
-                if (f >= 0) Gx = traces[f];
-                tile_copy_wait();
                 if (f >= 0) inner_products_simd4<VEC4>(my_tile + (size_t)lane * stride, s_center, n_atoms, M);
             }
             // round robin over this warp's solvers; the end marker goes to every one of them

@@ -97,6 +97,24 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return __shfl_sync(0xffffffffu, ok, 0);          // one answer for the whole warp
 }
+// wait of a warp that has nothing else to do for thousands of cycles (drain warps, the TMA producer):
+// poll with a suspend hint, then sleep -- a plain try_wait loop issues BRA / SYNCS / YIELD around the
+// clock and takes issue slots from the converters of the same scheduler (r2i profile: 5.7 G of the
+// kernel's 10.7 G warp instructions were such spins)
+template <bool SLEEP = true>
+__device__ __forceinline__ void mbar_wait_idle(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity), "r"(1000u) : "memory");
+        if (ok) break;
+        if (SLEEP) __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void mbar_arrive_local(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 const int row0 = (int)(t - P.tile_prefix[s]) * UM_KT;
                 int valid = P.seq_pairs[s] - row0;
                 if (valid > UM_KT) valid = UM_KT;
-                mbar_wait(&ctl->raw_empty[stage], phase ^ 1);
+                mbar_wait_idle<false>(&ctl->raw_empty[stage], phase ^ 1);   // hint only: the TMA issue is latency critical
                 ctl->valid_rows[stage] = valid;
                 mbar_expect_tx(&ctl->raw_full[stage], 2 * P.box_blocks * (UM_KT * 128));
                 unsigned char *st = raw_ring + stage * UM_RAW_BYTES;
@@ -515,13 +533,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
             auto convert_tile = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
-                {
-                    // all four units' loads first (32 in flight per thread: with two converter warps
-                    // per scheduler the arithmetic is latency bound otherwise), then the arithmetic
-                    constexpr int k0 = 0;
-                    float v[U][8];
 #pragma unroll
-                    for (int kk = 0; kk < U; ++kk) {
+                for (int k0 = 0; k0 < U; k0 += 2) {
+                    // two units at a time: 16 loads in flight, then the arithmetic (all four at once
+                    // spilled and was 40 % slower, r2k)
+                    float v[2][8];
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
                         const int k = k0 + kk;
                         if (!u_on[k]) continue;
                         const uint32_t b = rawst + u_src[k];
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                         v[kk][7] = lds_f32<7 * 128>(b ^ (7u << 4));
                     }
 #pragma unroll
-                    for (int kk = 0; kk < U; ++kk) {
+                    for (int kk = 0; kk < 2; ++kk) {
                         const int k = k0 + kk;
                         if (!u_on[k]) continue;
                         const uint64_t sc2 = f2_pack(u_sc[k], u_sc[k]);
@@ -661,7 +679,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             if (e == 0x7fffffff) break;
             const bool last = e == my_tiles - 1;
             const long long c0 = dbg_on ? clock64() : 0;
-            mbar_wait(&ctl->acc_full[q], full_ph[q]);
+            mbar_wait_idle(&ctl->acc_full[q], full_ph[q]);
             full_ph[q] ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;");
             const long long c1 = dbg_on ? clock64() : 0;
