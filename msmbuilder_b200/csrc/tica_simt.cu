@@ -26,20 +26,24 @@ static constexpr int kChunk = 4096;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-tica_outer_kernel(const TicaItem *__restrict__ items, int D, long long ld, int lag,
+tica_outer_kernel(const TicaItem *__restrict__ items, int n_items, int D, long long ld, int lag,
                   double *__restrict__ acc, const int *__restrict__ run_if)
 {
     // rescue launch of the tensor-core engine: uniform over the grid
     if (run_if != nullptr && *reinterpret_cast<const volatile int *>(run_if) == 0) return;
     __shared__ double sA0[RS][TS], sB0[RS][TS], sAt[RS][TS], sBt[RS][TS];
-    const TicaItem it = items[blockIdx.x];
-    const T *X = reinterpret_cast<const T *>(it.base);
     const int ci = blockIdx.z * TS;   // row block of the output (features i)
     const int cj = blockIdx.y * TS;   // col block of the output (features j)
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
     double c_tau[4][4] = {}, c_00[4][4] = {}, c_tt[4][4] = {};
 
+    // a block walks over items blockIdx.x, blockIdx.x + gridDim.x, ... and adds its sums once at the
+    // end: the grid stays a few blocks per SM whatever the number of frames (the guarded rescue
+    // launch of the tensor-core engine then costs microseconds, not the 0.5 ms of 200k empty blocks)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const TicaItem it = items[item];
+    const T *X = reinterpret_cast<const T *>(it.base);
     for (int r0 = 0; r0 < it.count; r0 += RS) {
         // stage RS rows x 64 columns of the four panels, widening to double
         for (int e = threadIdx.x; e < RS * TS; e += 256) {
@@ -80,6 +84,7 @@ tica_outer_kernel(const TicaItem *__restrict__ items, int D, long long ld, int l
                 }
         }
         __syncthreads();
+    }
     }
 
     const size_t DD = (size_t)D * D;
@@ -179,13 +184,17 @@ int tica_simt_launch(const void *d_items, size_t n_items, int D, int64_t ld, int
     if (n_items == 0) return MSMB200_OK;
     const TicaItem *items = reinterpret_cast<const TicaItem *>(d_items);
     const int tiles = (D + TS - 1) / TS;
-    dim3 grid((unsigned)n_items, tiles, tiles);
+    // ~4 resident blocks of this kernel per SM (36 KB of shared memory each)
+    size_t gx = ((size_t)sm_count() * 4 + (size_t)tiles * tiles - 1) / ((size_t)tiles * tiles);
+    if (gx > n_items) gx = n_items;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, tiles, tiles);
     if (dtype == MSMB200_F64) {
-        tica_outer_kernel<double><<<grid, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
+        tica_outer_kernel<double><<<grid, 256, 0, st>>>(items, (int)n_items, D, ld, lag, acc, run_if);
         MSMB_LAUNCH_CHECK();
         tica_sums_kernel<double><<<(unsigned)n_items, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
     } else {
-        tica_outer_kernel<float><<<grid, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
+        tica_outer_kernel<float><<<grid, 256, 0, st>>>(items, (int)n_items, D, ld, lag, acc, run_if);
         MSMB_LAUNCH_CHECK();
         tica_sums_kernel<float><<<(unsigned)n_items, 256, 0, st>>>(items, D, ld, lag, acc, run_if);
     }

@@ -531,8 +531,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const int valid = ctl->valid_rows[stage];
             const uint32_t rawst = raw_s + (uint32_t)stage * UM_RAW_BYTES;
             const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
-            auto convert_tile = [&](auto full_tag) {
+            // FAST: all four feature blocks exist (D = 256 per pair / 128 per single CTA): every warp has
+            // four units, the first two of operand 0 and the last two of operand 1 -- known at compile
+            // time, so the unit loop carries no branch and the loads of two units are in flight
+            // together (with the runtime `continue`s each unit waited for its own 8 loads: the first
+            // FFMA2 after the loads was the converters' top stall, r2i profile)
+            auto convert_tile = [&](auto full_tag, auto fast_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
+                constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
                 for (int k0 = 0; k0 < U; k0 += 2) {
                     // two units at a time: 16 loads in flight, then the arithmetic (all four at once
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
                         const int k = k0 + kk;
-                        if (!u_on[k]) continue;
+                        if (!FAST && !u_on[k]) continue;
                         const uint32_t b = rawst + u_src[k];
                         v[kk][0] = lds_f32<0 * 128>(b);
                         v[kk][1] = lds_f32<1 * 128>(b ^ (1u << 4));
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
                         const int k = k0 + kk;
-                        if (!u_on[k]) continue;
+                        if (!FAST && !u_on[k]) continue;
                         const uint64_t sc2 = f2_pack(u_sc[k], u_sc[k]);
                         const uint64_t nsh2 = f2_pack(u_nsh[k], u_nsh[k]);
                         uint32_t hw[4], lw[4];
@@ -592,7 +598,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                             asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
                         }
                         const uint32_t dst = st + u_dst[k];
-                        if (u_a[k]) {
+                        if (FAST ? (k < 2) : u_a[k]) {
                             sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // a
                             sts_v4<(V2_T_AL - V2_T_A) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // al
                             // h / 2 (one exact fp16 multiply per pair): the second factor of the G product
@@ -617,8 +623,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 }
             };
             if (P.dbg_mode & 1) { /* timing experiment: no conversion traffic */ }
-            else if (valid == UM_KT) convert_tile(std::true_type());
-            else convert_tile(std::false_type());
+            else if (nfb == 4) {
+                if (valid == UM_KT) convert_tile(std::true_type(), std::true_type());
+                else convert_tile(std::false_type(), std::true_type());
+            } else {
+                if (valid == UM_KT) convert_tile(std::true_type(), std::false_type());
+                else convert_tile(std::false_type(), std::false_type());
+            }
             long long q3 = dbg_on ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
