@@ -536,11 +536,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             // time, so the unit loop carries no branch and the loads of two units are in flight
             // together (with the runtime `continue`s each unit waited for its own 8 loads: the first
             // FFMA2 after the loads was the converters' top stall, r2i profile)
+            // (two feature blocks, D = 64: two units per warp, one of each operand -- the same trick)
             auto convert_tile = [&](auto full_tag, auto fast_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
-                constexpr bool FAST = decltype(fast_tag)::value;
+                constexpr int NU = decltype(fast_tag)::value;       // 0: runtime unit table; 4 or 2: static
+                constexpr bool FAST = NU != 0;
 #pragma unroll
-                for (int k0 = 0; k0 < U; k0 += 2) {
+                for (int k0 = 0; k0 < (FAST ? NU : U); k0 += 2) {
                     // two units at a time: 16 loads in flight, then the arithmetic (all four at once
                     // spilled and was 40 % slower, r2k)
                     float v[2][8];
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                             asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
                         }
                         const uint32_t dst = st + u_dst[k];
-                        if (FAST ? (k < 2) : u_a[k]) {
+                        if (FAST ? (k < NU / 2) : u_a[k]) {
                             sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);                            // a
                             sts_v4<(V2_T_AL - V2_T_A) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);  // al
                             // h / 2 (one exact fp16 multiply per pair): the second factor of the G product
@@ -624,11 +626,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             };
             if (P.dbg_mode & 1) { /* timing experiment: no conversion traffic */ }
             else if (nfb == 4) {
-                if (valid == UM_KT) convert_tile(std::true_type(), std::true_type());
-                else convert_tile(std::false_type(), std::true_type());
+                if (valid == UM_KT) convert_tile(std::true_type(), std::integral_constant<int, 4>());
+                else convert_tile(std::false_type(), std::integral_constant<int, 4>());
+            } else if (nfb == 2) {
+                if (valid == UM_KT) convert_tile(std::true_type(), std::integral_constant<int, 2>());
+                else convert_tile(std::false_type(), std::integral_constant<int, 2>());
             } else {
-                if (valid == UM_KT) convert_tile(std::true_type(), std::false_type());
-                else convert_tile(std::false_type(), std::false_type());
+                if (valid == UM_KT) convert_tile(std::true_type(), std::integral_constant<int, 0>());
+                else convert_tile(std::false_type(), std::integral_constant<int, 0>());
             }
             long long q3 = dbg_on ? clock64() : 0;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
