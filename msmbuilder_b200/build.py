@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libmsmb200.so")
-SOURCES = ["lib.cu", "dist_kernels.cu", "kcenters_lookahead.cu", "tica_simt.cu", "tica_umma.cu", "rmsd.cu",
+SOURCES = ["lib.cu", "dist_kernels.cu", "kcenters_lookahead.cu", "tica_simt.cu", "tica_umma.cu", "assign_umma.cu", "rmsd.cu",
            "scan_kernels.cu", "kmedoids_host.cpp"]
 HEADERS = ["common.cuh", "tica_umma_v2.cuh", os.path.join("..", "..", "include", "msmb200.h")]
 

@@ -15,6 +15,12 @@
 #include "common.cuh"
 
 namespace msmb {
+// K3 filter on the tensor cores (assign_umma.cu)
+bool assign_umma_supported(int64_t n_out, int d, int64_t ld, int k, const void *X, bool has_rows);
+int assign_umma_filter(const float *X, int64_t n, int d, int64_t ld, const float *Y, int k,
+                       int32_t *labels, int *amb_list, int *amb_count, cudaStream_t st);
+}
+namespace msmb {
 
 static constexpr int kThreads = 256;
 
@@ -775,11 +781,18 @@ extern "C" int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t l
         const int sq = metric == MSMB200_SQEUCLIDEAN;
         const float margin = 4.0f * (float)(d + 4) * 5.9604645e-8f;     // 4 (d+4) 2^-24
         MSMB_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), st));
-        const long long blocks = (n_out + AF_TR - 1) / AF_TR;
-        assign_filter_kernel<<<(unsigned)blocks, 256, 0, st>>>(
-            (const float *)X, n_out, d, ld, (const float *)Y, k, (const long long *)rows, margin,
-            labels, amb_list, amb_count);
-        MSMB_LAUNCH_CHECK();
+        if (assign_umma_supported(n_out, d, ld, k, X, rows != nullptr)) {
+            // tensor-core filter (assign_umma.cu): same contract -- labels + ambiguity list
+            const int rc = assign_umma_filter((const float *)X, n_out, d, ld, (const float *)Y, k, labels,
+                                              amb_list, amb_count, st);
+            if (rc != MSMB200_OK) return rc;
+        } else {
+            const long long blocks = (n_out + AF_TR - 1) / AF_TR;
+            assign_filter_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+                (const float *)X, n_out, d, ld, (const float *)Y, k, (const long long *)rows, margin,
+                labels, amb_list, amb_count);
+            MSMB_LAUNCH_CHECK();
+        }
         const int G = lanes_per_row(d, 1, false);
         assign_refine_kernel<<<sm_count() * 4, kThreads, 0, st>>>(
             (const float *)X, d, ld, (const float *)Y, k, (const long long *)rows, amb_list,

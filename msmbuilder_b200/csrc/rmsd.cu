@@ -952,11 +952,14 @@ static int rmsd_pass_tiles(const float *xyz, const float *traces, int64_t n, int
     int *list = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(dcc) + sizeof(double) * (size_t)(n_prev + 1));
     const bool vec4 = (n_atoms & 3) == 0 && (reinterpret_cast<uintptr_t>(xyz) & 15u) == 0;
     const size_t smem = tile_smem_bytes(n_atoms, vec4, true) + sizeof(SolveRecord) * (size_t)kTileWarps * kSolvers * 32;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[vec4 ? 1 : 0]) {
+    // function attributes belong to a device: the threads of a multi-GPU fit each set their own
+    static bool attr_done[64][2] = {};
+    int dev = 0;
+    MSMB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev][vec4 ? 1 : 0]) {
         if (vec4) MSMB_CUDA(cudaFuncSetAttribute(rmsd_tile_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         else MSMB_CUDA(cudaFuncSetAttribute(rmsd_tile_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done[vec4 ? 1 : 0] = true;
+        if (dev >= 0 && dev < 64) attr_done[dev][vec4 ? 1 : 0] = true;
     }
     const int *d_list = nullptr;
     if (prune) {

@@ -78,3 +78,38 @@ def test_large_rows_and_ragged_widths():
         X = rs.randn(5000, d).astype(np.float32)
         y = rs.randn(d).astype(np.float32)
         np.testing.assert_allclose(ld.dist(X, y, "euclidean"), lo.dist(X, y, "euclidean"), rtol=RTOL)
+
+
+@pytest.mark.parametrize("n,d,k", [(20000, 16, 500), (9000, 64, 100), (6000, 12, 37), (5000, 128, 180),
+                                   (4100, 256, 33), (12000, 8, 2)])
+def test_tensor_core_filter_labels_equal_exact_engine(n, d, k, monkeypatch):
+    # K3 on tcgen05 (assign_umma.cu, n >= 4096 frames without a row gather): labels must be those of the
+    # float64 scan (MSMB200_ASSIGN_EXACT) -- ties, duplicates and badly scaled features included
+    from msmbuilder_b200 import libdistance as ld
+    rs = np.random.RandomState(n + d + k)
+    X = (rs.randn(n, d) * 10.0 ** rs.uniform(-2, 2, size=d)).astype(np.float32)
+    Y = X[rs.choice(n, k, replace=False)].copy()
+    Y[k // 2] = Y[0]                                   # duplicate centre: lowest index wins
+    X[::7] = np.round(X[::7])                          # lattice points: exact ties between centres
+    Y[1::5] = np.round(Y[1::5])
+    labels, inertia = ld.assign_nearest(X, Y, "euclidean")
+    monkeypatch.setenv("MSMB200_ASSIGN_EXACT", "1")
+    ref_labels, ref_inertia = ld.assign_nearest(X, Y, "euclidean")
+    np.testing.assert_array_equal(labels, ref_labels)
+    assert abs(inertia - ref_inertia) <= 1e-12 * abs(ref_inertia)
+    monkeypatch.delenv("MSMB200_ASSIGN_EXACT")
+    monkeypatch.setenv("MSMB200_ASSIGN_SIMT", "1")
+    simt_labels, _ = ld.assign_nearest(X, Y, "sqeuclidean")
+    np.testing.assert_array_equal(simt_labels, ref_labels)
+
+
+def test_tensor_core_filter_vs_reference_cpp():
+    # against the compiled reference itself (oracle/_ref) on a size it finishes quickly
+    from msmbuilder_b200 import libdistance as ld
+    rs = np.random.RandomState(5)
+    X = rs.randn(8192, 16).astype(np.float32)
+    Y = rs.randn(64, 16).astype(np.float32)
+    labels, inertia = ld.assign_nearest(X, Y, "euclidean")
+    ref_labels, ref_inertia = lo.assign_nearest(X, Y, "euclidean")
+    np.testing.assert_array_equal(labels, ref_labels)
+    assert abs(inertia - ref_inertia) <= 1e-11 * abs(ref_inertia)
