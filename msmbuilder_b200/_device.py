@@ -1,6 +1,8 @@
 """Device-memory plumbing (PyTorch is used for allocation, streams and copies only)."""
 import ctypes
 
+import os
+
 import numpy as np
 import torch
 
@@ -70,8 +72,10 @@ class HostUploader(object):
     tica.py:401-403 both start from them)."""
 
     CHUNK = 32 << 20
-    SLOTS = 8
-    THREADS = 4
+    SLOTS = 12
+    # one host thread copies ~10 GB/s into the pinned ring: 4 threads capped the upload at 41 GB/s of
+    # the box's 55 GB/s pinned H2D rate (r2o bench e2e); leave a few cores to the caller
+    THREADS = max(4, min(8, (os.cpu_count() or 8) - 4))
 
     def __init__(self):
         self._pinned = None

@@ -38,7 +38,8 @@ namespace msmb {
 constexpr int V2_TILE = UM_KT * UM_F * 2;           // one fp16 component tile: 8 KB
 constexpr int V2_NTILES = 5;                        // a, al, ah, b, bl
 constexpr int V2_STAGE_BYTES = V2_NTILES * V2_TILE; // 40 KB
-constexpr int V2_RAW_STAGES = 2;
+constexpr int V2_RAW_STAGES = 2;                    // raw ring depth with full 4-block boxes (64 KB in all)
+constexpr int V2_RAW_MAX = 8;                       // ... 4 / 8 stages when a box only brings 2 / 1 feature blocks
 constexpr int V2_OP_STAGES = 4;
 constexpr int V2_CONV_WARPS = 8;
 constexpr int V2_DRAIN_WARPS = 8;
@@ -76,14 +77,14 @@ struct V2Params {
 };
 
 struct V2Smem {
-    uint64_t raw_full[V2_RAW_STAGES];
-    uint64_t raw_empty[V2_RAW_STAGES];
+    uint64_t raw_full[V2_RAW_MAX];
+    uint64_t raw_empty[V2_RAW_MAX];
     uint64_t conv[V2_OP_STAGES];       // leader's copy is used; CG arrivals
     uint64_t empty[V2_OP_STAGES];      // local; one commit arrival
     uint64_t acc_full[V2_REGIONS];     // local; one commit arrival
     uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 8 * CG arrivals
     uint32_t tmem_base;
-    int valid_rows[V2_RAW_STAGES];
+    int valid_rows[V2_RAW_MAX];
     float sc[UM_F];                    // this CTA's per-feature scale and -shift * scale
     float nsh[UM_F];
 };
@@ -270,6 +271,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     int d_local = P.D - UM_F * (int)cta_rank;
     d_local = d_local < 0 ? 0 : (d_local > UM_F ? UM_F : d_local);
     const int nfb = d_local / 32;
+    // raw ring: a stage holds the two boxes of a tile (unlagged, lagged), box_blocks * 4 KB each; the
+    // ring always spans 64 KB, so narrow inputs get a deeper ring (the TMA latency showed as 240 cycles
+    // of wait per tile at D = 64 with two stages)
+    const uint32_t raw_op_bytes = (uint32_t)P.box_blocks * (UM_KT * 128);
+    const uint32_t raw_stage_bytes = 2 * raw_op_bytes;
+    const int n_raw = V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes > V2_RAW_MAX
+                          ? V2_RAW_MAX : V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes;
     // N of every UMMA: all the columns the group has (a single CTA with <= 64 features runs N = 64)
     const int n_cols = CG == 2 ? 256 : (P.D > 64 ? 128 : 64);
     // slab boundaries: staggered across groups (so the drains of the whole chip do not coincide)
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     auto region_off = [&](int q) { return (slab_off + (q * ST) / V2_REGIONS) % ST; };
 
     if (tid == 0) {
-        for (int s = 0; s < V2_RAW_STAGES; ++s) {
+        for (int s = 0; s < V2_RAW_MAX; ++s) {
             mbar_init(&ctl->raw_full[s], 1);
             mbar_init(&ctl->raw_empty[s], 1);
         }
@@ -345,11 +353,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 mbar_wait_idle<false>(&ctl->raw_empty[stage], phase ^ 1);   // hint only: the TMA issue is latency critical
                 ctl->valid_rows[stage] = valid;
                 mbar_expect_tx(&ctl->raw_full[stage], 2 * P.box_blocks * (UM_KT * 128));
-                unsigned char *st = raw_ring + stage * UM_RAW_BYTES;
+                unsigned char *st = raw_ring + (size_t)stage * raw_stage_bytes;
                 tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
-                tma_load_3d(st + UM_TILE_BYTES, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
+                tma_load_3d(st + raw_op_bytes, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
                             4 * (int)cta_rank, policy);
-                if (++stage == V2_RAW_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == n_raw) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             // raw tile of block fb: [frame][128 B], 16-byte chunks XOR-swizzled by frame & 7.  Frame
             // 8 kq + i sits at  base + i * 128  with the chunk bits flipped by i: one XOR with an
             // immediate per load, the row offset folds into the instruction
-            u_src[k] = (uint32_t)(op * UM_TILE_BYTES + (u_fl[k] >> 5) * (UM_KT * 128)
+            u_src[k] = (uint32_t)(op * raw_op_bytes + (u_fl[k] >> 5) * (UM_KT * 128)
                                   + u_kq[k] * 1024 + (chunk << 4) + within);
             u_dst[k] = (uint32_t)((op == 0 ? V2_T_A : V2_T_B) * V2_TILE + u_fl[k] * 16 + u_kq[k] * UM_LBO);
         }
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             mbar_wait(&ctl->empty[ostage], ophase ^ 1);
             long long q2 = dbg_on ? clock64() : 0;
             const int valid = ctl->valid_rows[stage];
-            const uint32_t rawst = raw_s + (uint32_t)stage * UM_RAW_BYTES;
+            const uint32_t rawst = raw_s + (uint32_t)stage * raw_stage_bytes;
             const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
             // FAST: all four feature blocks exist (D = 256 per pair / 128 per single CTA): every warp has
             // four units, the first two of operand 0 and the last two of operand 1 -- known at compile
@@ -644,7 +652,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 else mbar_arrive_local(&ctl->conv[ostage]);
             }
             if (dbg_on) { long long q4 = clock64(); d_raw += q1 - q0; d_empty += q2 - q1; d_comp += q3 - q2; d_sync += q4 - q3; }
-            if (++stage == V2_RAW_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == n_raw) { stage = 0; phase ^= 1; }
             if (++ostage == S) { ostage = 0; ophase ^= 1; }
         }
         if (dbg_on) { P.dbg[4] = d_raw; P.dbg[5] = d_empty; P.dbg[6] = d_comp; P.dbg[7] = d_sync; }
