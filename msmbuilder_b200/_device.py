@@ -259,6 +259,9 @@ def device_sequences(sequences):
     return store.split(store.data)
 
 
+PINNED_RESULT_LIMIT = 256 << 20
+
+
 def to_host(t, dtype=None):
     """Device tensor -> NumPy array through PINNED host memory (torch's caching host allocator
     keeps the blocks, so repeated calls pay no cudaHostAlloc): a pageable ``.cpu()`` of the
@@ -274,7 +277,13 @@ def to_host(t, dtype=None):
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     out.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return out.numpy()
+    arr = out.numpy()
+    # labels_ / distances_ live as long as the estimator: above PINNED_RESULT_LIMIT bytes they move on to
+    # pageable memory (one host memcpy) so that a fit on hundreds of millions of frames does not keep
+    # gigabytes page-locked; smaller results keep their pinned storage (no second pass over them)
+    if arr.nbytes > PINNED_RESULT_LIMIT:
+        arr = arr.copy()
+    return arr
 
 
 class Workspace(object):

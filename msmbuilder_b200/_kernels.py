@@ -276,6 +276,12 @@ def regular_spatial_fit(data, d_min, metric, traces=None):
 
     Returns the list of centre indices."""
     st = KCentersState(data, metric, traces=traces)
+    # a frame with a NaN coordinate is never a centre in the reference (`np.all(d > d_min)` is False for
+    # NaN, regularspatial.py:70-77); here its distance to every centre is NaN too, the strict `<` of the
+    # pass would leave its running minimum at +inf and first_above would promote it: pin it to -inf
+    bad = torch.isnan(data.reshape(st.n, -1)).any(dim=1)
+    if st.n > 1 and bool(bad[1:].any()):
+        st.distances[bad] = float("-inf")
     cand = torch.zeros(st.cand_bytes, dtype=torch.uint8, device="cuda")
     nxt = torch.zeros(1, dtype=torch.int64, device="cuda")
     ids = [0]

@@ -63,6 +63,24 @@ def test_regular_spatial_every_frame_and_single_centre():
     np.testing.assert_array_equal(m.cluster_center_indices_[:, 1], np.arange(0, 50, 3))
 
 
+def test_regular_spatial_skips_nan_frames_like_the_reference():
+    # regularspatial.py:70-77: `np.all(d > d_min)` is False for a frame with a NaN coordinate, so such a
+    # frame never becomes a centre (the running-minimum pass used to leave it at +inf)
+    from msmbuilder_b200.cluster import RegularSpatial
+    rs = np.random.RandomState(3)
+    X = rs.randn(400, 5).astype(np.float32) * 3
+    X[7, 2] = np.nan
+    X[100] = np.nan
+    want = [0]
+    for i in range(1, len(X)):
+        d = np.sqrt(((X[i].astype(np.float64) - X[want].astype(np.float64)) ** 2).sum(1))
+        if np.all(d > 2.5):
+            want.append(i)
+    m = RegularSpatial(d_min=2.5, metric="euclidean").fit([X])
+    assert 7 not in want and 100 not in want
+    np.testing.assert_array_equal(m.cluster_centers_, X[want])
+
+
 # ------------------------------------------------------------------ KMedoids
 @pytest.mark.parametrize("metric,d_min", MORE)
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
