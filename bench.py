@@ -590,6 +590,9 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": dominant, "roofline_all": [roof_k1, roof_k2],
         "phases_ms": {"tica_fit": tica_s * 1e3, "kcenters_fit": kc_s * 1e3,
+                      # rank 0's phases of every timed step (an outlier step shows here, not in the mean)
+                      "tica_fit_steps": [round(float(v), 3) for v in phase_ms["tica"]],
+                      "kcenters_fit_steps": [round(float(v), 3) for v in phase_ms["kcenters"]],
                       "kcenters_launches": [[int(c), round(float(m), 3)] for c, m in
                                             zip(pass_centres[-n_passes:], pass_ms[-n_passes:])] if pass_ms else None},
         "tica_engine": args.engine,

@@ -387,6 +387,239 @@ kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused pass, second generation (J pending centres, never the first pass).  Same arithmetic, same
+// lane / slot layout and the same outputs as kcenters_multi_pass_kernel<..., FIRST = false, JB>, bit
+// for bit; what changed is everything AROUND the arithmetic.  The r2o profile of the first version
+// (7.5 G warp instructions for 4 centres x 50M frames, issue slots 70 % busy, 18.1 M cycles against
+// the 15.3 M of the HBM stream) showed ~540 instructions per 4-frame iteration of which only ~270
+// were the float32 filter and its reduction: the cp.async prefetch evaluated the clamped tail
+// addressing (four 64-bit row * pitch products) next to the fast one on EVERY iteration and picked
+// with SEL, the loop bounds (warp_gid0, full_span) were rematerialised from %tid / %ctaid per
+// iteration, and every row index was rebuilt from `it`.  Here
+//   * the number of full and of existing iterations of the warp is computed once; the loop is two
+//     counted loops, the prefetch takes a warp-uniform branch to a fast path that is 8 LDGSTS + 3
+//     pointer bumps;
+//   * a lane carries ONE row index and ONE pointer into distances (its frame slot of the current
+//     iteration), advanced by a constant;
+//   * the ring is addressed by 32-bit shared addresses with immediate offsets.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned addr)
+{
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+
+template <int METRIC, int ITERS, int R, int JB>
+__global__ void __launch_bounds__(kThreads, 2)
+kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long long ld,
+                           const float *__restrict__ centers, int J, int label0,
+                           double *__restrict__ dist, int *__restrict__ labels,
+                           long long row_offset, unsigned char *__restrict__ lane_buf, int G,
+                           float one_minus_eps)
+{
+    typedef Metric<METRIC, float> M;
+    constexpr int V = R * JB;                        // float32 sums per group and chunk
+    constexpr int STAGES = kStages;
+    constexpr unsigned SLOT_BYTES = 32 * 16;         // one 16-byte request of every lane of the warp
+    constexpr unsigned STAGE_BYTES = R * ITERS * SLOT_BYTES;
+    extern __shared__ float4 s_c[];                  // [J rounded up to JB][d / 4], NEGATED (see v1)
+    const int d4 = d >> 2;
+    const int Jpad = (J + JB - 1) / JB * JB;
+    {
+        const float4 *c4 = reinterpret_cast<const float4 *>(centers);
+        for (int i = threadIdx.x; i < Jpad * d4; i += blockDim.x) {
+            const int jc = i / d4;
+            const float4 v = c4[(jc < J ? jc : J - 1) * d4 + (i - jc * d4)];
+            s_c[i] = make_float4(-v.x, -v.y, -v.z, -v.w);
+        }
+    }
+    __syncthreads();
+
+    const int lane_in_group = threadIdx.x & (G - 1);
+    const long long tid_global = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gid = tid_global / G;
+    const long long NG = ((long long)gridDim.x * blockDim.x) / G;
+    const long long warp_gid0 = (tid_global >> 5) * (32 / G);
+    const long long ld4 = ld >> 2;
+    const float4 *X4 = reinterpret_cast<const float4 *>(X);
+
+    // reduction slots exactly as in v1: lane -> value index vsel = f * JB + jj, frame slot f
+    const int lanes_per_f = G / R;
+    const int fsel = lane_in_group / lanes_per_f;
+    const int vsel = lane_in_group / (G / V);
+    const int jjsel = vsel - fsel * JB;
+    const bool owner = (lane_in_group & (lanes_per_f - 1)) == 0;
+    int slot_shift = 0;
+    while ((1 << slot_shift) < G / V) ++slot_shift;
+    const unsigned slot_lanes = (G / V >= 32) ? 0xffffffffu : ((1u << (G / V)) - 1u);
+
+    // iterations of this warp: [0, n_full) touch only rows < n, [n_full, n_iter) are clamped
+    const long long step_rows = (long long)R * NG;
+    const long long full_span = (long long)(R - 1) * NG + warp_gid0 + (32 / G);
+    const long long n_full = n >= full_span ? (n - full_span) / step_rows + 1 : 0;
+    const long long n_iter = n > warp_gid0 ? (n - warp_gid0 + step_rows - 1) / step_rows : 0;
+
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(
+        s_c + (size_t)Jpad * d4 + (size_t)(threadIdx.x >> 5) * (STAGES * R * ITERS * 32) + (threadIdx.x & 31));
+    unsigned off_p = 0, off_c = 0;                   // byte offset of the stage being produced / consumed
+    const long long stride_j = NG * ld4;             // float4 units between the R frames of a group
+    const float4 *ppre = X4 + gid * ld4 + lane_in_group;
+    long long pit = 0;                               // iteration being prefetched
+    auto prefetch = [&]() {
+        if (pit < n_full) {                          // warp uniform
+            const float4 *p = ppre;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i)
+                    cp_async16(ring + off_p + (unsigned)(j * ITERS + i) * SLOT_BYTES, p + i * G);
+                p += stride_j;
+            }
+            ppre = p;
+        } else if (pit < n_iter) {
+            const long long row0 = pit * step_rows + gid;
+#pragma unroll 1
+            for (int j = 0; j < R; ++j) {
+                const long long row = row0 + j * NG;
+                const float4 *p = X4 + (row < n ? row : n - 1) * ld4 + lane_in_group;
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i)
+                    cp_async16(ring + off_p + (unsigned)(j * ITERS + i) * SLOT_BYTES, p + i * G);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty: keeps the count uniform)
+        ++pit;
+        off_p = off_p + STAGE_BYTES == STAGES * STAGE_BYTES ? 0u : off_p + STAGE_BYTES;
+    };
+#pragma unroll 1
+    for (int s = 0; s < STAGES - 1; ++s) prefetch();
+
+    double v1 = -INFINITY, v2 = -INFINITY;
+    long long i1 = kNoRow;
+    long long myrow = (long long)fsel * NG + gid;    // this lane's frame slot in the current iteration
+    double *dptr = dist + myrow;
+    double cur_pre = myrow < n ? __ldcg(dptr) : INFINITY;   // requested one iteration ahead (see v1)
+
+    auto iteration = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        prefetch();
+        asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 1) : "memory");
+        float4 x[R][ITERS];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+                x[j][i] = lds128(ring + off_c + (unsigned)(j * ITERS + i) * SLOT_BYTES);
+        const bool valid = FULL || myrow < n;
+        double cur = valid ? cur_pre : INFINITY;
+        int lab = -1;
+        cur_pre = myrow + step_rows < n ? __ldcg(dptr + step_rows) : INFINITY;
+        // float upper bound of what the float32 sums are compared with
+        float bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? cur * cur : cur);
+        for (int j0 = 0; j0 < J; j0 += JB) {
+            float s[V];
+#pragma unroll
+            for (int jj = 0; jj < JB; ++jj) {
+                float4 c[ITERS];
+#pragma unroll
+                for (int i = 0; i < ITERS; ++i) c[i] = s_c[(j0 + jj) * d4 + lane_in_group + i * G];
+#pragma unroll
+                for (int f = 0; f < R; ++f) {
+                    float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) {
+                        float2 t = __fadd2_rn(make_float2(x[f][i].x, x[f][i].y), make_float2(c[i].x, c[i].y));
+                        a2 = __ffma2_rn(t, t, a2);
+                        t = __fadd2_rn(make_float2(x[f][i].z, x[f][i].w), make_float2(c[i].z, c[i].w));
+                        a2 = __ffma2_rn(t, t, a2);
+                    }
+                    s[f * JB + jj] = a2.x + a2.y;
+                }
+            }
+            const float tot = group_reduce_split_f32<V>(s, G, lane_in_group);
+            // certainly not below the current minimum -> the reference's mask is false (the relative
+            // margin needs float32's normal range: a sum below 1e-30 always goes to the refine step; so
+            // does a sum that overflowed float32 -- its float64 value may still be below the minimum)
+            const bool need = valid && (j0 + jjsel) < J &&
+                              !(tot * one_minus_eps >= bound && tot >= 1e-30f && tot <= 3.0e38f);
+            const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+            if (need_mask == 0) continue;
+            unsigned m = need_mask;
+            for (int g = G; g < 32; g <<= 1) m |= m >> g;
+            if (G < 32) m &= (1u << G) - 1u;
+            while (m) {
+                const int q = (__ffs(m) - 1) >> slot_shift;
+                m &= ~(slot_lanes << (q << slot_shift));
+                const int f = q / JB, jj = q - f * JB;
+                const float4 *cn = s_c + (j0 + jj) * d4 + lane_in_group;
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int ff = 0; ff < R; ++ff) {
+                    if (ff != f) continue;                  // warp uniform; x[] stays in registers
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) {
+                        const float4 c = cn[i * G];
+                        M::acc(a, b, x[ff][i].x, -c.x);
+                        M::acc(a, b, x[ff][i].y, -c.y);
+                        M::acc(a, b, x[ff][i].z, -c.z);
+                        M::acc(a, b, x[ff][i].w, -c.w);
+                    }
+                }
+                a = group_combine<false>(a, G);
+                if (fsel == f && valid) {
+                    const double dv = M::fin(a, 0.0, d);
+                    if (dv < cur) {                         // strict: kcenters.py:93
+                        cur = dv;
+                        lab = label0 + j0 + jj;
+                        bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? a : dv);
+                    }
+                }
+            }
+        }
+        if (owner && valid) {
+            if (lab >= 0) {
+                *dptr = cur;
+                labels[myrow] = lab;
+            }
+            if (cur > v1) {                 // a lane's rows increase with the iteration: first row wins ties
+                v2 = v1;
+                v1 = cur;
+                i1 = myrow;
+            } else if (cur > v2) {
+                v2 = cur;
+            }
+        }
+        myrow += step_rows;
+        dptr += step_rows;
+        off_c = off_c + STAGE_BYTES == STAGES * STAGE_BYTES ? 0u : off_c + STAGE_BYTES;
+    };
+    long long it = 0;
+#pragma unroll 1
+    for (; it < n_full; ++it) iteration(std::true_type());
+#pragma unroll 1
+    for (; it < n_iter; ++it) iteration(std::false_type());
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    if (owner) {
+        LaneCand *out = reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader));
+        LaneCand lc;
+        lc.v1 = v1;
+        lc.i1 = i1 == kNoRow ? kNoRow : row_offset + i1;
+        lc.v2 = v2;
+        lc.pad = 0;
+        out[gid * R + fsel] = lc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        reinterpret_cast<LaneHeader *>(lane_buf)->n_slots = NG * R;
+}
+
+// ---------------------------------------------------------------------------------------
 // Candidate selection: one block.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long cand_key(double v)
@@ -717,9 +950,29 @@ extern "C" int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int6
                                            distances, labels, row_offset,                         \
                                            (unsigned char *)lane_buf, G, om_eps);                 \
     } while (0)
+    // the second-generation fused pass (same results bit for bit); MSMB200_K2B_V1=1 keeps the first one
+    const char *v1_env = getenv("MSMB200_K2B_V1");
+    const bool fused_v1 = v1_env && atoi(v1_env) != 0;
+#define MSMB_FUSED(METRIC, I, RR, JBV)                                                            \
+    do {                                                                                          \
+        auto kern = kcenters_fused_pass_kernel<METRIC, I, RR, JBV>;                               \
+        const size_t smem = (size_t)((n_centers + JBV - 1) / JBV * JBV) * d * sizeof(float) +     \
+            (size_t)(kThreads / 32) * kStages * RR * I * 32 * sizeof(float4);                     \
+        MSMB_REQUIRE(smem <= 113 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
+                     "the shared memory of two resident blocks", n_centers, d);                   \
+        if (smem > 48 * 1024)                                                                     \
+            MSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           (int)smem));                                           \
+        kern<<<grid, kThreads, smem, st>>>((const float *)X, n, d, ld, crow, n_centers, label0,   \
+                                           distances, labels, row_offset,                         \
+                                           (unsigned char *)lane_buf, G, om_eps);                 \
+    } while (0)
 #define MSMB_MULTI_M(I, RR, F, JBV)                                                               \
     do {                                                                                          \
-        if (metric == MSMB200_EUCLIDEAN) MSMB_MULTI(MSMB200_EUCLIDEAN, I, RR, F, JBV);            \
+        if (!(F) && !fused_v1) {                                                                  \
+            if (metric == MSMB200_EUCLIDEAN) MSMB_FUSED(MSMB200_EUCLIDEAN, I, RR, JBV);           \
+            else MSMB_FUSED(MSMB200_SQEUCLIDEAN, I, RR, JBV);                                     \
+        } else if (metric == MSMB200_EUCLIDEAN) MSMB_MULTI(MSMB200_EUCLIDEAN, I, RR, F, JBV);     \
         else MSMB_MULTI(MSMB200_SQEUCLIDEAN, I, RR, F, JBV);                                      \
     } while (0)
 #define MSMB_MULTI_F(I, RR)                                                                       \
@@ -735,6 +988,7 @@ extern "C" int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int6
     else MSMB_MULTI_F(4, 2);
 #undef MSMB_MULTI_F
 #undef MSMB_MULTI_M
+#undef MSMB_FUSED
 #undef MSMB_MULTI
     MSMB_LAUNCH_CHECK();
     return MSMB200_OK;

@@ -1450,10 +1450,6 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     if (V.slab_tiles < 1) V.slab_tiles = 1;
     V.D = D;
     V.box_blocks = box_blocks;
-    V.direct = env_int("MSMB200_UMMA_DIRECT", 0);
-    V.lag = lag;
-    V.ld = (long long)ld;
-    V.seqs = reinterpret_cast<const EdgeSeq *>(scratch + o_eseq);
     V.dbg_mode = P.dbg_mode;
     V.shift = d_shift;
     V.scale = d_scale;

@@ -66,11 +66,6 @@ struct V2Params {
     int slab_tiles;               // 32-frame tiles per TMEM slab
     int D;                        // real feature count (32k)
     int box_blocks;               // 32-feature blocks one TMA box brings (4; D / 32 for the single-CTA kernel)
-    int direct;                   // experiment (MSMB200_UMMA_DIRECT=1): converters load the frames straight from
-                                  // L2 (TMA only prefetches), no raw tile in shared memory
-    int lag;
-    long long ld;                 // row pitch of the sequences, in floats
-    const EdgeSeq *seqs;          // [n_seq] base pointer and length of every sequence
     int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
@@ -90,7 +85,6 @@ struct V2Smem {
     uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 8 * CG arrivals
     uint32_t tmem_base;
     int valid_rows[V2_RAW_MAX];
-    const float *row_ptr[V2_RAW_MAX];  // direct mode: first unlagged row of the tile, this CTA's first feature
     float sc[UM_F];                    // this CTA's per-feature scale and -shift * scale
     float nsh[UM_F];
 };
@@ -282,10 +276,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     // of wait per tile at D = 64 with two stages)
     const uint32_t raw_op_bytes = (uint32_t)P.box_blocks * (UM_KT * 128);
     const uint32_t raw_stage_bytes = 2 * raw_op_bytes;
-    const bool direct = P.direct != 0 && nfb == 4;
-    const int n_raw = direct ? V2_RAW_MAX
-                      : (V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes > V2_RAW_MAX
-                             ? V2_RAW_MAX : V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes);
+    const int n_raw = V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes > V2_RAW_MAX
+                          ? V2_RAW_MAX : V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes;
     // N of every UMMA: all the columns the group has (a single CTA with <= 64 features runs N = 64)
     const int n_cols = CG == 2 ? 256 : (P.D > 64 ? 128 : 64);
     // slab boundaries: staggered across groups (so the drains of the whole chip do not coincide)
@@ -360,18 +352,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 if (valid > UM_KT) valid = UM_KT;
                 mbar_wait_idle<false>(&ctl->raw_empty[stage], phase ^ 1);   // hint only: the TMA issue is latency critical
                 ctl->valid_rows[stage] = valid;
-                if (direct) {
-                    // the converters read the frames themselves: hand them the tile's address and pull its
-                    // two boxes into L2 (the ring is 8 tiles deep, so this runs well ahead of them)
-                    ctl->row_ptr[stage] = P.seqs[s].base + (size_t)row0 * (size_t)P.ld + UM_F * cta_rank;
-                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                                 :: "l"(&P.mapsA[s]), "r"(0), "r"(row0), "r"(4 * (int)cta_rank) : "memory");
-                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                                 :: "l"(&P.mapsB[s]), "r"(0), "r"(row0), "r"(4 * (int)cta_rank) : "memory");
-                    mbar_arrive_local(&ctl->raw_full[stage]);
-                    if (++stage == n_raw) { stage = 0; phase ^= 1; }
-                    continue;
-                }
                 mbar_expect_tx(&ctl->raw_full[stage], 2 * P.box_blocks * (UM_KT * 128));
                 unsigned char *st = raw_ring + (size_t)stage * raw_stage_bytes;
                 tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
@@ -550,116 +530,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         uint32_t phase = 0, ophase = 0;
         const bool dbg_on = P.dbg != nullptr && group == 0 && tid == V2_CONV_TID0 && cta_rank == 0;
         long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0;
-        if (direct) {
-            // -------- direct mode: units (A, kq0), (A, kq0 + 2), (B, kq0), (B, kq0 + 2) of one feature column.
-            // The 16 values of the next pair are in flight (plain global loads, L2 hits thanks to the
-            // producer's prefetch) while the current pair is converted.
-            const int kq0 = cw >> 2;                               // 0 or 1
-            const int col = 32 * (cw & 3) + lane;                  // feature inside the CTA
-            const float sc = ctl->sc[col], nsh = ctl->nsh[col];
-            const uint64_t sc2 = f2_pack(sc, sc), nsh2 = f2_pack(nsh, nsh);
-            const size_t ld = (size_t)P.ld;
-            const size_t lag_off = (size_t)P.lag * ld;
-            float sh[2] = {0.f, 0.f}, sl[2] = {0.f, 0.f};
-            float va[2][8], vb[2][8];
-            auto load_pair = [&](float (&v)[2][8], const float *base, int valid) {
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int r0 = 8 * (kq0 + 2 * kk);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        v[kk][i] = (valid == UM_KT || r0 + i < valid) ? __ldg(base + (size_t)(r0 + i) * ld + col) : 0.f;
-                }
-            };
-            auto convert_pair = [&](const float (&v)[2][8], bool is_a, uint32_t st) {
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    uint32_t hw[4], lw[4];
-                    uint64_t as2[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        as2[i] = f2_fma(f2_pack(v[kk][2 * i], v[kk][2 * i + 1]), sc2, nsh2);
-                        float a0, a1;
-                        f2_unpack(as2[i], a0, a1);
-                        hw[i] = pack_f16(a0, a1);
-                        float l0, l1;
-                        asm("{\n\t.reg .f16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
-                            "fma.rn.f32.f16 %0, lo, m1, %3;\n\tfma.rn.f32.f16 %1, hi, m1, %4;\n\t}"
-                            : "=f"(l0), "=f"(l1) : "r"(hw[i]), "f"(a0), "f"(a1));
-                        lw[i] = pack_f16(l0, l1);
-                    }
-                    {
-                        uint32_t m01, m23;
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(hw[0] & 0x7FFF7FFFu), "r"(hw[1] & 0x7FFF7FFFu));
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(m23) : "r"(hw[2] & 0x7FFF7FFFu), "r"(hw[3] & 0x7FFF7FFFu));
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(m01), "r"(m23));
-                        asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
-                    }
-                    const uint32_t dst = st + (uint32_t)((is_a ? V2_T_A : V2_T_B) * V2_TILE + col * 16
-                                                        + (kq0 + 2 * kk) * UM_LBO);
-                    if (is_a) {
-                        sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);
-                        sts_v4<(V2_T_AL - V2_T_A) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);
-                        uint32_t h0, h1, h2, h3;
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h0) : "r"(hw[0]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h1) : "r"(hw[1]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h2) : "r"(hw[2]), "r"(0x38003800u));
-                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(h3) : "r"(hw[3]), "r"(0x38003800u));
-                        sts_v4<(V2_T_AH - V2_T_A) * V2_TILE>(dst, h0, h1, h2, h3);
-                        float s0, s1;
-                        f2_unpack(f2_add(f2_add(as2[0], as2[1]), f2_add(as2[2], as2[3])), s0, s1);
-                        const float ts = s0 + s1;
-                        const float tt = sh[kk] + ts, bp = tt - sh[kk];
-                        sl[kk] += (sh[kk] - (tt - bp)) + (ts - bp);
-                        sh[kk] = tt;
-                    } else {
-                        sts_v4<0>(dst, hw[0], hw[1], hw[2], hw[3]);
-                        sts_v4<(V2_T_BL - V2_T_B) * V2_TILE>(dst, lw[0], lw[1], lw[2], lw[3]);
-                    }
-                }
-            };
-            const float *base = nullptr;
-            int valid = UM_KT;
-            if (my_tiles > 0) {
-                mbar_wait(&ctl->raw_full[0], 0);
-                base = ctl->row_ptr[0];
-                valid = ctl->valid_rows[0];
-                load_pair(va, base, valid);
-            }
-            for (int t = 0; t < my_tiles; ++t) {
-                long long q0 = dbg_on ? clock64() : 0;
-                load_pair(vb, base + lag_off, valid);                 // the lagged rows of tile t: in flight
-                mbar_wait(&ctl->empty[ostage], ophase ^ 1);
-                long long q2 = dbg_on ? clock64() : 0;
-                const uint32_t st = op_s + (uint32_t)ostage * V2_STAGE_BYTES;
-                convert_pair(va, true, st);
-                const int nstage = stage + 1 == n_raw ? 0 : stage + 1;
-                if (t + 1 < my_tiles) {
-                    mbar_wait(&ctl->raw_full[nstage], stage + 1 == n_raw ? phase ^ 1 : phase);
-                    base = ctl->row_ptr[nstage];
-                    const int nvalid = ctl->valid_rows[nstage];
-                    load_pair(va, base, nvalid);                      // the unlagged rows of tile t + 1: in flight
-                    convert_pair(vb, false, st);
-                    valid = nvalid;
-                } else {
-                    convert_pair(vb, false, st);
-                }
-                long long q3 = dbg_on ? clock64() : 0;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
-                if (tid == V2_CONV_TID0) {
-                    mbar_arrive_local(&ctl->raw_empty[stage]);
-                    if constexpr (CG == 2) mbar_arrive_cluster(&ctl->conv[ostage], 0);
-                    else mbar_arrive_local(&ctl->conv[ostage]);
-                }
-                if (dbg_on) { long long q4 = clock64(); d_empty += q2 - q0; d_comp += q3 - q2; d_sync += q4 - q3; }
-                if (++stage == n_raw) { stage = 0; phase ^= 1; }
-                if (++ostage == S) { ostage = 0; ophase ^= 1; }
-            }
-            // hand the column sums to the common epilogue below: units (A, kq0) and (A, kq0 + 2)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) { sAh[kk] = sh[kk]; sAl[kk] = sl[kk]; }
-        } else
         for (int t = 0; t < my_tiles; ++t) {
             long long q0 = dbg_on ? clock64() : 0;
             mbar_wait(&ctl->raw_full[stage], phase);
