@@ -194,6 +194,11 @@ int msmb200_kcenters_chain(void *sets, int n_sets, size_t set_stride, int d, int
  * rows (DEVICE i64, may be NULL): optional gather X_indices; n_out = n_rows.
  */
 size_t msmb200_assign_workspace_bytes(int64_t n_out, int k, int d);
+/* which filter engine float32 (sq)euclidean assign_nearest takes for this shape (contiguous,
+ * 16-byte aligned frames, no row gather): 0 = tcgen05 with the centres resident in shared
+ * memory, 1 = tcgen05 with streamed centre chunks, 2 = SIMT float32 filter.  Labels are the
+ * exact engine's in every case (ambiguous frames are re-scanned in float64). */
+int msmb200_assign_engine(int64_t n_out, int k, int d);
 int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t ld, int dtype,
                            const void *Y, int k, int metric, const int64_t *rows,
                            int64_t n_rows, int32_t *labels, double *min_dist,

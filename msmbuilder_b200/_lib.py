@@ -52,6 +52,7 @@ SIGNATURES = {
     "msmb200_kcenters_chain": (c_int, [c_vp, c_int, c_sz, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "msmb200_candidate_from_row": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_i64, c_vp, c_vp]),
     "msmb200_assign_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
+    "msmb200_assign_engine": (c_int, [c_i64, c_int, c_int]),
     "msmb200_assign_nearest": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_int, c_int,
                                        c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "msmb200_dist": (c_int, [c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_int, c_vp, c_i64,

@@ -15,13 +15,16 @@
 // recomputed in float64 by assign_mindist_kernel as before.
 //
 // One CTA (cta_group::1, M = 128 frames, N <= 256 centres per UMMA, K = 16 features per UMMA):
-//   warps 2-5  converters: 32-byte segments of the frame tile straight from global memory (coalesced
-//              16-byte loads), per-frame scale from a butterfly over the frame's segments, fp16 h / l
-//              K-major chunks into a double-buffered operand stage;
+//   warps 2-9  converters: 32-byte segments of the frame tile straight from global memory (coalesced
+//              16-byte loads, four segments per thread in flight), per-frame scale from a butterfly over
+//              the frame's segments, fp16 h / l K-major chunks into a double-buffered operand stage;
 //   warp 1     UMMA issuer (one elected lane), accumulators double buffered in TMEM (2 x 256 columns);
-//   warps 6-9  epilogue, one per TMEM lane quarter: lane = frame.
-// The centres' fp16 tiles are prepared once per call by assign_umma_prep_kernel and stay resident in
-// shared memory (k_pad * d_pad * 4 bytes <= 96 KB; larger problems keep the SIMT filter).
+//   warps 10-13 epilogue, one per TMEM lane quarter: lane = frame.
+// The centres' fp16 tiles are prepared once per call by assign_umma_prep_kernel.  When they fit 96 KB
+// (k_pad * d_pad * 4 bytes) they stay resident in shared memory (assign_umma_kernel); larger centre
+// tables -- every d > 64, k = 2000 at d = 128 -- are STREAMED (assign_umma_stream_kernel): the frame
+// tile's operand stays in shared memory while chunks of NS centres arrive from L2 through a two-slot
+// ring of TMA bulk copies (a loader lane, mbarrier complete_tx), one accumulator buffer per chunk.
 #include "common.cuh"
 
 namespace msmb {
@@ -30,11 +33,12 @@ namespace {
 
 constexpr int AU_M = 128;                 // frames per tile
 constexpr int AU_NT = 256;                // centres per UMMA / accumulator buffer
-constexpr int AU_CONV_WARPS = 4;
+constexpr int AU_CONV_WARPS = 8;
 constexpr int AU_EPI_WARPS = 4;
 constexpr int AU_FIRST_CONV = 2;
-constexpr int AU_FIRST_EPI = AU_FIRST_CONV + AU_CONV_WARPS;       // 6: 6 % 4 = 2 ... quarter = warp & 3
-constexpr int AU_THREADS = 32 * (AU_FIRST_EPI + AU_EPI_WARPS + 2);   // 12 warps
+constexpr int AU_FIRST_EPI = AU_FIRST_CONV + AU_CONV_WARPS;       // 10: quarter = warp & 3 (any 4 consecutive warps)
+constexpr int AU_THREADS = 32 * (AU_FIRST_EPI + AU_EPI_WARPS + 2);   // 16 warps (14: loader of the streamed kernel)
+constexpr int AU_CONV_BATCH = 4;          // segments a converter thread has in flight
 constexpr size_t AU_B_LIMIT = 96 * 1024;
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,10 +140,10 @@ struct AuPrep {              // written by the prep kernel, read by the main ker
 
 }  // namespace
 
-// centres -> fp16 h / l tiles [n_tile][k chunk][256 rows][16 B] (zero padded), |c_j|^2, global scale.
+// centres -> fp16 h / l tiles [n_tile][k chunk][nt_rows rows][16 B] (zero padded), |c_j|^2, global scale.
 // One block; the centre table is small (<= 96 KB of tiles).
 __global__ void __launch_bounds__(256)
-assign_umma_prep_kernel(const float *__restrict__ Y, int k, int d, int d_pad, int k_pad,
+assign_umma_prep_kernel(const float *__restrict__ Y, int k, int d, int d_pad, int k_pad, int nt_rows,
                         unsigned char *__restrict__ tiles_h, unsigned char *__restrict__ tiles_l,
                         float *__restrict__ cn, AuPrep *__restrict__ prep)
 {
@@ -161,7 +165,7 @@ assign_umma_prep_kernel(const float *__restrict__ Y, int k, int d, int d_pad, in
     for (int j = tid; j < k_pad; j += 256) {
         double s2 = 0.0;
         float sp2 = 0.f;
-        const int nt = j / AU_NT, r = j % AU_NT;
+        const int nt = j / nt_rows, r = j % nt_rows;
         for (int c = 0; c < nc; ++c) {
             float a[8];
 #pragma unroll
@@ -177,7 +181,7 @@ assign_umma_prep_kernel(const float *__restrict__ Y, int k, int d, int d_pad, in
             split_h2(a[2], a[3], hw.y, lw.y);
             split_h2(a[4], a[5], hw.z, lw.z);
             split_h2(a[6], a[7], hw.w, lw.w);
-            const size_t o = (((size_t)nt * nc + c) * AU_NT + r) * 16;
+            const size_t o = (((size_t)nt * nc + c) * nt_rows + r) * 16;
             *reinterpret_cast<uint4 *>(tiles_h + o) = hw;
             *reinterpret_cast<uint4 *>(tiles_l + o) = lw;
         }
@@ -204,6 +208,79 @@ assign_umma_prep_kernel(const float *__restrict__ Y, int k, int d, int d_pad, in
         prep->c_norm_max = nm;
         prep->cn_max = s_red[0];
         prep->pad = 0;
+    }
+}
+
+// One frame tile (128 frames x d_pad features) -> fp16 h / l K-major chunks [nc][128][16 B] plus the
+// per-frame multiplier and ambiguity margin; shared by the resident and the streamed kernel.  A thread
+// takes 32-byte segments s = fr * nc + c (nc = d_pad / 8, a power of two: the segments of a frame sit
+// in adjacent lanes) and keeps AU_CONV_BATCH of them in flight -- with one segment per round trip
+// the 32 segments a thread owns at d = 256 cost 30 us of pure load latency per tile (r2t: 22.8 ms
+// for 10M x 256 frames against 8 centres).
+__device__ __forceinline__ void au_convert_tile(const float *__restrict__ X, long long n, int d, long long ld,
+                                                int nc, int d_pad, long long row0, unsigned char *ah,
+                                                unsigned char *al, int ct, float *f_mul, float *f_margin,
+                                                float c_inv, float c_nmax, float cn_max)
+{
+    constexpr int STRIDE = 32 * AU_CONV_WARPS;
+    const int segs = AU_M * nc;                              // a multiple of STRIDE (nc >= 2)
+    const int nc_shift = 31 - __clz(nc);
+    for (int s0 = ct; s0 < segs; s0 += AU_CONV_BATCH * STRIDE) {
+        float4 u[AU_CONV_BATCH], w[AU_CONV_BATCH];
+#pragma unroll
+        for (int q = 0; q < AU_CONV_BATCH; ++q) {
+            const int s = s0 + q * STRIDE;
+            const int fr = s >> nc_shift, c = s & (nc - 1);
+            const long long row = row0 + fr;
+            u[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < segs && row < n && 8 * c < d) {
+                const float4 *src = reinterpret_cast<const float4 *>(X + row * ld + 8 * c);
+                u[q] = __ldg(src);
+                if (8 * c + 4 < d) w[q] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < AU_CONV_BATCH; ++q) {
+            const int s = s0 + q * STRIDE;
+            if (s >= segs) break;                            // block uniform
+            const int fr = s >> nc_shift, c = s & (nc - 1);
+            const float a[8] = {u[q].x, u[q].y, u[q].z, u[q].w, w[q].x, w[q].y, w[q].z, w[q].w};
+            // largest magnitude and squared norm of the frame: butterfly over its nc segments
+            float m = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { m = fmaxf(m, fabsf(a[e])); s2 = fmaf(a[e], a[e], s2); }
+            for (int off = 1; off < nc && off < 32; off <<= 1) {
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            }
+            float inv;
+            const float scale = pow2_scale(m, inv);
+            uint4 hw, lw;
+            split_h2(a[0] * scale, a[1] * scale, hw.x, lw.x);
+            split_h2(a[2] * scale, a[3] * scale, hw.y, lw.y);
+            split_h2(a[4] * scale, a[5] * scale, hw.z, lw.z);
+            split_h2(a[6] * scale, a[7] * scale, hw.w, lw.w);
+            const size_t o = ((size_t)c * AU_M + fr) * 16;
+            *reinterpret_cast<uint4 *>(ah + o) = hw;
+            *reinterpret_cast<uint4 *>(al + o) = lw;
+            if (c == 0) {
+                // S = S' * 2^(e + E);  value = |c|^2 - 2 S.  Error of S' (DESIGN.md section 4, K3):
+                //   operands  3 * 2^-22 |x'| |c'|  (h + l is x' to 2^-22, the l cl product is dropped)
+                //             + 2^-23 d            (fp16 subnormal low parts, |x'|, |c'| <= 2)
+                //   fp32 TMEM accumulation, one truncation per UMMA: (3 d / 16) 2^-22 |x'| |c'|
+                // and of the value: 2 * 2^(e + E) * that, + 2^-24 |c|^2 (float |c|^2) + the fma's own
+                // rounding; two values are compared, so the margin is twice the sum (x 1.5 for slack).
+                const float unit = inv * c_inv;
+                f_mul[fr] = -2.f * unit;
+                const float nxp = sqrtf(s2) * scale;
+                const float coef = 2.3841858e-7f * (3.f + 3.f * (float)d_pad * 0.0625f);     // 2^-22 (3 + 3 d / 16)
+                float eS = coef * nxp * c_nmax + 1.1920929e-7f * (float)d_pad;
+                float mg = 3.f * (2.f * unit * eS + 1.7881393e-7f * (cn_max + 2.f * unit * nxp * c_nmax));
+                if (!(m < INFINITY) || !(mg < INFINITY)) mg = INFINITY;      // non-finite frame: exact path
+                f_margin[fr] = mg;
+            }
+        }
     }
 }
 
@@ -312,67 +389,15 @@ assign_umma_kernel(const float *__restrict__ X, long long n, int d, long long ld
             }
         }
     } else if (warp >= AU_FIRST_CONV && warp < AU_FIRST_EPI) {
-        // ================================ converters (128 threads)
+        // ================================ converters (256 threads): au_convert_tile
         const int ct = tid - 32 * AU_FIRST_CONV;
-        const int segs = AU_M * nc;                          // 32-byte segments per tile (nc per frame)
         long long it = 0;
         for (long long t = my_first; t < n_tiles; t += tile_step, ++it) {
             const int st = (int)(it & 1);
             bar_wait(&ctl->a_empty[st], (uint32_t)(((it >> 1) & 1) ^ 1));
             unsigned char *ah = sA + (size_t)st * 2 * a_tile, *al = ah + a_tile;
-            const long long row0 = t * AU_M;
-            for (int s0 = 0; s0 < segs; s0 += 32 * AU_CONV_WARPS) {
-                const int s = s0 + ct;                       // segs is a multiple of 128: always valid
-                const int fr = s / nc, c = s % nc;
-                const long long row = row0 + fr;
-                float a[8];
-                if (row < n && 8 * c < d) {
-                    const float4 *src = reinterpret_cast<const float4 *>(X + row * ld + 8 * c);
-                    const float4 u = __ldg(src);
-                    a[0] = u.x; a[1] = u.y; a[2] = u.z; a[3] = u.w;
-                    if (8 * c + 4 < d) {
-                        const float4 w = __ldg(src + 1);
-                        a[4] = w.x; a[5] = w.y; a[6] = w.z; a[7] = w.w;
-                    } else { a[4] = a[5] = a[6] = a[7] = 0.f; }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) a[q] = 0.f;
-                }
-                // largest magnitude and squared norm of the frame: butterfly over its nc segments
-                float m = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { m = fmaxf(m, fabsf(a[q])); s2 = fmaf(a[q], a[q], s2); }
-                for (int off = 1; off < nc && off < 32; off <<= 1) {
-                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-                }
-                float inv;
-                const float scale = pow2_scale(m, inv);
-                uint4 hw, lw;
-                split_h2(a[0] * scale, a[1] * scale, hw.x, lw.x);
-                split_h2(a[2] * scale, a[3] * scale, hw.y, lw.y);
-                split_h2(a[4] * scale, a[5] * scale, hw.z, lw.z);
-                split_h2(a[6] * scale, a[7] * scale, hw.w, lw.w);
-                const size_t o = ((size_t)c * AU_M + fr) * 16;
-                *reinterpret_cast<uint4 *>(ah + o) = hw;
-                *reinterpret_cast<uint4 *>(al + o) = lw;
-                if (c == 0) {
-                    // S = S' * 2^(e + E);  value = |c|^2 - 2 S.  Error of S' (DESIGN.md section 4, K3):
-                    //   operands  3 * 2^-22 |x'| |c'|  (h + l is x' to 2^-22, the l cl product is dropped)
-                    //             + 2^-23 d            (fp16 subnormal low parts, |x'|, |c'| <= 2)
-                    //   fp32 TMEM accumulation, one truncation per UMMA: (3 d / 16) 2^-22 |x'| |c'|
-                    // and of the value: 2 * 2^(e + E) * that, + 2^-24 |c|^2 (float |c|^2) + the fma's own
-                    // rounding; two values are compared, so the margin is twice the sum (x 1.5 for slack).
-                    const float unit = inv * c_inv;
-                    ctl->f_mul[it & 3][fr] = -2.f * unit;
-                    const float nxp = sqrtf(s2) * scale;
-                    const float coef = 2.3841858e-7f * (3.f + 3.f * (float)d_pad * 0.0625f);     // 2^-22 (3 + 3 d / 16)
-                    float eS = coef * nxp * c_nmax + 1.1920929e-7f * (float)d_pad;
-                    float mg = 3.f * (2.f * unit * eS + 1.7881393e-7f * (cn_max + 2.f * unit * nxp * c_nmax));
-                    if (!(m < INFINITY) || !(mg < INFINITY)) mg = INFINITY;      // non-finite frame: exact path
-                    ctl->f_margin[it & 3][fr] = mg;
-                }
-            }
+            au_convert_tile(X, n, d, ld, nc, d_pad, t * AU_M, ah, al, ct, ctl->f_mul[it & 3], ctl->f_margin[it & 3],
+                            c_inv, c_nmax, cn_max);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) bar_arrive(&ctl->a_full[st]);
@@ -427,10 +452,242 @@ assign_umma_kernel(const float *__restrict__ X, long long n, int d, long long ld
 }
 
 // ------------------------------------------------------------------------------------------------
+// Streamed centres: the same three-product filter when the centre table does not fit shared memory.
+//   warp 14    loader (one lane): chunk ch of the centres' h / l tiles -> ring slot, two TMA bulk copies
+//              (the tiles of a chunk are contiguous in global memory), completion on b_full[slot];
+//   warp 1     issuer: per frame tile, per chunk: wait b_full + acc_empty, d_pad / 16 K steps of three
+//              UMMAs (M = 128 frames, N = NS centres), commit -> acc_full, b_empty (and a_empty after
+//              the tile's last chunk);
+//   warps 2-9  converters, warps 10-13 epilogue: as in assign_umma_kernel.
+// NS (centres per chunk) and the number of frame-operand stages follow the shared-memory budget:
+// d_pad 256 -> NS 32, 128 -> 128, <= 64 -> 256; the frame operand is single buffered above d_pad 64
+// (the UMMAs of a tile then take several times longer than its conversion).  |c_j|^2 of every centre
+// stays resident (4 k bytes).
+// ------------------------------------------------------------------------------------------------
+struct AsSmem {
+    uint64_t a_full[2], a_empty[2];
+    uint64_t b_full[2], b_empty[2];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    float f_mul[4][AU_M];
+    float f_margin[4][AU_M];
+};
+constexpr int AS_LOADER_WARP = AU_FIRST_EPI + AU_EPI_WARPS;          // 14
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(AU_THREADS, 1)
+assign_umma_stream_kernel(const float *__restrict__ X, long long n, int d, long long ld, int d_pad,
+                          int n_ch, int ns, int a_stages, const unsigned char *__restrict__ tiles_h,
+                          const unsigned char *__restrict__ tiles_l, const float *__restrict__ cn,
+                          const AuPrep *__restrict__ prep, int *__restrict__ labels,
+                          int *__restrict__ amb_list, int *__restrict__ amb_count)
+{
+    extern __shared__ __align__(1024) unsigned char au_smem[];
+    const int nc = d_pad / 8;                               // 16-byte K chunks per row
+    const uint32_t a_tile = (uint32_t)AU_M * d_pad * 2;     // bytes of one fp16 component of a frame tile
+    const uint32_t b_tile = (uint32_t)ns * d_pad * 2;       // bytes of one component of one centre chunk
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(au_smem) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sB = base;                                         // [2 slots][h | l][nc][ns][16]
+    unsigned char *sA = sB + 4 * (size_t)b_tile;                      // [a_stages][h | l][nc][128][16]
+    float *s_cn = reinterpret_cast<float *>(sA + (size_t)a_stages * 2 * a_tile);   // [n_ch * ns]
+    AsSmem *ctl = reinterpret_cast<AsSmem *>(s_cn + (size_t)n_ch * ns);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            bar_init(&ctl->a_full[s], AU_CONV_WARPS);
+            bar_init(&ctl->a_empty[s], 1);
+            bar_init(&ctl->b_full[s], 1);
+            bar_init(&ctl->b_empty[s], 1);
+            bar_init(&ctl->acc_full[s], 1);
+            bar_init(&ctl->acc_empty[s], AU_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < n_ch * ns; i += AU_THREADS) s_cn[i] = cn[i];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(s_u32(&ctl->tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    const long long n_tiles = (n + AU_M - 1) / AU_M;
+    const long long my_first = blockIdx.x, tile_step = gridDim.x;
+    const float c_inv = prep->c_inv_scale, c_nmax = prep->c_norm_max, cn_max = prep->cn_max;
+
+    if (warp == AS_LOADER_WARP) {
+        // ================================ loader: centre chunks, once per frame tile (L2 resident)
+        // (the whole warp walks the loop, one lane issues: no lane is left behind at the final barrier)
+        long long bit = 0;
+        for (long long t = my_first; t < n_tiles; t += tile_step) {
+            for (int ch = 0; ch < n_ch; ++ch, ++bit) {
+                const int slot = (int)(bit & 1);
+                bar_wait(&ctl->b_empty[slot], (uint32_t)(((bit >> 1) & 1) ^ 1));
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                 :: "r"(s_u32(&ctl->b_full[slot])), "r"(2u * b_tile) : "memory");
+                    unsigned char *dst = sB + (size_t)slot * 2 * b_tile;
+                    bulk_g2s(dst, tiles_h + (size_t)ch * b_tile, b_tile, &ctl->b_full[slot]);
+                    bulk_g2s(dst + b_tile, tiles_l + (size_t)ch * b_tile, b_tile, &ctl->b_full[slot]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ UMMA issuer
+        const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+        const uint32_t a_addr = __shfl_sync(0xffffffffu, s_u32(sA), 0);
+        const uint32_t b_addr = __shfl_sync(0xffffffffu, s_u32(sB), 0);
+        uint32_t idesc = 0;
+        idesc |= 1u << 4;                                   // f32 accumulate, f16 x f16
+        idesc |= (uint32_t)(ns >> 3) << 17;
+        idesc |= (uint32_t)(AU_M >> 4) << 24;
+        long long it = 0, cit = 0;                          // frame tiles / chunks done by this CTA
+        for (long long t = my_first; t < n_tiles; t += tile_step, ++it) {
+            const int st = (int)(it % a_stages);
+            bar_wait(&ctl->a_full[st], (uint32_t)((it / a_stages) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int ch = 0; ch < n_ch; ++ch, ++cit) {
+                const int ab = (int)(cit & 1);              // accumulator buffer and ring slot advance together
+                bar_wait(&ctl->b_full[ab], (uint32_t)((cit >> 1) & 1));
+                bar_wait(&ctl->acc_empty[ab], (uint32_t)(((cit >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (elect_one()) {
+                    const uint32_t ah = a_addr + (uint32_t)st * 2 * a_tile, al = ah + a_tile;
+                    const uint32_t bh = b_addr + (uint32_t)ab * 2 * b_tile, bl = bh + b_tile;
+                    for (int ks = 0; ks < d_pad / 16; ++ks) {
+                        const uint64_t dAh = kdesc(ah + (uint32_t)ks * 2 * (AU_M * 16), AU_M * 16, 128);
+                        const uint64_t dAl = kdesc(al + (uint32_t)ks * 2 * (AU_M * 16), AU_M * 16, 128);
+                        const uint64_t dBh = kdesc(bh + (uint32_t)ks * 2 * ((uint32_t)ns * 16), (uint32_t)ns * 16, 128);
+                        const uint64_t dBl = kdesc(bl + (uint32_t)ks * 2 * ((uint32_t)ns * 16), (uint32_t)ns * 16, 128);
+                        mma_f16(tmem + (uint32_t)ab * (uint32_t)ns, dAh, dBh, idesc, ks ? 1u : 0u);
+                        mma_f16(tmem + (uint32_t)ab * (uint32_t)ns, dAh, dBl, idesc, 1u);
+                        mma_f16(tmem + (uint32_t)ab * (uint32_t)ns, dAl, dBh, idesc, 1u);
+                    }
+                    mma_commit(&ctl->acc_full[ab]);
+                    mma_commit(&ctl->b_empty[ab]);                          // the slot may be refilled
+                    if (ch == n_ch - 1) mma_commit(&ctl->a_empty[st]);      // ... and the frame stage
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= AU_FIRST_CONV && warp < AU_FIRST_EPI) {
+        // ================================ converters (256 threads): au_convert_tile
+        const int ct = tid - 32 * AU_FIRST_CONV;
+        long long it = 0;
+        for (long long t = my_first; t < n_tiles; t += tile_step, ++it) {
+            const int st = (int)(it % a_stages);
+            bar_wait(&ctl->a_empty[st], (uint32_t)(((it / a_stages) & 1) ^ 1));
+            unsigned char *ah = sA + (size_t)st * 2 * a_tile, *al = ah + a_tile;
+            au_convert_tile(X, n, d, ld, nc, d_pad, t * AU_M, ah, al, ct, ctl->f_mul[it & 3], ctl->f_margin[it & 3],
+                            c_inv, c_nmax, cn_max);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bar_arrive(&ctl->a_full[st]);
+        }
+    } else if (warp >= AU_FIRST_EPI && warp < AU_FIRST_EPI + AU_EPI_WARPS) {
+        // ================================ epilogue: lane = frame, scan the centres of every chunk
+        const int quarter = warp & 3;
+        const int fr = quarter * 32 + lane;
+        const uint32_t tmem = ctl->tmem_base;
+        long long it = 0, cit = 0;
+        for (long long t = my_first; t < n_tiles; t += tile_step, ++it) {
+            float best = INFINITY, second = INFINITY;
+            int arg = 0;
+            float mul = 0.f, margin = 0.f;
+            for (int ch = 0; ch < n_ch; ++ch, ++cit) {
+                const int ab = (int)(cit & 1);
+                bar_wait(&ctl->acc_full[ab], (uint32_t)((cit >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                if (ch == 0) { mul = ctl->f_mul[it & 3][fr]; margin = ctl->f_margin[it & 3][fr]; }
+                for (int c0 = 0; c0 < ns; c0 += 32) {
+                    uint32_t v[32];
+                    AU_TMEM_LD32(v, tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * ns + c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float *cnp = s_cn + ch * ns + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float val = fmaf(__uint_as_float(v[j]), mul, cnp[j]);
+                        if (val < best) { second = best; best = val; arg = ch * ns + c0 + j; }
+                        else if (val < second) second = val;
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) bar_arrive(&ctl->acc_empty[ab]);
+            }
+            const long long row = t * AU_M + fr;
+            if (row < n) {
+                labels[row] = arg;
+                if (!(second - best > margin)) {
+                    const int slot = atomicAdd(amb_count, 1);
+                    amb_list[slot] = (int)row;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(ctl->tmem_base), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------------
 static int next_pow2_16(int d)
 {
     int p = 16;
     while (p < d) p <<= 1;
+    return p;
+}
+
+// which kernel takes (d, k): resident centre tiles, streamed chunks, or neither (-> SIMT filter)
+struct AuPlan {
+    bool ok, stream;
+    int d_pad, k_pad;        // k_pad: padded centre count of the tile table (n_nt * 256 or n_ch * ns)
+    int rows;                // rows per tile of the table (256 resident, ns streamed)
+    int n_tiles;             // n_nt or n_ch
+    int a_stages;
+    size_t smem;
+};
+static AuPlan au_plan(int d, int k)
+{
+    AuPlan p = {};
+    p.d_pad = next_pow2_16(d);
+    const int k16 = (k + 15) / 16 * 16;
+    const int n_nt = (k16 + AU_NT - 1) / AU_NT;
+    const size_t a_tile = (size_t)AU_M * p.d_pad * 2;
+    if ((size_t)n_nt * AU_NT * p.d_pad * 4 <= AU_B_LIMIT && !getenv("MSMB200_ASSIGN_STREAM")) {
+        p.ok = true;
+        p.stream = false;
+        p.rows = AU_NT;
+        p.n_tiles = n_nt;
+        p.k_pad = k16;
+        p.a_stages = 2;
+        p.smem = 1024 + 2 * (size_t)n_nt * AU_NT * p.d_pad * 2 + 4 * a_tile + sizeof(float) * (size_t)n_nt * AU_NT
+                 + sizeof(AuSmem) + 64;
+        // all 512 TMEM columns belong to one CTA: ask for more than half of the shared memory so that a
+        // second CTA is never scheduled on the same SM (its tcgen05.alloc would wait for the first to end)
+        if (p.smem < 120 * 1024) p.smem = 120 * 1024;
+        return p;
+    }
+    p.stream = true;
+    p.rows = p.d_pad >= 256 ? 32 : (p.d_pad == 128 ? 128 : 256);
+    p.n_tiles = (k + p.rows - 1) / p.rows;
+    p.k_pad = p.n_tiles * p.rows;
+    p.a_stages = p.d_pad <= 64 ? 2 : 1;
+    p.smem = 1024 + 4 * (size_t)p.rows * p.d_pad * 2 + (size_t)p.a_stages * 2 * a_tile
+             + sizeof(float) * (size_t)p.k_pad + sizeof(AsSmem) + 64;
+    if (p.smem < 120 * 1024) p.smem = 120 * 1024;
+    p.ok = p.smem <= 225 * 1024;
     return p;
 }
 
@@ -439,52 +696,56 @@ bool assign_umma_supported(int64_t n_out, int d, int64_t ld, int k, const void *
     if (has_rows || getenv("MSMB200_ASSIGN_SIMT")) return false;
     if (d > 256 || (d % 4) != 0 || k < 2 || (ld % 4) != 0 || (reinterpret_cast<uintptr_t>(X) & 15u)) return false;
     if (n_out < 4096) return false;                         // latency bound below that: the SIMT filter is fine
-    const int d_pad = next_pow2_16(d);
-    const int k_pad = (k + 15) / 16 * 16;
-    const int n_nt = (k_pad + AU_NT - 1) / AU_NT;
-    return (size_t)n_nt * AU_NT * d_pad * 4 <= AU_B_LIMIT;
+    return au_plan(d, k).ok;
+}
+
+// 1 when the streamed-centres kernel would take (d, k), 0 for the resident one, -1 for neither
+int assign_umma_mode(int d, int k)
+{
+    const AuPlan p = au_plan(d, k);
+    return !p.ok ? -1 : (p.stream ? 1 : 0);
 }
 
 size_t assign_umma_scratch_bytes(int d, int k)
 {
-    const int d_pad = next_pow2_16(d);
-    const int n_nt = ((k + 15) / 16 * 16 + AU_NT - 1) / AU_NT;
-    return 2 * (size_t)n_nt * AU_NT * d_pad * 2 + sizeof(float) * (size_t)n_nt * AU_NT + 256;
+    const AuPlan p = au_plan(d, k);
+    const size_t rows = (size_t)p.n_tiles * p.rows;
+    return 2 * rows * p.d_pad * 2 + sizeof(float) * rows + 256;
 }
 
 // filter stage on the tensor cores: labels + ambiguity list (amb_count zeroed by the caller)
 int assign_umma_filter(const float *X, int64_t n, int d, int64_t ld, const float *Y, int k,
                        int32_t *labels, int *amb_list, int *amb_count, cudaStream_t st)
 {
-    const int d_pad = next_pow2_16(d);
-    const int k_pad = (k + 15) / 16 * 16;
-    const int n_nt = (k_pad + AU_NT - 1) / AU_NT;
-    const size_t b_tile = (size_t)AU_NT * d_pad * 2;
+    const AuPlan p = au_plan(d, k);
+    MSMB_REQUIRE(p.ok, "assign_umma_filter: unsupported shape (d=%d k=%d)", d, k);
+    const size_t rows = (size_t)p.n_tiles * p.rows;
+    const size_t comp_bytes = rows * p.d_pad * 2;            // one fp16 component of the whole table
     unsigned char *scratch = nullptr;
     MSMB_CUDA(cudaMallocAsync(&scratch, assign_umma_scratch_bytes(d, k), st));
-    unsigned char *tiles_h = scratch, *tiles_l = scratch + (size_t)n_nt * b_tile;
-    float *cn = reinterpret_cast<float *>(tiles_l + (size_t)n_nt * b_tile);
-    AuPrep *prep = reinterpret_cast<AuPrep *>(cn + (size_t)n_nt * AU_NT);
-    assign_umma_prep_kernel<<<1, 256, 0, st>>>(Y, k, d, d_pad, n_nt * AU_NT, tiles_h, tiles_l, cn, prep);
+    unsigned char *tiles_h = scratch, *tiles_l = scratch + comp_bytes;
+    float *cn = reinterpret_cast<float *>(tiles_l + comp_bytes);
+    AuPrep *prep = reinterpret_cast<AuPrep *>(cn + rows);
+    assign_umma_prep_kernel<<<1, 256, 0, st>>>(Y, k, d, p.d_pad, (int)rows, p.rows, tiles_h, tiles_l, cn, prep);
     MSMB_LAUNCH_CHECK();
-    const size_t a_tile = (size_t)AU_M * d_pad * 2;
-    size_t smem = 1024 + 2 * (size_t)n_nt * b_tile + 4 * a_tile + sizeof(float) * (size_t)n_nt * AU_NT
-                  + sizeof(AuSmem) + 64;
-    // all 512 TMEM columns belong to one CTA: ask for more than half of the shared memory so that a
-    // second CTA is never scheduled on the same SM (its tcgen05.alloc would wait for the first to end)
-    if (smem < 120 * 1024) smem = 120 * 1024;
     static bool attr_set[64] = {false};
     int dev = 0;
     MSMB_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         MSMB_CUDA(cudaFuncSetAttribute(assign_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MSMB_CUDA(cudaFuncSetAttribute(assign_umma_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev] = true;
     }
     const long long n_tiles = (n + AU_M - 1) / AU_M;
     long long grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    assign_umma_kernel<<<(unsigned)grid, AU_THREADS, smem, st>>>(
-        X, n, d, ld, d_pad, k, k_pad, tiles_h, tiles_l, cn, prep, labels, amb_list, amb_count);
+    if (p.stream)
+        assign_umma_stream_kernel<<<(unsigned)grid, AU_THREADS, p.smem, st>>>(
+            X, n, d, ld, p.d_pad, p.n_tiles, p.rows, p.a_stages, tiles_h, tiles_l, cn, prep, labels, amb_list,
+            amb_count);
+    else
+        assign_umma_kernel<<<(unsigned)grid, AU_THREADS, p.smem, st>>>(
+            X, n, d, ld, p.d_pad, k, p.k_pad, tiles_h, tiles_l, cn, prep, labels, amb_list, amb_count);
     MSMB_LAUNCH_CHECK();
     MSMB_CUDA(cudaFreeAsync(scratch, st));
     return MSMB200_OK;

@@ -17,6 +17,7 @@
 namespace msmb {
 // K3 filter on the tensor cores (assign_umma.cu)
 bool assign_umma_supported(int64_t n_out, int d, int64_t ld, int k, const void *X, bool has_rows);
+int assign_umma_mode(int d, int k);
 int assign_umma_filter(const float *X, int64_t n, int d, int64_t ld, const float *Y, int k,
                        int32_t *labels, int *amb_list, int *amb_count, cudaStream_t st);
 }
@@ -754,6 +755,13 @@ extern "C" size_t msmb200_assign_workspace_bytes(int64_t n_out, int k, int d)
 {
     (void)k; (void)d;
     return sizeof(double) * (size_t)(8 * 256) + 256 + sizeof(int) * (size_t)(n_out > 0 ? n_out : 0) + 256;
+}
+
+extern "C" int msmb200_assign_engine(int64_t n_out, int k, int d)
+{
+    static const float aligned_dummy[4] __attribute__((aligned(16))) = {0.f, 0.f, 0.f, 0.f};
+    if (!assign_umma_supported(n_out, d, d, k, aligned_dummy, false)) return 2;
+    return assign_umma_mode(d, k) == 1 ? 1 : 0;
 }
 
 extern "C" int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t ld, int dtype,

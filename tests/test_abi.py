@@ -106,3 +106,18 @@ def test_host_kmedoids_restarts_match_oracle():
         assert a[1] == b[1] and a[2] == b[2], (trial, a[1:], b[1:])
     with pytest.raises(ValueError):
         K.kmedoids(3, np.zeros(10), -1)
+
+
+def test_assign_engine_choice():
+    # which filter float32 (sq)euclidean assign_nearest takes (include/msmb200.h): resident tcgen05
+    # while the centres' fp16 tiles fit 96 KB, streamed chunks above, SIMT for small n / odd widths
+    lib = _lib.load()
+    assert lib.msmb200_assign_engine(10_000_000, 500, 16) == 0      # config 3
+    assert lib.msmb200_assign_engine(10_000_000, 2000, 128) == 1    # the k = 2000 x D = 128 point
+    assert lib.msmb200_assign_engine(50_000_000, 8, 256) == 1       # KCenters.predict at the bench width
+    assert lib.msmb200_assign_engine(10_000_000, 2000, 16) == 1
+    assert lib.msmb200_assign_engine(10_000_000, 256, 64) == 0
+    assert lib.msmb200_assign_engine(1000, 500, 16) == 2            # latency bound: SIMT
+    assert lib.msmb200_assign_engine(10_000_000, 500, 18) == 2      # d % 4 != 0
+    assert lib.msmb200_assign_engine(10_000_000, 500, 300) == 2     # d > 256
+    assert lib.msmb200_assign_engine(10_000_000, 12000, 128) == 2   # |c|^2 table beyond the shared-memory budget

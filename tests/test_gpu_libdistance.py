@@ -103,6 +103,57 @@ def test_tensor_core_filter_labels_equal_exact_engine(n, d, k, monkeypatch):
     np.testing.assert_array_equal(simt_labels, ref_labels)
 
 
+@pytest.mark.parametrize("n,d,k", [(6000, 128, 300), (5000, 256, 100), (8000, 64, 600), (9000, 16, 2000),
+                                   (5000, 100, 129), (148 * 128 * 2 + 77, 128, 256), (4500, 256, 2)])
+def test_streamed_centres_filter_labels_equal_exact_engine(n, d, k, monkeypatch):
+    # K3 with streamed centre chunks (assign_umma_stream_kernel: the centre table does not fit shared
+    # memory -- every d > 64, k = 2000 at d = 16): several chunks per frame tile, more frame tiles than
+    # SMs, single- and double-buffered frame operands; labels of the float64 scan, ties included
+    from msmbuilder_b200 import libdistance as ld, _lib
+    assert _lib.load().msmb200_assign_engine(n, k, d) == 1
+    rs = np.random.RandomState(n + d + k)
+    X = (rs.randn(n, d) * 10.0 ** rs.uniform(-2, 2, size=d)).astype(np.float32)
+    Y = X[rs.choice(n, k, replace=False)].copy()
+    Y[k // 2] = Y[0]                                   # duplicate centre: lowest index wins
+    X[::7] = np.round(X[::7])                          # lattice points: exact ties between centres
+    Y[1::5] = np.round(Y[1::5])
+    labels, inertia = ld.assign_nearest(X, Y, "euclidean")
+    monkeypatch.setenv("MSMB200_ASSIGN_EXACT", "1")
+    ref_labels, ref_inertia = ld.assign_nearest(X, Y, "euclidean")
+    np.testing.assert_array_equal(labels, ref_labels)
+    assert abs(inertia - ref_inertia) <= 1e-12 * abs(ref_inertia)
+    monkeypatch.delenv("MSMB200_ASSIGN_EXACT")
+    # a resident-size problem forced through the streamed kernel gives the same labels too
+    if d <= 64 and k <= 256:
+        return
+    sq_labels, _ = ld.assign_nearest(X, Y, "sqeuclidean")
+    np.testing.assert_array_equal(sq_labels, ref_labels)
+
+
+def test_streamed_kernel_on_a_resident_size_problem(monkeypatch):
+    from msmbuilder_b200 import libdistance as ld
+    rs = np.random.RandomState(3)
+    X = rs.randn(20000, 16).astype(np.float32)
+    Y = X[rs.choice(len(X), 500, replace=False)].copy()
+    labels, _ = ld.assign_nearest(X, Y, "euclidean")
+    monkeypatch.setenv("MSMB200_ASSIGN_STREAM", "1")
+    s_labels, _ = ld.assign_nearest(X, Y, "euclidean")
+    np.testing.assert_array_equal(s_labels, labels)
+    ref_labels, _ = lo.assign_nearest(X[:3000], Y, "euclidean")
+    np.testing.assert_array_equal(s_labels[:3000], ref_labels)
+
+
+def test_streamed_centres_filter_vs_reference_cpp():
+    from msmbuilder_b200 import libdistance as ld
+    rs = np.random.RandomState(8)
+    X = rs.randn(4096, 128).astype(np.float32)
+    Y = rs.randn(40, 128).astype(np.float32)
+    labels, inertia = ld.assign_nearest(X, Y, "euclidean")
+    ref_labels, ref_inertia = lo.assign_nearest(X, Y, "euclidean")
+    np.testing.assert_array_equal(labels, ref_labels)
+    assert abs(inertia - ref_inertia) <= 1e-11 * abs(ref_inertia)
+
+
 def test_tensor_core_filter_vs_reference_cpp():
     # against the compiled reference itself (oracle/_ref) on a size it finishes quickly
     from msmbuilder_b200 import libdistance as ld
