@@ -4,12 +4,16 @@
 // i+1 = argmax_x min_{j<=i} d(x, c_j) is only known after pass i.  A pass is HBM bound
 // (4*D + 8 bytes per frame), so k centres cost k reads of the data set.
 //
-// Look-ahead: while a pass streams the frames it also keeps, per owning lane, the largest and the
-// second largest running minimum it has seen.  After the pass
-//   * the CANDIDATES are the lanes' largest values above the T-th largest of them (plus the true
-//     arg-max), with their frames gathered;
-//   * every frame that is NOT a candidate has a running minimum <= tau = max(largest lane
-//     runner-up, T-th largest lane maximum), and running minima only ever decrease.
+// Look-ahead: while a pass streams the frames it also keeps, per owning lane, the THREE largest
+// running minima it has seen (the two largest with their rows).  After the pass
+//   * the CANDIDATES are the lanes' two largest values above the T-th largest of all of them (plus
+//     the true arg-max), with their frames gathered;
+//   * every frame that is NOT a candidate has a running minimum <= tau = max(largest lane third
+//     best, T-th largest entry), and running minima only ever decrease.
+// (Round 2 kept two values and one candidate per lane: with 37 888 lanes two of the ~250 largest
+// frames share a lane -- the birthday bound -- so tau was the 221st largest value of the bench data
+// and the first chain stopped after 4 of the 7 centres it could have certified,
+// profiles/r2u_lookahead_diag_top2.log.  Three of the top frames in one lane need ~2000 of them.)
 // A chain kernel then plays the reference's loop on the candidates alone: pick the arg-max
 // (lowest index on ties, np.argmax), lower the candidates' minima by their distance to it, pick
 // again ...  A pick whose value is strictly above tau is provably the arg-max over ALL frames,
@@ -36,12 +40,49 @@ static constexpr int kThreads = 256;
 static constexpr int kStages = 3;            // per-warp frame ring of the fused passes (4 KB per stage)
 static constexpr long long kNoRow = 0x7fffffffffffffffLL;
 
-struct LaneCand {           // one per (group, frame slot) of the fused pass
+struct LaneCand {           // one per (group, frame slot) of a pass
     double v1;              // largest running minimum seen (-inf: no rows)
     long long i1;           // its GLOBAL row (lowest row among equals)
     double v2;              // second largest (ties with v1 included)
+    long long i2;           // its GLOBAL row
+    double v3;              // third largest (ties included): bounds every other frame of the lane
     long long pad;
 };
+// The owning lane's record lives in SHARED memory while a pass runs (ten registers otherwise: the first
+// pass then either spills or drops to three resident blocks per SM, and HBM latency needs four -- r2v:
+// 8.0 -> 8.3 ms).  The hot path is one 8-byte load and a compare; an update is rare once the lane has
+// seen a few frames.  A lane's rows increase from iteration to iteration and the comparisons are
+// strict: the first row wins ties.  Every record has exactly one owner: no synchronisation.
+struct LaneTop {
+    LaneCand *p;
+    __device__ __forceinline__ void init(LaneCand *slot, bool owner)
+    {
+        p = slot;
+        if (owner) {
+            p->v1 = p->v2 = p->v3 = -INFINITY;
+            p->i1 = p->i2 = kNoRow;
+            p->pad = 0;
+        }
+    }
+    __device__ __forceinline__ void add(double cur, long long row)
+    {
+        if (cur > p->v3) {
+            const double a1 = p->v1, a2 = p->v2;
+            if (cur > a1) { p->v3 = a2; p->v2 = a1; p->i2 = p->i1; p->v1 = cur; p->i1 = row; }
+            else if (cur > a2) { p->v3 = a2; p->v2 = cur; p->i2 = row; }
+            else p->v3 = cur;
+        }
+    }
+    __device__ __forceinline__ void store(LaneCand *out, long long row_offset) const
+    {
+        LaneCand lc = *p;
+        if (lc.i1 != kNoRow) lc.i1 += row_offset;
+        if (lc.i2 != kNoRow) lc.i2 += row_offset;
+        *out = lc;
+    }
+};
+// shared-memory bytes of the lane records of one block: one per owner = (frame slot of a group)
+static inline size_t lane_top_bytes(int G, int R) { return sizeof(LaneCand) * (size_t)(kThreads / G) * R; }
 struct LaneHeader {         // first 32 bytes of the lane buffer
     long long n_slots;
     long long pad[3];
@@ -100,296 +141,111 @@ __device__ __forceinline__ float group_reduce_split_f32(float (&v)[V], int G, in
 }
 
 // ---------------------------------------------------------------------------------------
-// Fused pass over J pending centres (labels label0 .. label0 + J - 1).
-//   FIRST  the very first pass (J == 1, every running minimum is +inf): the body of
-//          kcenters_pass_fast_kernel, no filter.
-//   else   centres are taken JB at a time: R x JB float32 squared distances per group and
-//          iteration (packed f32x2 add / fma), ONE split reduction for all of them (its shuffle
-//          latency is paid once per JB centres), then lane (f, jj) decides whether centre jj can
-//          possibly lower the running minimum of frame f; the few pairs that can are redone in
-//          the reference arithmetic by the whole group, in centre order.
-// Every lane whose reduction slot belongs to frame f carries that frame's running minimum
-// (identical copies), one of them (`owner`) writes it back and keeps the lane's top two.
+// The very first pass (one centre, every running minimum is +inf): the body of
+// kcenters_pass_fast_kernel (dist_kernels.cu) -- R frames per group and iteration straight from
+// global memory, reference arithmetic, one split reduction -- plus the lane records.  Nothing is
+// read back from `dist`, so it runs at the HBM roof (4 d bytes per frame).
 // ---------------------------------------------------------------------------------------
-template <int METRIC, int ITERS, int R, bool FIRST, int JB>
-__global__ void __launch_bounds__(kThreads, FIRST ? 4 : 2)
-kcenters_multi_pass_kernel(const float *__restrict__ X, long long n, int d, long long ld,
-                           const float *__restrict__ centers, int J, int label0,
+template <int METRIC, int ITERS, int R>
+__global__ void __launch_bounds__(kThreads, 4)
+kcenters_first_pass_kernel(const float *__restrict__ X, long long n, int d, long long ld,
+                           const float *__restrict__ center, int label0,
                            double *__restrict__ dist, int *__restrict__ labels,
-                           long long row_offset, unsigned char *__restrict__ lane_buf, int G,
-                           float one_minus_eps)
+                           long long row_offset, unsigned char *__restrict__ lane_buf, int G)
 {
     typedef Metric<METRIC, float> M;
-    constexpr int V = R * JB;                        // float32 sums per group and chunk
-    constexpr int STAGES = kStages;                  // cp.async ring depth of the fused passes
-    extern __shared__ float4 s_c[];                  // [J rounded up to JB][d / 4], NEGATED
-    const int d4 = d >> 2;
-    {
-        // stored negated: x + (-c) is x - c bit for bit, and the float32 filter can then use the
-        // packed f32x2 add / fma of sm_100 (two elements per instruction); the padding centres of
-        // the last chunk are copies of the last real one and never looked at
-        const int Jpad = (J + JB - 1) / JB * JB;      // (recomputed below: this block is a scope)
-        const float4 *c4 = reinterpret_cast<const float4 *>(centers);
-        for (int i = threadIdx.x; i < Jpad * d4; i += blockDim.x) {
-            const int jc = i / d4;
-            const float4 v = c4[(jc < J ? jc : J - 1) * d4 + (i - jc * d4)];
-            s_c[i] = make_float4(-v.x, -v.y, -v.z, -v.w);
-        }
-    }
-    __syncthreads();
-
     const int lane_in_group = threadIdx.x & (G - 1);
     const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const long long NG = ((long long)gridDim.x * blockDim.x) / G;
     const long long warp_gid0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / G);
     const long long ld4 = ld >> 2;
     const float4 *X4 = reinterpret_cast<const float4 *>(X);
-
-    // reduction slots: lane -> value index vsel = lig / (G / V) = f * JB + jj; frame slot
-    // f = lig / (G / R) (the split reduction peels the frame bits first)
     const int lanes_per_f = G / R;
-    const int fsel = lane_in_group / lanes_per_f;
-    const int vsel = FIRST ? 0 : lane_in_group / (G / V);
-    const int jjsel = FIRST ? 0 : vsel - fsel * JB;
+    const int fsel = lane_in_group / lanes_per_f;    // the split reduction peels the frame bits first
     const bool owner = (lane_in_group & (lanes_per_f - 1)) == 0;
-    // lanes per reduction slot (a power of two) as a shift and as a mask of that many low bits
-    int slot_shift = 0;
-    while ((1 << slot_shift) < G / V) ++slot_shift;
-    const unsigned slot_lanes = (G / V >= 32) ? 0xffffffffu : ((1u << (G / V)) - 1u);
 
-    double v1 = -INFINITY, v2 = -INFINITY;
-    long long i1 = kNoRow;
-    float4 c_first[ITERS];                           // FIRST: the one centre lives in registers
+    float4 c_first[ITERS];                           // the one centre lives in registers
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-        const float4 v = s_c[lane_in_group + i * G];
-        c_first[i] = make_float4(-v.x, -v.y, -v.z, -v.w);
-    }
+    for (int i = 0; i < ITERS; ++i)
+        c_first[i] = reinterpret_cast<const float4 *>(center)[lane_in_group + i * G];
 
+    extern __shared__ float4 s_dyn[];
+    LaneTop top;
+    top.init(reinterpret_cast<LaneCand *>(s_dyn) + (threadIdx.x / G) * R + fsel, owner);
     const long long stride_j = NG * ld4;
     const float4 *pfull = X4 + gid * ld4 + lane_in_group;
-
-    // Fused passes are compute heavy (J float32 distances per frame): the frames of the next
-    // STAGES - 1 iterations are already on their way into a per-warp shared-memory ring
-    // (cp.async.cg, 16 bytes per lane and request, each lane reads back only what it wrote), so
-    // HBM latency overlaps the arithmetic without holding the data in registers.
-    const int Jpad = (J + JB - 1) / JB * JB;
-    float4 *my_ring = s_c + (size_t)Jpad * d4 + (size_t)(threadIdx.x >> 5) * (STAGES * R * ITERS * 32) +
-                      (threadIdx.x & 31);
-    int stage_c = 0, stage_p = 0;                    // ring slot being consumed / produced
-    const float4 *ppre = pfull;
-    long long prow = 0;                              // it_p * R * NG
-    auto prefetch = [&]() {
-        if (prow + warp_gid0 < n) {                  // warp uniform: this iteration exists
-            const bool full = prow + (long long)(R - 1) * NG + warp_gid0 + (32 / G) <= n;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const long long row = prow + j * NG + gid;
-                const float4 *p = full ? ppre + j * stride_j
-                                       : X4 + (row < n ? row : n - 1) * ld4 + lane_in_group;
-#pragma unroll
-                for (int i = 0; i < ITERS; ++i) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(
-                        my_ring + (stage_p * (R * ITERS) + j * ITERS + i) * 32);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(p + i * G) : "memory");
-                }
-            }
-            ppre += R * stride_j;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty: keeps the count uniform)
-        prow += (long long)R * NG;
-        if (++stage_p == STAGES) stage_p = 0;
-    };
-    if (!FIRST) {
-#pragma unroll 1
-        for (int s = 0; s < STAGES - 1; ++s) prefetch();
-    }
-    long long rbase = gid;                           // it * R * NG + gid, advanced per iteration
-    const long long next_off = (long long)(R + fsel) * NG;
-    double cur_pre = INFINITY;                       // running minimum of the NEXT iteration's frame
-    if (!FIRST) {
-        const long long r0 = (long long)fsel * NG + gid;
-        if (r0 < n) cur_pre = __ldcg(dist + r0);
-    }
-    auto iteration = [&](long long it, auto full_tag) {
+    long long rbase = gid;                           // it * R * NG + gid
+    auto iteration = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         long long rr[R];
         float4 x[R][ITERS];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            rr[j] = rbase + j * NG;                  // == (it * R + j) * NG + gid
-            if (FIRST) {
-                const long long rc = (FULL || rr[j] < n) ? rr[j] : n - 1;
-                const float4 *p = FULL ? pfull + j * stride_j : X4 + rc * ld4 + lane_in_group;
+            rr[j] = rbase + j * NG;
+            const long long rc = (FULL || rr[j] < n) ? rr[j] : n - 1;
+            const float4 *p = FULL ? pfull + j * stride_j : X4 + rc * ld4 + lane_in_group;
 #pragma unroll
-                for (int i = 0; i < ITERS; ++i) x[j][i] = ldg_stream(p + i * G);
-            } else {
-                // staged by cp.async STAGES - 1 iterations ago (lane-private slots: no barrier)
-#pragma unroll
-                for (int i = 0; i < ITERS; ++i) x[j][i] = my_ring[(stage_c * (R * ITERS) + j * ITERS + i) * 32];
-            }
+            for (int i = 0; i < ITERS; ++i) x[j][i] = ldg_stream(p + i * G);
         }
         long long myrow = -1;
 #pragma unroll
         for (int j = 0; j < R; ++j)
             if (fsel == j && (FULL || rr[j] < n)) myrow = rr[j];
-        double cur = INFINITY;
-        int lab = -1;
-
-        if (FIRST) {
-            double va[R];
+        double va[R];
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                double a = 0.0, b = 0.0;
+        for (int j = 0; j < R; ++j) {
+            double a = 0.0, b = 0.0;
 #pragma unroll
-                for (int i = 0; i < ITERS; ++i) {
-                    M::acc(a, b, x[j][i].x, c_first[i].x);
-                    M::acc(a, b, x[j][i].y, c_first[i].y);
-                    M::acc(a, b, x[j][i].z, c_first[i].z);
-                    M::acc(a, b, x[j][i].w, c_first[i].w);
-                }
-                va[j] = a;
+            for (int i = 0; i < ITERS; ++i) {
+                M::acc(a, b, x[j][i].x, c_first[i].x);
+                M::acc(a, b, x[j][i].y, c_first[i].y);
+                M::acc(a, b, x[j][i].z, c_first[i].z);
+                M::acc(a, b, x[j][i].w, c_first[i].w);
             }
-            const double ra = group_reduce_split<false, R>(va, G, lane_in_group);
-            const double dv = M::fin(ra, 0.0, d);
+            va[j] = a;
+        }
+        const double ra = group_reduce_split<false, R>(va, G, lane_in_group);
+        const double dv = M::fin(ra, 0.0, d);
+        double cur = INFINITY;
+        if (owner && myrow >= 0) {
             if (dv < cur) {                  // false for NaN, like the reference's mask
                 cur = dv;
-                lab = label0;
-            }
-        } else {
-            // this frame's running minimum was requested one iteration ago (its load latency
-            // would otherwise sit in front of every iteration: 30 % of the stall samples), the
-            // next one is requested now
-            if (myrow >= 0) cur = cur_pre;
-            {
-                const long long rn = rbase + next_off;       // == ((it + 1) * R + fsel) * NG + gid
-                cur_pre = rn < n ? __ldcg(dist + rn) : INFINITY;
-            }
-            // float upper bound of what the float32 sums are compared with
-            float bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? cur * cur : cur);
-            for (int j0 = 0; j0 < J; j0 += JB) {
-                float s[V];
-#pragma unroll
-                for (int jj = 0; jj < JB; ++jj) {
-                    float4 c[ITERS];
-#pragma unroll
-                    for (int i = 0; i < ITERS; ++i) c[i] = s_c[(j0 + jj) * d4 + lane_in_group + i * G];
-#pragma unroll
-                    for (int f = 0; f < R; ++f) {
-                        float2 a2 = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int i = 0; i < ITERS; ++i) {
-                            float2 t = __fadd2_rn(make_float2(x[f][i].x, x[f][i].y), make_float2(c[i].x, c[i].y));
-                            a2 = __ffma2_rn(t, t, a2);
-                            t = __fadd2_rn(make_float2(x[f][i].z, x[f][i].w), make_float2(c[i].z, c[i].w));
-                            a2 = __ffma2_rn(t, t, a2);
-                        }
-                        s[f * JB + jj] = a2.x + a2.y;
-                    }
-                }
-                const float tot = group_reduce_split_f32<V>(s, G, lane_in_group);
-                // certainly not below the current minimum -> the reference's mask is false
-                // (the relative margin needs float32's normal range: a sum below 1e-30, i.e. frames
-                //  closer than 1e-15, always goes to the refine step)
-                const bool need = myrow >= 0 && (j0 + jjsel) < J &&
-                                  !(tot * one_minus_eps >= bound && tot >= 1e-30f);
-                const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-                if (need_mask == 0) continue;
-                // needed slots of ANY group of the warp, lowest first: slot order is (frame, centre),
-                // so every frame meets its centres in ascending order (ties keep the first, like
-                // the reference's strict '<' over k sequential passes)
-                unsigned m = need_mask;
-                for (int g = G; g < 32; g <<= 1) m |= m >> g;
-                if (G < 32) m &= (1u << G) - 1u;
-                while (m) {
-                    const int q = (__ffs(m) - 1) >> slot_shift;
-                    m &= ~(slot_lanes << (q << slot_shift));
-                    const int f = q / JB, jj = q - f * JB;
-                    const float4 *cn = s_c + (j0 + jj) * d4 + lane_in_group;
-                    double a = 0.0, b = 0.0;
-#pragma unroll
-                    for (int ff = 0; ff < R; ++ff) {
-                        if (ff != f) continue;                  // warp uniform; x[] stays in registers
-#pragma unroll
-                        for (int i = 0; i < ITERS; ++i) {
-                            const float4 c = cn[i * G];
-                            M::acc(a, b, x[ff][i].x, -c.x);
-                            M::acc(a, b, x[ff][i].y, -c.y);
-                            M::acc(a, b, x[ff][i].z, -c.z);
-                            M::acc(a, b, x[ff][i].w, -c.w);
-                        }
-                    }
-                    a = group_combine<false>(a, G);
-                    if (fsel == f && myrow >= 0) {
-                        const double dv = M::fin(a, 0.0, d);
-                        if (dv < cur) {                         // strict: kcenters.py:93
-                            cur = dv;
-                            lab = label0 + j0 + jj;
-                            bound = __double2float_ru(METRIC == MSMB200_EUCLIDEAN ? a : dv);
-                        }
-                    }
-                }
-            }
-        }
-        if (owner && myrow >= 0) {
-            if (lab >= 0) {
                 dist[myrow] = cur;
-                labels[myrow] = lab;
+                labels[myrow] = label0;
             }
-            if (cur > v1) {                 // a lane's rows increase with `it`: first row wins ties
-                v2 = v1;
-                v1 = cur;
-                i1 = myrow;
-            } else if (cur > v2) {
-                v2 = cur;
-            }
+            top.add(cur, myrow);
         }
     };
-    auto stage_in = [&]() {          // make iteration `it`'s frames visible, keep STAGES - 1 in flight
-        if (!FIRST) {
-            prefetch();
-            asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 1) : "memory");
-        }
-    };
-    auto stage_out = [&]() {
-        if (!FIRST && ++stage_c == STAGES) stage_c = 0;
-    };
-    long long it = 0;
     const long long full_span = (long long)(R - 1) * NG + warp_gid0 + (32 / G);   // + it * R * NG <= n: full
     const long long step_rows = (long long)R * NG;
     long long wrow = 0;                              // it * R * NG
-    for (; wrow + full_span <= n; ++it, wrow += step_rows) {
-        stage_in();
-        iteration(it, std::true_type());
-        stage_out();
+    for (; wrow + full_span <= n; wrow += step_rows) {
+        iteration(std::true_type());
         pfull += R * stride_j;
         rbase += step_rows;
     }
-    for (; wrow + warp_gid0 < n; ++it, wrow += step_rows) {
-        stage_in();
-        iteration(it, std::false_type());
-        stage_out();
+    for (; wrow + warp_gid0 < n; wrow += step_rows) {
+        iteration(std::false_type());
         rbase += step_rows;
     }
-    if (!FIRST) asm volatile("cp.async.wait_group 0;" ::: "memory");
-
-    if (owner) {
-        LaneCand *out = reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader));
-        LaneCand lc;
-        lc.v1 = v1;
-        lc.i1 = i1 == kNoRow ? kNoRow : row_offset + i1;
-        lc.v2 = v2;
-        lc.pad = 0;
-        out[gid * R + fsel] = lc;
-    }
+    if (owner)
+        top.store(reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader)) + (gid * R + fsel), row_offset);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         reinterpret_cast<LaneHeader *>(lane_buf)->n_slots = NG * R;
 }
 
 // ---------------------------------------------------------------------------------------
-// Fused pass, second generation (J pending centres, never the first pass).  Same arithmetic, same
-// lane / slot layout and the same outputs as kcenters_multi_pass_kernel<..., FIRST = false, JB>, bit
-// for bit; what changed is everything AROUND the arithmetic.  The r2o profile of the first version
+// Fused pass over J pending centres (labels label0 .. label0 + J - 1), never the first pass.
+// Centres are taken JB at a time: R x JB float32 squared distances per group and iteration (packed
+// f32x2 add / fma), ONE split reduction for all of them (its shuffle latency is paid once per JB
+// centres), then lane (f, jj) decides whether centre jj can possibly lower the running minimum of
+// frame f; the few pairs that can are redone in the reference arithmetic by the whole group, in
+// centre order.  Every lane whose reduction slot belongs to frame f carries that frame's running
+// minimum (identical copies), one of them (`owner`) writes it back and keeps the lane's top three.
+// Frames arrive through a per-warp cp.async ring (HBM latency overlaps the arithmetic without
+// holding the data in registers).
+// This is the second generation of the kernel: same arithmetic and outputs as the first, bit for
+// bit; what changed is everything AROUND the arithmetic.  The r2o profile of the first version
 // (7.5 G warp instructions for 4 centres x 50M frames, issue slots 70 % busy, 18.1 M cycles against
 // the 15.3 M of the HBM stream) showed ~540 instructions per 4-frame iteration of which only ~270
 // were the float32 filter and its reduction: the cp.async prefetch evaluated the clamped tail
@@ -428,7 +284,10 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
     constexpr int STAGES = kStages;
     constexpr unsigned SLOT_BYTES = 32 * 16;         // one 16-byte request of every lane of the warp
     constexpr unsigned STAGE_BYTES = R * ITERS * SLOT_BYTES;
-    extern __shared__ float4 s_c[];                  // [J rounded up to JB][d / 4], NEGATED (see v1)
+    // stored negated: x + (-c) is x - c bit for bit, and the float32 filter can then use the packed
+    // f32x2 add / fma of sm_100 (two elements per instruction); the padding centres of the last
+    // chunk are copies of the last real one and never looked at
+    extern __shared__ float4 s_c[];                  // [J rounded up to JB][d / 4], NEGATED
     const int d4 = d >> 2;
     const int Jpad = (J + JB - 1) / JB * JB;
     {
@@ -449,7 +308,8 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
     const long long ld4 = ld >> 2;
     const float4 *X4 = reinterpret_cast<const float4 *>(X);
 
-    // reduction slots exactly as in v1: lane -> value index vsel = f * JB + jj, frame slot f
+    // reduction slots: lane -> value index vsel = lig / (G / V) = f * JB + jj; frame slot
+    // f = lig / (G / R) (the split reduction peels the frame bits first)
     const int lanes_per_f = G / R;
     const int fsel = lane_in_group / lanes_per_f;
     const int vsel = lane_in_group / (G / V);
@@ -500,11 +360,14 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
 #pragma unroll 1
     for (int s = 0; s < STAGES - 1; ++s) prefetch();
 
-    double v1 = -INFINITY, v2 = -INFINITY;
-    long long i1 = kNoRow;
+    LaneTop top;                                     // records: behind the frame ring
+    top.init(reinterpret_cast<LaneCand *>(s_c + (size_t)Jpad * d4 + (size_t)(kThreads / 32) * (STAGES * R * ITERS * 32)) +
+                 (threadIdx.x / G) * R + fsel, owner);
     long long myrow = (long long)fsel * NG + gid;    // this lane's frame slot in the current iteration
     double *dptr = dist + myrow;
-    double cur_pre = myrow < n ? __ldcg(dptr) : INFINITY;   // requested one iteration ahead (see v1)
+    // the frame's running minimum is requested one iteration ahead (its load latency would
+    // otherwise sit in front of every iteration: 30 % of the stall samples of the first version)
+    double cur_pre = myrow < n ? __ldcg(dptr) : INFINITY;
 
     auto iteration = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
@@ -587,13 +450,7 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
                 *dptr = cur;
                 labels[myrow] = lab;
             }
-            if (cur > v1) {                 // a lane's rows increase with the iteration: first row wins ties
-                v2 = v1;
-                v1 = cur;
-                i1 = myrow;
-            } else if (cur > v2) {
-                v2 = cur;
-            }
+            top.add(cur, myrow);
         }
         myrow += step_rows;
         dptr += step_rows;
@@ -606,17 +463,212 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
     for (; it < n_iter; ++it) iteration(std::false_type());
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-    if (owner) {
-        LaneCand *out = reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader));
-        LaneCand lc;
-        lc.v1 = v1;
-        lc.i1 = i1 == kNoRow ? kNoRow : row_offset + i1;
-        lc.v2 = v2;
-        lc.pad = 0;
-        out[gid * R + fsel] = lc;
-    }
+    if (owner)
+        top.store(reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader)) + (gid * R + fsel), row_offset);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         reinterpret_cast<LaneHeader *>(lane_buf)->n_slots = NG * R;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused pass, third generation, for d = 64 .. 512: A LANE OWNS A FRAME.
+// The cooperative layout above (a group of lanes per frame) spends more instructions on the split
+// reductions of its float32 partial sums, the need bookkeeping and the per-iteration set-up than on
+// the filter itself -- 170 warp instructions per frame for 7 centres at d = 256 (r2v: 13 -- 17.5 ms
+// for the [1, 7] schedule of the bench against the 8 ms of the HBM stream), and the cost grows with
+// every further chunk of four centres.  Here a warp takes 32 CONSECUTIVE frames, one per lane, and
+// walks them in slices of 64 features that arrive through a per-warp cp.async ring
+// ([32 frames][64 + 4 floats]: a lane's 16-byte reads of its own row are bank-conflict free); every
+// lane accumulates the float32 squared distance of ITS frame to all J centres (centre chunks are
+// warp-wide broadcast reads).  No reduction, no shuffle: 64 x (1 + 5 J) instructions per 32 frames
+// and 256 features, ~80 per frame for 7 centres.  The decision is the same -- a centre that cannot
+// beat the frame's minimum by the float32 bound is skipped -- and every other (frame, centre) pair
+// is recomputed by the WHOLE warp in the reference arithmetic, from the frame's row in L2 and with
+// exactly the lane partition and butterfly of kcenters_pass_fast_kernel (lane l holds the float4s
+// l + i G of the row), in centre order per frame: distances, labels and lane records are those of
+// the pass-per-centre path bit for bit.  Lane records: one per (warp, lane), three values in
+// registers (one block of eight warps per SM: registers are not scarce here).
+// ---------------------------------------------------------------------------------------
+static constexpr int kOwnWarps = 8;
+static constexpr int kOwnStages = 3;
+static constexpr int kOwnSlice = 64;                              // floats of a frame per stage
+static constexpr int kOwnRowBytes = (kOwnSlice + 4) * 4;          // 272
+static constexpr int kOwnStageBytes = 32 * kOwnRowBytes;          // 8704
+
+struct LaneTopR {           // LaneTop in registers
+    double v1, v2, v3;
+    long long i1, i2;
+    __device__ __forceinline__ void init() { v1 = v2 = v3 = -INFINITY; i1 = i2 = kNoRow; }
+    __device__ __forceinline__ void add(double cur, long long row)
+    {
+        if (cur > v3) {
+            if (cur > v1) { v3 = v2; v2 = v1; i2 = i1; v1 = cur; i1 = row; }
+            else if (cur > v2) { v3 = v2; v2 = cur; i2 = row; }
+            else v3 = cur;
+        }
+    }
+};
+
+template <int JC>
+__global__ void __launch_bounds__(32 * kOwnWarps, 1)
+kcenters_fused_own_kernel(const float *__restrict__ X, long long n, int d, long long ld,
+                          const float *__restrict__ centers, int J, int label0, int is_sq,
+                          double *__restrict__ dist, int *__restrict__ labels,
+                          long long row_offset, unsigned char *__restrict__ lane_buf, int G,
+                          float one_minus_eps)
+{
+    typedef Metric<MSMB200_SQEUCLIDEAN, float> M;    // acc() is the euclidean family's; the sqrt is applied below
+    extern __shared__ float4 s_c[];                  // [JC][d / 4] NEGATED (rows >= J: copies of the last) | ring
+    const int d4 = d >> 2;
+    {
+        const float4 *c4 = reinterpret_cast<const float4 *>(centers);
+        for (int i = threadIdx.x; i < JC * d4; i += blockDim.x) {
+            const int jc = i / d4;
+            const float4 v = c4[(jc < J ? jc : J - 1) * d4 + (i - jc * d4)];
+            s_c[i] = make_float4(-v.x, -v.y, -v.z, -v.w);
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kOwnWarps + warp;       // global warp
+    const long long NW = (long long)gridDim.x * kOwnWarps;
+    const long long n_tiles = (n + 31) >> 5;
+    const long long my_tiles = gw < n_tiles ? (n_tiles - 1 - gw) / NW + 1 : 0;
+    const int n_slices = d / kOwnSlice;
+    const long long Q = my_tiles * n_slices;                             // stages this warp consumes
+    const long long ld4 = ld >> 2;
+    const float4 *X4 = reinterpret_cast<const float4 *>(X);
+    const int lig = lane & (G - 1);                                      // lane of the reference group
+    const int iters = d4 / G;
+
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(s_c + (size_t)JC * d4) +
+                          (unsigned)warp * (kOwnStages * kOwnStageBytes);
+    // ---- producer side: stage pq = (tile pq / n_slices, slice pq % n_slices); instruction q of a stage
+    // moves the 64-float slices of frames 2 q and 2 q + 1 (16 lanes x 16 bytes each)
+    long long pq = 0;
+    int p_slice = 0;
+    long long p_r0 = gw << 5;                                            // first row of the tile being produced
+    unsigned off_p = 0, off_c = 0;
+    const unsigned dst_lane = (unsigned)(lane >> 4) * kOwnRowBytes + (unsigned)(lane & 15) * 16;
+    auto prefetch = [&]() {
+        if (pq < Q) {
+            const unsigned dst = ring + off_p + dst_lane;
+            if (p_r0 + 32 <= n) {                                        // warp uniform: every frame exists
+                const float4 *p = X4 + (p_r0 + (lane >> 4)) * ld4 + p_slice * (kOwnSlice / 4) + (lane & 15);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    cp_async16(dst + (unsigned)q * (2 * kOwnRowBytes), p);
+                    p += 2 * ld4;
+                }
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < 16; ++q) {
+                    long long row = p_r0 + 2 * q + (lane >> 4);
+                    row = row < n ? row : n - 1;                         // clamped: loaded, never used
+                    cp_async16(dst + (unsigned)q * (2 * kOwnRowBytes),
+                               X4 + row * ld4 + p_slice * (kOwnSlice / 4) + (lane & 15));
+                }
+            }
+            if (++p_slice == n_slices) { p_slice = 0; p_r0 += NW << 5; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");            // (possibly empty: keeps the count uniform)
+        ++pq;
+        off_p = off_p + kOwnStageBytes == kOwnStages * kOwnStageBytes ? 0u : off_p + kOwnStageBytes;
+    };
+#pragma unroll 1
+    for (int s = 0; s < kOwnStages - 1; ++s) prefetch();
+
+    LaneTopR top;
+    top.init();
+    long long r0 = gw << 5;
+    for (long long t = 0; t < my_tiles; ++t, r0 += NW << 5) {
+        const long long row = r0 + lane;
+        const bool valid = row < n;
+        // the running minimum of this lane's frame: requested now, used after the slices
+        double cur = INFINITY;
+        if (valid) cur = __ldcg(dist + row);
+        float2 acc[JC];
+#pragma unroll
+        for (int j = 0; j < JC; ++j) acc[j] = make_float2(0.f, 0.f);
+        for (int sl = 0; sl < n_slices; ++sl) {
+            prefetch();
+            asm volatile("cp.async.wait_group %0;" :: "n"(kOwnStages - 1) : "memory");
+            __syncwarp();                                                // every lane's copies of this stage have landed
+            const unsigned xrow = ring + off_c + (unsigned)lane * kOwnRowBytes;
+            const float4 *cs = s_c + sl * (kOwnSlice / 4);
+#pragma unroll 4
+            for (int i = 0; i < kOwnSlice / 4; ++i) {
+                const float4 x = lds128(xrow + (unsigned)i * 16);
+#pragma unroll
+                for (int j = 0; j < JC; ++j) {
+                    const float4 c = cs[j * d4 + i];                     // the same address in every lane: broadcast
+                    float2 u = __fadd2_rn(make_float2(x.x, x.y), make_float2(c.x, c.y));
+                    acc[j] = __ffma2_rn(u, u, acc[j]);
+                    u = __fadd2_rn(make_float2(x.z, x.w), make_float2(c.z, c.w));
+                    acc[j] = __ffma2_rn(u, u, acc[j]);
+                }
+            }
+            __syncwarp();                                                // stage consumed: the next prefetch refills it
+            off_c = off_c + kOwnStageBytes == kOwnStages * kOwnStageBytes ? 0u : off_c + kOwnStageBytes;
+        }
+        int lab = -1;
+        // float upper bound of what the float32 sums are compared with
+        float bound = __double2float_ru(is_sq ? cur : cur * cur);
+#pragma unroll
+        for (int j = 0; j < JC; ++j) {
+            if (j >= J) break;                                           // warp uniform
+            const float tot = acc[j].x + acc[j].y;
+            // certainly not below the current minimum -> the reference's mask is false (the relative margin
+            // needs float32's normal range: tiny and overflowed sums always go to the exact step)
+            const bool need = valid && !(tot * one_minus_eps >= bound && tot >= 1e-30f && tot <= 3.0e38f);
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            while (m) {                                                  // frames in ascending order; centres ascend outside
+                const int f = __ffs(m) - 1;
+                m &= m - 1;
+                const float4 *xp = X4 + (r0 + f) * ld4 + lig;
+                const float4 *cn = s_c + j * d4 + lig;
+                double a = 0.0, b = 0.0;
+                for (int i = 0; i < iters; ++i) {
+                    const float4 xv = __ldcg(xp + i * G);                // the row was streamed a moment ago: L2
+                    const float4 c = cn[i * G];
+                    M::acc(a, b, xv.x, -c.x);
+                    M::acc(a, b, xv.y, -c.y);
+                    M::acc(a, b, xv.z, -c.z);
+                    M::acc(a, b, xv.w, -c.w);
+                }
+                a = group_combine<false>(a, G);
+                if (lane == f) {
+                    const double dv = is_sq ? a : sqrt(a);
+                    if (dv < cur) {                                      // strict: kcenters.py:93
+                        cur = dv;
+                        lab = label0 + j;
+                        bound = __double2float_ru(is_sq ? dv : a);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            if (lab >= 0) {
+                dist[row] = cur;
+                labels[row] = lab;
+            }
+            top.add(cur, row);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    {
+        LaneCand lc;
+        lc.v1 = top.v1;
+        lc.i1 = top.i1 == kNoRow ? kNoRow : row_offset + top.i1;
+        lc.v2 = top.v2;
+        lc.i2 = top.i2 == kNoRow ? kNoRow : row_offset + top.i2;
+        lc.v3 = top.v3;
+        lc.pad = 0;
+        reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader))[gw * 32 + lane] = lc;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        reinterpret_cast<LaneHeader *>(lane_buf)->n_slots = NW * 32;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -634,7 +686,7 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
                        unsigned char *__restrict__ set_out)
 {
     __shared__ ArgMax s_arg[32];
-    __shared__ double s_v2[32];
+    __shared__ double s_v3[32];
     __shared__ unsigned long long s_cnt[32];
     __shared__ unsigned long long s_total;
     __shared__ int s_count;
@@ -643,32 +695,33 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
     const long long n_slots = reinterpret_cast<const LaneHeader *>(lane_buf)->n_slots;
     const LaneCand *lc = reinterpret_cast<const LaneCand *>(lane_buf + sizeof(LaneHeader));
 
-    // (1) global arg-max of v1 (lowest row among equals) and the largest runner-up
+    // (1) global arg-max of v1 (lowest row among equals) and the largest third best
     ArgMax best{-INFINITY, kNoRow};
-    double maxv2 = -INFINITY;
+    double maxv3 = -INFINITY;
     for (long long s = tid; s < n_slots; s += blockDim.x) {
         ArgMax c{lc[s].v1, lc[s].i1};
         if (c.i != kNoRow) best = argmax_merge(best, c);
-        maxv2 = fmax(maxv2, lc[s].v2);
+        maxv3 = fmax(maxv3, lc[s].v3);
     }
     best = argmax_warp(best);
-    for (int off = 16; off > 0; off >>= 1) maxv2 = fmax(maxv2, __shfl_xor_sync(0xffffffffu, maxv2, off));
-    if (lane == 0) { s_arg[warp] = best; s_v2[warp] = maxv2; }
+    for (int off = 16; off > 0; off >>= 1) maxv3 = fmax(maxv3, __shfl_xor_sync(0xffffffffu, maxv3, off));
+    if (lane == 0) { s_arg[warp] = best; s_v3[warp] = maxv3; }
     __syncthreads();
     if (warp == 0) {
         ArgMax b = s_arg[lane];
-        double m2 = s_v2[lane];
+        double m3 = s_v3[lane];
         b = argmax_warp(b);
-        for (int off = 16; off > 0; off >>= 1) m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, off));
-        if (lane == 0) { s_best = b; s_v2[0] = m2; }
+        for (int off = 16; off > 0; off >>= 1) m3 = fmax(m3, __shfl_xor_sync(0xffffffffu, m3, off));
+        if (lane == 0) { s_best = b; s_v3[0] = m3; }
     }
     __syncthreads();
     best = s_best;
-    maxv2 = s_v2[0];
+    maxv3 = s_v3[0];
 
-    // (2) key of the t_cap-th largest lane maximum (0 if fewer than t_cap are positive): radix select,
-    //     8 bits per round from the top -- 8 passes over the lane records instead of the 63 of a
-    //     bitwise search (this block is the serial section between two fused passes)
+    // (2) key of the t_cap-th largest ENTRY (every lane contributes its two largest values; 0 if fewer
+    //     than t_cap are positive): radix select, 8 bits per round from the top -- 8 passes over the
+    //     lane records instead of the 63 of a bitwise search (this block is the serial section
+    //     between two fused passes)
     unsigned long long K = 0;
     {
         __shared__ unsigned s_hist[256];
@@ -676,7 +729,8 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
         __shared__ unsigned s_rank;
         // positive keys in all
         unsigned long long cnt = 0;
-        for (long long s = tid; s < n_slots; s += blockDim.x) cnt += cand_key(lc[s].v1) != 0ull;
+        for (long long s = tid; s < n_slots; s += blockDim.x)
+            cnt += (cand_key(lc[s].v1) != 0ull) + (cand_key(lc[s].v2) != 0ull);
         for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
         if (lane == 0) s_cnt[warp] = cnt;
         __syncthreads();
@@ -692,10 +746,14 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
                 __syncthreads();
                 const unsigned long long prefix = s_prefix;
                 for (long long s = tid; s < n_slots; s += blockDim.x) {
-                    const unsigned long long key = cand_key(lc[s].v1);
-                    // keys that agree with the digits chosen so far
-                    if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
-                        atomicAdd(&s_hist[(unsigned)(key >> shift) & 0xFFu], 1u);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned long long key = cand_key(e ? lc[s].v2 : lc[s].v1);
+                        // keys that agree with the digits chosen so far (a zero key -- no entry -- only
+                        // ever lands in bin 0 of a prefix that is still all zeros, below every rank asked for)
+                        if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8)))
+                            atomicAdd(&s_hist[(unsigned)(key >> shift) & 0xFFu], 1u);
+                    }
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -716,7 +774,7 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
         __syncthreads();
     }
 
-    // (3) candidates: lane maxima strictly above that value (< t_cap of them), plus the arg-max
+    // (3) candidates: entries strictly above that value (< t_cap of them), plus the arg-max
     SetHeader *hdr = reinterpret_cast<SetHeader *>(set_out);
     double *val = set_val(set_out);
     long long *idx = set_idx(set_out, t_cap);
@@ -725,12 +783,16 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
     __syncthreads();
     bool have_best = false;
     for (long long s = tid; s < n_slots; s += blockDim.x) {
-        const double v = lc[s].v1;
-        if (cand_key(v) > K) {
-            const int slot = atomicAdd(&s_count, 1);
-            val[slot] = v;
-            idx[slot] = lc[s].i1;
-            if (lc[s].i1 == best.i) have_best = true;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double v = e ? lc[s].v2 : lc[s].v1;
+            const long long i = e ? lc[s].i2 : lc[s].i1;
+            if (cand_key(v) > K) {
+                const int slot = atomicAdd(&s_count, 1);
+                val[slot] = v;
+                idx[slot] = i;
+                if (i == best.i) have_best = true;
+            }
         }
     }
     const int any_best = __syncthreads_or(have_best);
@@ -744,10 +806,11 @@ kcenters_select_kernel(const unsigned char *__restrict__ lane_buf, const float *
     if (tid == 0) {
         hdr->count = count;
         hdr->cap = t_cap;
-        // frames that are not candidates: not a lane maximum (<= largest runner-up) or a lane
-        // maximum at or below the cut (<= its value; 0 when the cut is "everything positive")
+        // frames that are not candidates: neither of their lane's two largest (<= its third best <= the
+        // largest third best) or an entry at or below the cut (<= its value; 0 when the cut is
+        // "everything positive")
         const double cut = K ? __longlong_as_double((long long)K) : 0.0;
-        hdr->tau = fmax(maxv2, cut);
+        hdr->tau = fmax(maxv3, cut);
     }
     // (4) their frames
     for (int c = warp; c < count; c += blockDim.x >> 5) {
@@ -935,29 +998,16 @@ extern "C" int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int6
     const float *crow = reinterpret_cast<const float *>(
         reinterpret_cast<const unsigned char *>(centers) + sizeof(CentersHeader) + (size_t)j_cap * 8);
     const float om_eps = 1.0f - 4.0f * (float)(d + 8) * 5.9604645e-8f;
-    // centres per chunk: R * JB float32 sums are reduced at once and must not outnumber the lanes
-#define MSMB_MULTI(METRIC, I, RR, F, JBV)                                                         \
-    do {                                                                                          \
-        auto kern = kcenters_multi_pass_kernel<METRIC, I, RR, F, JBV>;                            \
-        const size_t smem = (size_t)((n_centers + JBV - 1) / JBV * JBV) * d * sizeof(float) +     \
-            ((F) ? 0 : (size_t)(kThreads / 32) * kStages * RR * I * 32 * sizeof(float4));         \
-        MSMB_REQUIRE(smem <= 113 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
-                     "the shared memory of two resident blocks", n_centers, d);                   \
-        if (smem > 48 * 1024)                                                                     \
-            MSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                           (int)smem));                                           \
-        kern<<<grid, kThreads, smem, st>>>((const float *)X, n, d, ld, crow, n_centers, label0,   \
-                                           distances, labels, row_offset,                         \
-                                           (unsigned char *)lane_buf, G, om_eps);                 \
-    } while (0)
-    // the second-generation fused pass (same results bit for bit); MSMB200_K2B_V1=1 keeps the first one
-    const char *v1_env = getenv("MSMB200_K2B_V1");
-    const bool fused_v1 = v1_env && atoi(v1_env) != 0;
+#define MSMB_FIRST(METRIC, I, RR)                                                                 \
+    kcenters_first_pass_kernel<METRIC, I, RR><<<grid, kThreads, lane_top_bytes(G, RR), st>>>(    \
+        (const float *)X, n, d, ld, crow, label0, distances, labels, row_offset,                  \
+        (unsigned char *)lane_buf, G)
 #define MSMB_FUSED(METRIC, I, RR, JBV)                                                            \
     do {                                                                                          \
         auto kern = kcenters_fused_pass_kernel<METRIC, I, RR, JBV>;                               \
         const size_t smem = (size_t)((n_centers + JBV - 1) / JBV * JBV) * d * sizeof(float) +     \
-            (size_t)(kThreads / 32) * kStages * RR * I * 32 * sizeof(float4);                     \
+            (size_t)(kThreads / 32) * kStages * RR * I * 32 * sizeof(float4) +                    \
+            lane_top_bytes(G, RR);                                                                \
         MSMB_REQUIRE(smem <= 113 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
                      "the shared memory of two resident blocks", n_centers, d);                   \
         if (smem > 48 * 1024)                                                                     \
@@ -967,29 +1017,59 @@ extern "C" int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int6
                                            distances, labels, row_offset,                         \
                                            (unsigned char *)lane_buf, G, om_eps);                 \
     } while (0)
-#define MSMB_MULTI_M(I, RR, F, JBV)                                                               \
-    do {                                                                                          \
-        if (!(F) && !fused_v1) {                                                                  \
-            if (metric == MSMB200_EUCLIDEAN) MSMB_FUSED(MSMB200_EUCLIDEAN, I, RR, JBV);           \
-            else MSMB_FUSED(MSMB200_SQEUCLIDEAN, I, RR, JBV);                                     \
-        } else if (metric == MSMB200_EUCLIDEAN) MSMB_MULTI(MSMB200_EUCLIDEAN, I, RR, F, JBV);     \
-        else MSMB_MULTI(MSMB200_SQEUCLIDEAN, I, RR, F, JBV);                                      \
-    } while (0)
-#define MSMB_MULTI_F(I, RR)                                                                       \
+    // centres per chunk (JB): R * JB float32 sums are reduced at once and must not outnumber the lanes
+#define MSMB_PASS_M(METRIC, I, RR)                                                                \
     do {                                                                                          \
         const int jb = G / RR >= 4 ? 4 : G / RR;                                                  \
-        if (first) MSMB_MULTI_M(I, RR, true, 1);                                                  \
-        else if (jb == 4) MSMB_MULTI_M(I, RR, false, 4);                                          \
-        else if (jb == 2) MSMB_MULTI_M(I, RR, false, 2);                                          \
-        else MSMB_MULTI_M(I, RR, false, 1);                                                       \
+        if (first) MSMB_FIRST(METRIC, I, RR);                                                     \
+        else if (jb == 4) MSMB_FUSED(METRIC, I, RR, 4);                                           \
+        else if (jb == 2) MSMB_FUSED(METRIC, I, RR, 2);                                           \
+        else MSMB_FUSED(METRIC, I, RR, 1);                                                        \
     } while (0)
-    if (iters == 1) MSMB_MULTI_F(1, 4);
-    else if (iters == 2) MSMB_MULTI_F(2, 4);
-    else MSMB_MULTI_F(4, 2);
-#undef MSMB_MULTI_F
-#undef MSMB_MULTI_M
+#define MSMB_PASS(I, RR)                                                                          \
+    do {                                                                                          \
+        if (metric == MSMB200_EUCLIDEAN) MSMB_PASS_M(MSMB200_EUCLIDEAN, I, RR);                   \
+        else MSMB_PASS_M(MSMB200_SQEUCLIDEAN, I, RR);                                             \
+    } while (0)
+    const char *coop_env = getenv("MSMB200_K2B_COOP");          // 1: keep the cooperative fused pass (A/B timing)
+    if (!first && d % kOwnSlice == 0 && !(coop_env && atoi(coop_env) != 0)) {
+        // lane-owns-frame fused pass: one block of eight warps per SM
+        const long long n_tiles32 = (n + 31) / 32;
+        long long gb = (n_tiles32 + kOwnWarps - 1) / kOwnWarps;
+        if (gb > sm_count()) gb = sm_count();
+        if (gb < 1) gb = 1;
+        MSMB_REQUIRE(lane_bytes >= sizeof(LaneHeader) + sizeof(LaneCand) * (size_t)gb * kOwnWarps * 32,
+                     "kcenters_multi_pass: lane buffer too small");
+        const int is_sq = metric == MSMB200_SQEUCLIDEAN ? 1 : 0;
+#define MSMB_OWN(JCV)                                                                             \
+    do {                                                                                          \
+        auto kern = kcenters_fused_own_kernel<JCV>;                                               \
+        const size_t smem = (size_t)JCV * d * sizeof(float) +                                     \
+            (size_t)kOwnWarps * kOwnStages * kOwnStageBytes;                                      \
+        MSMB_REQUIRE(smem <= 227 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
+                     "the shared memory of a block", n_centers, d);                               \
+        MSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       (int)smem));                                               \
+        kern<<<(unsigned)gb, 32 * kOwnWarps, smem, st>>>(                                         \
+            (const float *)X, n, d, ld, crow, n_centers, label0, is_sq, distances, labels,        \
+            row_offset, (unsigned char *)lane_buf, G, om_eps);                                    \
+    } while (0)
+        if (n_centers <= 1) MSMB_OWN(1);
+        else if (n_centers <= 2) MSMB_OWN(2);
+        else if (n_centers <= 3) MSMB_OWN(3);
+        else if (n_centers <= 4) MSMB_OWN(4);
+        else if (n_centers <= 6) MSMB_OWN(6);
+        else if (n_centers <= 8) MSMB_OWN(8);
+        else if (n_centers <= 12) MSMB_OWN(12);
+        else MSMB_OWN(16);
+#undef MSMB_OWN
+    } else if (iters == 1) MSMB_PASS(1, 4);
+    else if (iters == 2) MSMB_PASS(2, 4);
+    else MSMB_PASS(4, 2);
+#undef MSMB_PASS
+#undef MSMB_PASS_M
 #undef MSMB_FUSED
-#undef MSMB_MULTI
+#undef MSMB_FIRST
     MSMB_LAUNCH_CHECK();
     return MSMB200_OK;
 }

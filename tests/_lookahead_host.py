@@ -1,18 +1,19 @@
 """Host stand-in for msmbuilder_b200._kernels.LookaheadState (test infrastructure).
 
-It models exactly the information flow of csrc/kcenters_lookahead.cu -- per-lane top two of the
-running minima, candidate cut at the T-th lane maximum, the bound tau on every frame that is not a
-candidate, the certified chain -- with NumPy arithmetic through the oracle, so the *logic* of the
-look-ahead (what may be certified, tie handling, degenerate inputs) is pinned to the reference loop on
-the CPU, independently of the CUDA kernels (tests/test_gpu_lookahead.py pins those)."""
+It models exactly the information flow of csrc/kcenters_lookahead.cu -- per-lane top three of the
+running minima (the two largest are entries, the third bounds the rest of the lane), candidate cut at
+the T-th largest entry, the bound tau on every frame that is not a candidate, the certified chain --
+with NumPy arithmetic through the oracle, so the *logic* of the look-ahead (what may be certified, tie
+handling, degenerate inputs) is pinned to the reference loop on the CPU, independently of the CUDA
+kernels (tests/test_gpu_lookahead.py pins those)."""
 import numpy as np
 import torch
 
 
 class HostLookahead(object):
     """Host stand-in for _kernels.LookaheadState (same five methods, NumPy arithmetic through the
-    oracle): rows are dealt to `n_lanes` strided lanes that keep their two largest running minima,
-    exactly the information the CUDA pass leaves behind."""
+    oracle): rows are dealt to `n_lanes` strided lanes that keep their three largest running minima
+    (first row first among equals), exactly the information the CUDA pass leaves behind."""
 
     def __init__(self, Xl, row_offset, n_lanes=7, t_cap=5, j_cap=4):
         from oracle import libdistance_oracle as lo
@@ -55,27 +56,29 @@ class HostLookahead(object):
     def select(self):
         out = torch.zeros(self.set_len, dtype=torch.float64)
         dist_np = self.distances.numpy()
-        tops, seconds = [], [-np.inf]
+        entries, thirds, tops = [], [-np.inf], []
         for lane in range(self.n_lanes):
             rows = np.arange(lane, self.n, self.n_lanes)
             if len(rows) == 0:
                 continue
             v = dist_np[rows]
-            a = int(np.argmax(v))
-            tops.append((v[a], self.row_offset + int(rows[a])))
-            if len(rows) > 1:
-                seconds.append(np.max(np.delete(v, a)))
+            order = sorted(range(len(rows)), key=lambda r: (-v[r], r))     # strict '>' updates: first row first
+            tops.append((v[order[0]], self.row_offset + int(rows[order[0]])))
+            for r in order[:2]:
+                entries.append((v[r], self.row_offset + int(rows[r])))
+            if len(rows) > 2:
+                thirds.append(v[order[2]])
         if not tops:
             out[1] = -np.inf
             return out
         best = min(tops, key=lambda t: (-t[0], t[1]))
-        vals = sorted((t[0] for t in tops if t[0] > 0), reverse=True)
+        vals = sorted((t[0] for t in entries if t[0] > 0), reverse=True)
         cut = vals[self.t_cap - 1] if len(vals) >= self.t_cap else 0.0
-        cands = [t for t in tops if t[0] > 0 and t[0] > cut]
+        cands = [t for t in entries if t[0] > 0 and t[0] > cut]
         if best not in cands:
             cands.append(best)
         out[0] = len(cands)
-        out[1] = max(max(seconds), cut)
+        out[1] = max(max(thirds), cut)
         for c, (v, gi) in enumerate(cands):
             out[2 + c] = v
             out[2 + self.t_cap + c] = gi

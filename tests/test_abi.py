@@ -50,7 +50,7 @@ def test_lookahead_host_helpers():
     assert lib.msmb200_kcenters_lookahead_supported(256, 258, _lib.F32, eu) == 0      # rows not 16-byte aligned
     assert lib.msmb200_kcenters_set_bytes(256, 512) == 32 + 512 * 16 + 512 * 256 * 4
     assert lib.msmb200_kcenters_centers_bytes(256, 16) == 32 + 16 * 8 + 16 * 256 * 4
-    assert lib.msmb200_kcenters_lane_bytes(0) >= 32 + 32 * 148 * 8 * 256
+    assert lib.msmb200_kcenters_lane_bytes(0) >= 32 + 48 * 148 * 9 * 256
 
 
 def test_no_cpu_fallback_is_loud():

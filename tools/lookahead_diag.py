@@ -55,12 +55,13 @@ def main():
     vals = cs[32:32 + 8 * st.t_cap].view(torch.float64)[:count].numpy()
     lane = st.lane.cpu()
     n_slots = int(lane[:8].view(torch.int64)[0])
-    rec = lane[32:32 + 32 * n_slots].view(torch.float64).reshape(n_slots, 4).numpy()
-    v1, v2 = rec[:, 0], rec[:, 2]
+    rec = lane[32:32 + 48 * n_slots].view(torch.float64).reshape(n_slots, 6).numpy()   # v1 i1 v2 i2 v3 pad
+    v1, v2, v3 = rec[:, 0], rec[:, 2], rec[:, 4]
     sv = np.sort(vals)[::-1]
     d_all = np.sort(st.distances.cpu().numpy())[::-1]
-    print("first set: count %d  tau %.6f  | largest lane runner-up %.6f  T-th lane maximum %.6f"
-          % (count, tau, v2.max(), np.sort(v1)[::-1][min(st.t_cap, len(v1)) - 1]))
+    ent = np.sort(np.concatenate([v1, v2]))[::-1]
+    print("first set: count %d  tau %.6f  | largest lane third best %.6f  T-th largest entry %.6f  (largest runner-up %.6f)"
+          % (count, tau, v3.max(), ent[min(st.t_cap, len(ent)) - 1], v2.max()))
     print("top candidate values:", np.round(sv[:12], 4))
     print("rank of tau among ALL frames' distances: %d" % int((d_all > tau).sum()))
     print("lane slots %d; top-20 frames' distances: %s" % (n_slots, np.round(d_all[:20], 4)))
