@@ -343,6 +343,12 @@ def run_ours(args):
     profiling = os.environ.get("MSMB_PROFILE") == "1"     # ncu --profile-from-start off
     if profiling:
         torch.cuda.profiler.start()
+    # like timeit: no cyclic garbage collection inside the timed region (a generation-2 sweep of this
+    # process -- torch, sklearn and 500 tensor views per step -- takes 50-100 ms and showed up as single
+    # tICA phases of 80-118 ms between steps of 30 ms, profiles/r2w_bench_gc_outliers.json)
+    import gc
+    gc.collect()
+    gc.disable()
     sampler.mark_begin()
     t_start.record()
     state["time_passes"] = True          # CUDA events around every fused K2 launch (look-ahead path)
@@ -358,6 +364,7 @@ def run_ours(args):
             pass_centres.append(nc)
     t_stop.record()
     barrier()
+    gc.enable()
     sampler.mark_end()
     if profiling:
         torch.cuda.profiler.stop()

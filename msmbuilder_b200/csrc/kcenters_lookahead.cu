@@ -469,207 +469,12 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
         reinterpret_cast<LaneHeader *>(lane_buf)->n_slots = NG * R;
 }
 
-// ---------------------------------------------------------------------------------------
-// Fused pass, third generation, for d = 64 .. 512: A LANE OWNS A FRAME.
-// The cooperative layout above (a group of lanes per frame) spends more instructions on the split
-// reductions of its float32 partial sums, the need bookkeeping and the per-iteration set-up than on
-// the filter itself -- 170 warp instructions per frame for 7 centres at d = 256 (r2v: 13 -- 17.5 ms
-// for the [1, 7] schedule of the bench against the 8 ms of the HBM stream), and the cost grows with
-// every further chunk of four centres.  Here a warp takes 32 CONSECUTIVE frames, one per lane, and
-// walks them in slices of 64 features that arrive through a per-warp cp.async ring
-// ([32 frames][64 + 4 floats]: a lane's 16-byte reads of its own row are bank-conflict free); every
-// lane accumulates the float32 squared distance of ITS frame to all J centres (centre chunks are
-// warp-wide broadcast reads).  No reduction, no shuffle: 64 x (1 + 5 J) instructions per 32 frames
-// and 256 features, ~80 per frame for 7 centres.  The decision is the same -- a centre that cannot
-// beat the frame's minimum by the float32 bound is skipped -- and every other (frame, centre) pair
-// is recomputed by the WHOLE warp in the reference arithmetic, from the frame's row in L2 and with
-// exactly the lane partition and butterfly of kcenters_pass_fast_kernel (lane l holds the float4s
-// l + i G of the row), in centre order per frame: distances, labels and lane records are those of
-// the pass-per-centre path bit for bit.  Lane records: one per (warp, lane), three values in
-// registers (one block of eight warps per SM: registers are not scarce here).
-// ---------------------------------------------------------------------------------------
-static constexpr int kOwnWarps = 8;
-static constexpr int kOwnStages = 3;
-static constexpr int kOwnSlice = 64;                              // floats of a frame per stage
-static constexpr int kOwnRowBytes = (kOwnSlice + 4) * 4;          // 272
-static constexpr int kOwnStageBytes = 32 * kOwnRowBytes;          // 8704
-
-struct LaneTopR {           // LaneTop in registers
-    double v1, v2, v3;
-    long long i1, i2;
-    __device__ __forceinline__ void init() { v1 = v2 = v3 = -INFINITY; i1 = i2 = kNoRow; }
-    __device__ __forceinline__ void add(double cur, long long row)
-    {
-        if (cur > v3) {
-            if (cur > v1) { v3 = v2; v2 = v1; i2 = i1; v1 = cur; i1 = row; }
-            else if (cur > v2) { v3 = v2; v2 = cur; i2 = row; }
-            else v3 = cur;
-        }
-    }
-};
-
-template <int JC>
-__global__ void __launch_bounds__(32 * kOwnWarps, 1)
-kcenters_fused_own_kernel(const float *__restrict__ X, long long n, int d, long long ld,
-                          const float *__restrict__ centers, int J, int label0, int is_sq,
-                          double *__restrict__ dist, int *__restrict__ labels,
-                          long long row_offset, unsigned char *__restrict__ lane_buf, int G,
-                          float one_minus_eps)
-{
-    typedef Metric<MSMB200_SQEUCLIDEAN, float> M;    // acc() is the euclidean family's; the sqrt is applied below
-    extern __shared__ float4 s_c[];                  // [JC][d / 4] NEGATED (rows >= J: copies of the last) | ring
-    const int d4 = d >> 2;
-    {
-        const float4 *c4 = reinterpret_cast<const float4 *>(centers);
-        for (int i = threadIdx.x; i < JC * d4; i += blockDim.x) {
-            const int jc = i / d4;
-            const float4 v = c4[(jc < J ? jc : J - 1) * d4 + (i - jc * d4)];
-            s_c[i] = make_float4(-v.x, -v.y, -v.z, -v.w);
-        }
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * kOwnWarps + warp;       // global warp
-    const long long NW = (long long)gridDim.x * kOwnWarps;
-    const long long n_tiles = (n + 31) >> 5;
-    const long long my_tiles = gw < n_tiles ? (n_tiles - 1 - gw) / NW + 1 : 0;
-    const int n_slices = d / kOwnSlice;
-    const long long Q = my_tiles * n_slices;                             // stages this warp consumes
-    const long long ld4 = ld >> 2;
-    const float4 *X4 = reinterpret_cast<const float4 *>(X);
-    const int lig = lane & (G - 1);                                      // lane of the reference group
-    const int iters = d4 / G;
-
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(s_c + (size_t)JC * d4) +
-                          (unsigned)warp * (kOwnStages * kOwnStageBytes);
-    // ---- producer side: stage pq = (tile pq / n_slices, slice pq % n_slices); instruction q of a stage
-    // moves the 64-float slices of frames 2 q and 2 q + 1 (16 lanes x 16 bytes each)
-    long long pq = 0;
-    int p_slice = 0;
-    long long p_r0 = gw << 5;                                            // first row of the tile being produced
-    unsigned off_p = 0, off_c = 0;
-    const unsigned dst_lane = (unsigned)(lane >> 4) * kOwnRowBytes + (unsigned)(lane & 15) * 16;
-    auto prefetch = [&]() {
-        if (pq < Q) {
-            const unsigned dst = ring + off_p + dst_lane;
-            if (p_r0 + 32 <= n) {                                        // warp uniform: every frame exists
-                const float4 *p = X4 + (p_r0 + (lane >> 4)) * ld4 + p_slice * (kOwnSlice / 4) + (lane & 15);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    cp_async16(dst + (unsigned)q * (2 * kOwnRowBytes), p);
-                    p += 2 * ld4;
-                }
-            } else {
-#pragma unroll 1
-                for (int q = 0; q < 16; ++q) {
-                    long long row = p_r0 + 2 * q + (lane >> 4);
-                    row = row < n ? row : n - 1;                         // clamped: loaded, never used
-                    cp_async16(dst + (unsigned)q * (2 * kOwnRowBytes),
-                               X4 + row * ld4 + p_slice * (kOwnSlice / 4) + (lane & 15));
-                }
-            }
-            if (++p_slice == n_slices) { p_slice = 0; p_r0 += NW << 5; }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");            // (possibly empty: keeps the count uniform)
-        ++pq;
-        off_p = off_p + kOwnStageBytes == kOwnStages * kOwnStageBytes ? 0u : off_p + kOwnStageBytes;
-    };
-#pragma unroll 1
-    for (int s = 0; s < kOwnStages - 1; ++s) prefetch();
-
-    LaneTopR top;
-    top.init();
-    long long r0 = gw << 5;
-    for (long long t = 0; t < my_tiles; ++t, r0 += NW << 5) {
-        const long long row = r0 + lane;
-        const bool valid = row < n;
-        // the running minimum of this lane's frame: requested now, used after the slices
-        double cur = INFINITY;
-        if (valid) cur = __ldcg(dist + row);
-        float2 acc[JC];
-#pragma unroll
-        for (int j = 0; j < JC; ++j) acc[j] = make_float2(0.f, 0.f);
-        for (int sl = 0; sl < n_slices; ++sl) {
-            prefetch();
-            asm volatile("cp.async.wait_group %0;" :: "n"(kOwnStages - 1) : "memory");
-            __syncwarp();                                                // every lane's copies of this stage have landed
-            const unsigned xrow = ring + off_c + (unsigned)lane * kOwnRowBytes;
-            const float4 *cs = s_c + sl * (kOwnSlice / 4);
-#pragma unroll 4
-            for (int i = 0; i < kOwnSlice / 4; ++i) {
-                const float4 x = lds128(xrow + (unsigned)i * 16);
-#pragma unroll
-                for (int j = 0; j < JC; ++j) {
-                    const float4 c = cs[j * d4 + i];                     // the same address in every lane: broadcast
-                    float2 u = __fadd2_rn(make_float2(x.x, x.y), make_float2(c.x, c.y));
-                    acc[j] = __ffma2_rn(u, u, acc[j]);
-                    u = __fadd2_rn(make_float2(x.z, x.w), make_float2(c.z, c.w));
-                    acc[j] = __ffma2_rn(u, u, acc[j]);
-                }
-            }
-            __syncwarp();                                                // stage consumed: the next prefetch refills it
-            off_c = off_c + kOwnStageBytes == kOwnStages * kOwnStageBytes ? 0u : off_c + kOwnStageBytes;
-        }
-        int lab = -1;
-        // float upper bound of what the float32 sums are compared with
-        float bound = __double2float_ru(is_sq ? cur : cur * cur);
-#pragma unroll
-        for (int j = 0; j < JC; ++j) {
-            if (j >= J) break;                                           // warp uniform
-            const float tot = acc[j].x + acc[j].y;
-            // certainly not below the current minimum -> the reference's mask is false (the relative margin
-            // needs float32's normal range: tiny and overflowed sums always go to the exact step)
-            const bool need = valid && !(tot * one_minus_eps >= bound && tot >= 1e-30f && tot <= 3.0e38f);
-            unsigned m = __ballot_sync(0xffffffffu, need);
-            while (m) {                                                  // frames in ascending order; centres ascend outside
-                const int f = __ffs(m) - 1;
-                m &= m - 1;
-                const float4 *xp = X4 + (r0 + f) * ld4 + lig;
-                const float4 *cn = s_c + j * d4 + lig;
-                double a = 0.0, b = 0.0;
-                for (int i = 0; i < iters; ++i) {
-                    const float4 xv = __ldcg(xp + i * G);                // the row was streamed a moment ago: L2
-                    const float4 c = cn[i * G];
-                    M::acc(a, b, xv.x, -c.x);
-                    M::acc(a, b, xv.y, -c.y);
-                    M::acc(a, b, xv.z, -c.z);
-                    M::acc(a, b, xv.w, -c.w);
-                }
-                a = group_combine<false>(a, G);
-                if (lane == f) {
-                    const double dv = is_sq ? a : sqrt(a);
-                    if (dv < cur) {                                      // strict: kcenters.py:93
-                        cur = dv;
-                        lab = label0 + j;
-                        bound = __double2float_ru(is_sq ? dv : a);
-                    }
-                }
-            }
-        }
-        if (valid) {
-            if (lab >= 0) {
-                dist[row] = cur;
-                labels[row] = lab;
-            }
-            top.add(cur, row);
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-
-    {
-        LaneCand lc;
-        lc.v1 = top.v1;
-        lc.i1 = top.i1 == kNoRow ? kNoRow : row_offset + top.i1;
-        lc.v2 = top.v2;
-        lc.i2 = top.i2 == kNoRow ? kNoRow : row_offset + top.i2;
-        lc.v3 = top.v3;
-        lc.pad = 0;
-        reinterpret_cast<LaneCand *>(lane_buf + sizeof(LaneHeader))[gw * 32 + lane] = lc;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        reinterpret_cast<LaneHeader *>(lane_buf)->n_slots = NW * 32;
-}
+// (A "lane owns its frames" formulation of this pass -- 32 or 64 consecutive frames per warp, one or two
+// per lane, float32 sums without any reduction, the exact step done by the whole warp from L2 -- was
+// built, passed the same bit-for-bit tests and was SLOWER: 13.2 ms (one frame per lane: the warp-wide
+// broadcast reads of the centre chunks saturate the shared-memory pipe) and 16.7 ms (two frames per
+// lane, 128-byte row segments per stage: DRAM page locality) against 11.9 ms for the 7-centre pass
+// of the bench; profiles/r2x_lane_owns_frame_experiment.log.  Removed.)
 
 // ---------------------------------------------------------------------------------------
 // Candidate selection: one block.
@@ -1031,39 +836,7 @@ extern "C" int msmb200_kcenters_multi_pass(const void *X, int64_t n, int d, int6
         if (metric == MSMB200_EUCLIDEAN) MSMB_PASS_M(MSMB200_EUCLIDEAN, I, RR);                   \
         else MSMB_PASS_M(MSMB200_SQEUCLIDEAN, I, RR);                                             \
     } while (0)
-    const char *coop_env = getenv("MSMB200_K2B_COOP");          // 1: keep the cooperative fused pass (A/B timing)
-    if (!first && d % kOwnSlice == 0 && !(coop_env && atoi(coop_env) != 0)) {
-        // lane-owns-frame fused pass: one block of eight warps per SM
-        const long long n_tiles32 = (n + 31) / 32;
-        long long gb = (n_tiles32 + kOwnWarps - 1) / kOwnWarps;
-        if (gb > sm_count()) gb = sm_count();
-        if (gb < 1) gb = 1;
-        MSMB_REQUIRE(lane_bytes >= sizeof(LaneHeader) + sizeof(LaneCand) * (size_t)gb * kOwnWarps * 32,
-                     "kcenters_multi_pass: lane buffer too small");
-        const int is_sq = metric == MSMB200_SQEUCLIDEAN ? 1 : 0;
-#define MSMB_OWN(JCV)                                                                             \
-    do {                                                                                          \
-        auto kern = kcenters_fused_own_kernel<JCV>;                                               \
-        const size_t smem = (size_t)JCV * d * sizeof(float) +                                     \
-            (size_t)kOwnWarps * kOwnStages * kOwnStageBytes;                                      \
-        MSMB_REQUIRE(smem <= 227 * 1024, "kcenters_multi_pass: %d centres of %d floats exceed "   \
-                     "the shared memory of a block", n_centers, d);                               \
-        MSMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                       (int)smem));                                               \
-        kern<<<(unsigned)gb, 32 * kOwnWarps, smem, st>>>(                                         \
-            (const float *)X, n, d, ld, crow, n_centers, label0, is_sq, distances, labels,        \
-            row_offset, (unsigned char *)lane_buf, G, om_eps);                                    \
-    } while (0)
-        if (n_centers <= 1) MSMB_OWN(1);
-        else if (n_centers <= 2) MSMB_OWN(2);
-        else if (n_centers <= 3) MSMB_OWN(3);
-        else if (n_centers <= 4) MSMB_OWN(4);
-        else if (n_centers <= 6) MSMB_OWN(6);
-        else if (n_centers <= 8) MSMB_OWN(8);
-        else if (n_centers <= 12) MSMB_OWN(12);
-        else MSMB_OWN(16);
-#undef MSMB_OWN
-    } else if (iters == 1) MSMB_PASS(1, 4);
+    if (iters == 1) MSMB_PASS(1, 4);
     else if (iters == 2) MSMB_PASS(2, 4);
     else MSMB_PASS(4, 2);
 #undef MSMB_PASS
