@@ -273,9 +273,14 @@ def kcenters_fit_gpu(data_local, row_offset, n_clusters, metric, seed_global, tr
     # the local base address alignment, which FrameStore / torch allocations always satisfy
     if traces is None and lookahead and K.lookahead_supported(data_local, metric):
         gather_sets, bcast = lookahead_collectives(comm=comm)
+        # the chain kernel works on the UNION of the ranks' candidate sets (one block; its cost grows with
+        # the union): every rank keeps its share of the single-GPU cap, the union stays ~1024 candidates and
+        # tau (the largest per-rank cut) stays near the 1024th largest value overall
+        t_cap = max(64, K.LOOKAHEAD_T_CAP // max(1, comm.ws))
+        state = K.LookaheadState(data_local, metric, row_offset=row_offset, t_cap=t_cap)
         ids, rows, distances, labels = K.kcenters_fit_lookahead(
             data_local, n_clusters, metric, seed_global, gather_sets=gather_sets, bcast=bcast,
-            row_offset=row_offset, stats=stats)
+            row_offset=row_offset, stats=stats, state=state)
         k = int(n_clusters)
         cand_bytes = CAND_HEADER + 4 * int(data_local.shape[1])
         ring = torch.zeros((k + 1, cand_bytes), dtype=torch.uint8, device="cuda")
