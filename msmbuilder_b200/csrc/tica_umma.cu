@@ -1247,6 +1247,9 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     // second-generation fp16 engine (tica_umma_v2.cuh): single-CTA tiles for D <= 128, CTA pairs above
     const bool v2 = f16 && env_int("MSMB200_UMMA_V1", 0) == 0;
     const int v2_cg = D <= UM_F ? 1 : 2;
+    // MN-major rolling-window operands (tica_umma_v2.cuh, "MN-major mode"): every CTA has its four feature
+    // blocks and the lag fits the mirror tile
+    const bool v3 = v2 && (D == UM_D || D == UM_F) && lag <= UM_KT && env_int("MSMB200_UMMA_MN", 0) != 0;
     const size_t n_items = v2 ? tica_simt_items(seq_ptrs, seq_rows, n_seq_in, lag, nullptr, nullptr, nullptr) : 0;
     const size_t o_items = off; off = align_up(off + tica_simt_item_bytes() * n_items, 128);
     int dev = 0;
@@ -1294,22 +1297,25 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
         }
         seq_pairs[s] = (int)Pn;
         tile_prefix[s] = (int)tiles;
-        tiles += (Pn + UM_KT - 1) / UM_KT;
+        // MN-major mode: tiles cover every row of the sequence and `lag` rows of zeros behind it
+        tiles += v3 ? (seqs[s].n + lag + UM_KT - 1) / UM_KT : (Pn + UM_KT - 1) / UM_KT;
         if (tiles > 0x7fffffffLL) {
             set_error("too many tiles");
             return MSMB200_E_UNSUPPORTED;
         }
-        for (int which = 0; which < 2; ++which) {
+        for (int which = 0; which < (v3 ? 1 : 2); ++which) {
             // (32 features, Pn rows, D/32 blocks); rows >= Pn read as zeros
+            // (MN-major mode: ONE map over all n rows; the lagged operand is the same converted rows)
             void *base = (void *)(seqs[s].base + (which ? (size_t)lag * ld : 0));
             CUtensorMap *dst = which ? &mapsB[s] : &mapsA[s];
-            const MapKey key{base, Pn, (long long)ld, D, box_blocks};
+            const long long map_rows = v3 ? seqs[s].n : Pn;
+            const MapKey key{base, map_rows, (long long)ld, D, box_blocks};
             auto hit = g_map_cache.find(key);
             if (hit != g_map_cache.end()) {
                 *dst = hit->second;
                 continue;
             }
-            cuuint64_t dims[3] = {32, (cuuint64_t)Pn, (cuuint64_t)(D / 32)};
+            cuuint64_t dims[3] = {32, (cuuint64_t)map_rows, (cuuint64_t)(D / 32)};
             cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
             cuuint32_t box[3] = {32, UM_KT, (cuuint32_t)box_blocks};
             cuuint32_t es[3] = {1, 1, 1};
@@ -1451,6 +1457,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     V.D = D;
     V.box_blocks = box_blocks;
     V.dbg_mode = P.dbg_mode;
+    V.mn = v3 ? 1 : 0;
+    V.lag = lag;
     V.shift = d_shift;
     V.scale = d_scale;
     V.overflow = d_flag;
@@ -1538,14 +1546,14 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
             tica_umma_v2_finalize_kernel<2><<<fin_blocks, 256, 0, st>>>(
                 d_R, V.sums, n_groups, reinterpret_cast<const double *>(wsb + w_E),
                 reinterpret_cast<const double *>(wsb + w_es), d_shift, d_scale, d_flag,
-                n_pairs_total, n_obs, (double)n_seq, D, acc);
+                n_pairs_total, n_obs, (double)n_seq, D, v3 ? 1 : 0, acc);
         } else {
             tica_umma_v2_reduce_kernel<1><<<red_blocks, 256, 0, st>>>(V.lvl1, V.hi, V.lo, n_groups, d_flag, d_R);
             MSMB_LAUNCH_CHECK();
             tica_umma_v2_finalize_kernel<1><<<fin_blocks, 256, 0, st>>>(
                 d_R, V.sums, n_groups, reinterpret_cast<const double *>(wsb + w_E),
                 reinterpret_cast<const double *>(wsb + w_es), d_shift, d_scale, d_flag,
-                n_pairs_total, n_obs, (double)n_seq, D, acc);
+                n_pairs_total, n_obs, (double)n_seq, D, v3 ? 1 : 0, acc);
         }
         MSMB_LAUNCH_CHECK();
         // Range rescue, all on the stream (no host round trip): when a converter raised the flag the

@@ -31,6 +31,21 @@
 //    CG = 1 is the single-CTA kernel for D <= 128 (cta_group::1, M = 128, N = 128 or 64, 148
 //    independent CTAs): narrow inputs no longer pay 256-wide tiles (config 2, 10M x 64).
 //  * Bit-reproducible like v1: every address has one writer, all sums are taken in a fixed order.
+//
+// MN-major mode (P.mn, all four feature blocks per CTA, lag <= 32; profiles/r2z_probe7_mn_major_sw128.log).
+// The K-major chunks above (8 frames of one feature per 16 bytes) cannot serve both operands: the lagged
+// operand's chunks start `lag` frames later, so every frame is TMA-loaded and converted twice and the
+// gather that builds a chunk costs eight 4-byte shared loads.  tcgen05 also takes MN-major fp16 operands
+// (features contiguous, one frame = one 128-byte row of 64 features, SWIZZLE_128B, LBO = distance of the
+// next 64 features, SBO = 8 rows), and the swizzle is a function of the absolute shared-memory address,
+// so a descriptor may start at ANY row: the lagged operand is the same converted buffer, `lag` rows on.
+// Per CTA three windows H (h), L (l), Q (h / 2) of [2 blocks of 64 features][4 ring tiles + 1 mirror tile
+// of 32 rows][128 B] (120 KB, inside the operand ring of the K-major mode); a frame is loaded once and
+// converted once: two 16-byte loads of the raw row, three 16-byte stores.  Tile t's UMMAs read rows
+// [32 t, 32 t + 32 + lag): they wait for ring tiles t and t + 1, a group converts one tile more than it
+// multiplies, ring tile 0 is mirrored behind tile 3.  Tiles cover ALL rows of a sequence plus `lag` rows
+// of zeros (TMA fills them), so G sums x x^T over every row and the finalize kernel takes the tail rows
+// out of C_00 and the head rows out of C_tautau (the float64 edge terms it already has).
 #pragma once
 
 namespace msmb {
@@ -67,6 +82,8 @@ struct V2Params {
     int D;                        // real feature count (32k)
     int box_blocks;               // 32-feature blocks one TMA box brings (4; D / 32 for the single-CTA kernel)
     int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
+    int mn;                       // 1: MN-major rolling-window operands (see "MN-major mode" below)
+    int lag;                      // (MN-major mode) rows between the two operands
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
     int *overflow;                // set to 1 when a scaled value reached 2^6 (or was not finite): float64 rescue
@@ -224,6 +241,23 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
     return v;
 }
+__device__ __forceinline__ float4 lds_v4f(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v4r(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// MN-major windows: rows of 128 bytes (64 features), 4 ring tiles + the mirror of tile 0
+constexpr int V3_WIN_ROWS = 32 * V2_OP_STAGES + 32;               // 160
+constexpr int V3_BLOCK_BYTES = V3_WIN_ROWS * 128;                 // 20480: LBO (next 64 features)
+constexpr int V3_WIN_BYTES = 2 * V3_BLOCK_BYTES;                  // 40960: H, L, Q follow each other
+constexpr int V3_MIRROR = 32 * V2_OP_STAGES * 128;                // 16384: ring tile 0 again, behind tile 3
+static_assert(3 * V3_WIN_BYTES <= V2_OP_STAGES * V2_STAGE_BYTES, "the windows live in the operand ring");
+
 template <int IMM>
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
@@ -274,8 +308,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     // raw ring: a stage holds the two boxes of a tile (unlagged, lagged), box_blocks * 4 KB each; the
     // ring always spans 64 KB, so narrow inputs get a deeper ring (the TMA latency showed as 240 cycles
     // of wait per tile at D = 64 with two stages)
+    const bool mn = P.mn != 0;
     const uint32_t raw_op_bytes = (uint32_t)P.box_blocks * (UM_KT * 128);
-    const uint32_t raw_stage_bytes = 2 * raw_op_bytes;
+    const uint32_t raw_stage_bytes = mn ? raw_op_bytes : 2 * raw_op_bytes;      // MN-major: one box per tile
+    // MN-major: one ring tile more is converted than multiplied (tile t's lagged rows reach into t + 1)
+    const int conv_tiles = (mn && my_tiles > 0) ? my_tiles + 1 : my_tiles;
     const int n_raw = V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes > V2_RAW_MAX
                           ? V2_RAW_MAX : V2_RAW_STAGES * UM_RAW_BYTES / (int)raw_stage_bytes;
     // N of every UMMA: all the columns the group has (a single CTA with <= 64 features runs N = 64)
@@ -345,25 +382,40 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             int stage = 0;
             uint32_t phase = 0;
             const uint64_t policy = l2_evict_first_policy();
-            for (long long t = t_begin; t < t_end; ++t) {
+            for (long long t = t_begin; t < t_begin + conv_tiles; ++t) {
+                if (t >= P.n_tiles) {
+                    // (MN-major) behind the last tile of the call: a tile of zeros, nothing to load
+                    mbar_wait_idle<false>(&ctl->raw_empty[stage], phase ^ 1);
+                    ctl->valid_rows[stage] = 0;
+                    mbar_arrive_local(&ctl->raw_full[stage]);
+                    if (++stage == n_raw) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 while (t >= P.tile_prefix[s + 1]) ++s;
                 const int row0 = (int)(t - P.tile_prefix[s]) * UM_KT;
-                int valid = P.seq_pairs[s] - row0;
+                int valid = P.seq_pairs[s] + (mn ? P.lag : 0) - row0;      // MN-major: all rows of the sequence
                 if (valid > UM_KT) valid = UM_KT;
+                if (valid < 0) valid = 0;
                 mbar_wait_idle<false>(&ctl->raw_empty[stage], phase ^ 1);   // hint only: the TMA issue is latency critical
                 ctl->valid_rows[stage] = valid;
-                mbar_expect_tx(&ctl->raw_full[stage], 2 * P.box_blocks * (UM_KT * 128));
                 unsigned char *st = raw_ring + (size_t)stage * raw_stage_bytes;
-                tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
-                tma_load_3d(st + raw_op_bytes, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
-                            4 * (int)cta_rank, policy);
+                if (mn) {
+                    mbar_expect_tx(&ctl->raw_full[stage], P.box_blocks * (UM_KT * 128));
+                    tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
+                } else {
+                    mbar_expect_tx(&ctl->raw_full[stage], 2 * P.box_blocks * (UM_KT * 128));
+                    tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
+                    tma_load_3d(st + raw_op_bytes, &P.mapsB[s], &ctl->raw_full[stage], 0, row0,
+                                4 * (int)cta_rank, policy);
+                }
                 if (++stage == n_raw) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA; warp-uniform, one elected lane issues)
         if (cta_rank == 0 && my_tiles > 0) {
-            const uint32_t idesc = v2_idesc<CG>(n_cols);
+            // (MN-major mode: bits 15 / 16 = A / B are MN-major)
+            const uint32_t idesc = v2_idesc<CG>(n_cols) | (mn ? ((1u << 15) | (1u << 16)) : 0u);
             // provably warp-uniform operands (a value loaded from shared memory is not, to the compiler)
             const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
             const uint32_t ring_addr = __shfl_sync(0xffffffffu, smem_u32(op_ring), 0);
@@ -387,15 +439,28 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     : "r"(base_lo + (byte_off >> 4)), "r"((uint32_t)((UM_SBO >> 4) | (1u << 14))));
                 return d;
             };
+            // MN-major mode: window `win` (0 H, 1 L, 2 Q), row `row` of the ring: SWIZZLE_128B (layout type 2 in
+            // bits 61-63), LBO = next 64 features, SBO = 8 rows; any row may start a descriptor
+            auto desc_mn = [](uint32_t ring, int win, int row) -> uint64_t {
+                const uint32_t a = ring + (uint32_t)win * V3_WIN_BYTES + (uint32_t)row * 128;
+                uint64_t d;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(d)
+                    : "r"(((a >> 4) & 0x3FFFu) | ((uint32_t)(V3_BLOCK_BYTES >> 4) << 16)),
+                      "r"((uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29))));
+                return d;
+            };
+            const int lag = P.lag;
             int conv_done = 0;                       // tiles whose conversion has been observed
             int released = 0;                        // tiles whose operand stage has been handed back
             while (released < my_tiles) {
-                while (conv_done < my_tiles && conv_done < released + S &&
+                while (conv_done < conv_tiles && conv_done < released + S &&
                        mbar_test(&ctl->conv[conv_done % S], (uint32_t)((conv_done / S) & 1)))
                     ++conv_done;
                 bool progressed = false;
                 // every tile index some region is waiting at: batch the regions that can go
-                for (int tt = released; tt < conv_done; ++tt) {
+                // (MN-major mode: tile tt reads ring tiles tt and tt + 1)
+                const int ready = mn ? conv_done - 1 : conv_done;
+                for (int tt = released; tt < ready; ++tt) {
                     uint32_t mask = 0, firsts = 0;
 #pragma unroll
                     for (int q = 0; q < V2_REGIONS; ++q) {
@@ -421,38 +486,60 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     if (mask == 3u) ++d_fast;
                     if (elect_one_sync()) {
                         const uint32_t f0 = (firsts & 1u) ? 0u : 1u, f1 = (firsts & 2u) ? 0u : 1u;
+                        // operand descriptors of K step ks: A = h, A = l, B = b (lagged h), B = bl (lagged l),
+                        // B = h / 2, B = l (both of the unlagged frames)
+                        const int ring_row = (tt % S) * UM_KT;
+                        auto opd = [&](int which, int ks) -> uint64_t {
+                            if (mn) {
+                                const int ra = ring_row + 16 * ks, rb = ra + lag;
+                                switch (which) {
+                                case 0: return desc_mn(ring_addr, 0, ra);
+                                case 1: return desc_mn(ring_addr, 1, ra);
+                                case 2: return desc_mn(ring_addr, 0, rb);
+                                case 3: return desc_mn(ring_addr, 1, rb);
+                                case 4: return desc_mn(ring_addr, 2, ra);
+                                default: return desc_mn(ring_addr, 1, ra);
+                                }
+                            }
+                            const uint32_t off = ks * 2 * UM_LBO;
+                            switch (which) {
+                            case 0: return desc(base_lo, V2_T_A * V2_TILE + off);
+                            case 1: return desc(base_lo, V2_T_AL * V2_TILE + off);
+                            case 2: return desc(base_lo, V2_T_B * V2_TILE + off);
+                            case 3: return desc(base_lo, V2_T_BL * V2_TILE + off);
+                            case 4: return desc(base_lo, V2_T_AH * V2_TILE + off);
+                            default: return desc(base_lo, V2_T_AL * V2_TILE + off);
+                            }
+                        };
                         if (mask == 3u) {
                             // both regions: 5 UMMAs per K step, A = h kept in the collector for 4 of them
 #pragma unroll
                             for (int ks = 0; ks < UM_KT / 16; ++ks) {
-                                const uint32_t off = ks * 2 * UM_LBO;
-                                const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
-                                const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off);
+                                const uint64_t dA = opd(0, ks);
+                                const uint64_t dB = opd(2, ks);
                                 v2_mma<CG, 1>(tmem, dA, dB, idesc, ks == 0 ? f0 : 1u);
-                                v2_mma<CG, 2>(tmem, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u);
-                                v2_mma<CG, 2>(tmem + RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, ks == 0 ? f1 : 1u);
-                                v2_mma<CG, 3>(tmem + RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u);
-                                v2_mma<CG, 0>(tmem, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u);
+                                v2_mma<CG, 2>(tmem, dA, opd(3, ks), idesc, 1u);
+                                v2_mma<CG, 2>(tmem + RW, dA, opd(4, ks), idesc, ks == 0 ? f1 : 1u);
+                                v2_mma<CG, 3>(tmem + RW, dA, opd(5, ks), idesc, 1u);
+                                v2_mma<CG, 0>(tmem, opd(1, ks), dB, idesc, 1u);
                             }
                         } else if (mask == 1u) {
                             // C_tau alone (G is being drained, or C_tau is catching up)
 #pragma unroll
                             for (int ks = 0; ks < UM_KT / 16; ++ks) {
-                                const uint32_t off = ks * 2 * UM_LBO;
-                                const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
-                                const uint64_t dB = desc(base_lo, V2_T_B * V2_TILE + off);
+                                const uint64_t dA = opd(0, ks);
+                                const uint64_t dB = opd(2, ks);
                                 v2_mma<CG, 1>(tmem, dA, dB, idesc, ks == 0 ? f0 : 1u);
-                                v2_mma<CG, 3>(tmem, dA, desc(base_lo, V2_T_BL * V2_TILE + off), idesc, 1u);
-                                v2_mma<CG, 0>(tmem, desc(base_lo, V2_T_AL * V2_TILE + off), dB, idesc, 1u);
+                                v2_mma<CG, 3>(tmem, dA, opd(3, ks), idesc, 1u);
+                                v2_mma<CG, 0>(tmem, opd(1, ks), dB, idesc, 1u);
                             }
                         } else {
                             // G alone
 #pragma unroll
                             for (int ks = 0; ks < UM_KT / 16; ++ks) {
-                                const uint32_t off = ks * 2 * UM_LBO;
-                                const uint64_t dA = desc(base_lo, V2_T_A * V2_TILE + off);
-                                v2_mma<CG, 1>(tmem + RW, dA, desc(base_lo, V2_T_AH * V2_TILE + off), idesc, ks == 0 ? f1 : 1u);
-                                v2_mma<CG, 3>(tmem + RW, dA, desc(base_lo, V2_T_AL * V2_TILE + off), idesc, 1u);
+                                const uint64_t dA = opd(0, ks);
+                                v2_mma<CG, 1>(tmem + RW, dA, opd(4, ks), idesc, ks == 0 ? f1 : 1u);
+                                v2_mma<CG, 3>(tmem + RW, dA, opd(5, ks), idesc, 1u);
                             }
                         }
 #pragma unroll
@@ -530,6 +617,118 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         uint32_t phase = 0, ophase = 0;
         const bool dbg_on = P.dbg != nullptr && group == 0 && tid == V2_CONV_TID0 && cta_rank == 0;
         long long d_raw = 0, d_empty = 0, d_comp = 0, d_sync = 0;
+        // -------- MN-major mode: a thread owns 8 consecutive features (32 bytes of a raw row) of two rows of
+        // every tile.  Thread map (ct = 0..255): cq = ct & 3 (which 8 of a 32-feature block), fbl / fbh = low /
+        // high bit of the block, swp, rp: rows 2 rp + (fbl ^ swp) and + 16.  Within a quarter warp (fixed
+        // fbh, rp, swp) the lanes with fbl = 1 take the other row of the pair: the 16-byte loads of the
+        // swizzled raw rows and the 16-byte stores into the swizzled windows are both bank-conflict free.
+        float mn_sh[8], mn_sl[8];                        // column sums of this thread's 8 features (float pairs)
+        float mn_sc[8];
+        const int mct = tid - V2_CONV_TID0;
+        const int m_cq = mct & 3, m_fbl = (mct >> 2) & 1, m_swp = (mct >> 3) & 1, m_fbh = (mct >> 4) & 1, m_rp = mct >> 5;
+        const int m_f0 = 32 * (2 * m_fbh + m_fbl) + 8 * m_cq;     // first feature (inside the CTA)
+        if (mn) {
+            const int row_lo = 2 * m_rp + (m_fbl ^ m_swp);
+            const uint32_t swz = (uint32_t)(row_lo & 7);           // (row_lo + 16) & 7 is the same
+            const uint32_t src_a = (uint32_t)((2 * m_fbh + m_fbl) * (UM_KT * 128) + row_lo * 128) + (((2u * m_cq) ^ swz) << 4);
+            const uint32_t src_b = (uint32_t)((2 * m_fbh + m_fbl) * (UM_KT * 128) + row_lo * 128) + (((2u * m_cq + 1u) ^ swz) << 4);
+            const uint32_t dst0 = (uint32_t)(m_fbh * V3_BLOCK_BYTES + row_lo * 128) + ((((uint32_t)(4 * m_fbl + m_cq)) ^ swz) << 4);
+            uint64_t sc2[4], nsh2[4], ps[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sc2[i] = f2_pack(ctl->sc[m_f0 + 2 * i], ctl->sc[m_f0 + 2 * i + 1]);
+                nsh2[i] = f2_pack(ctl->nsh[m_f0 + 2 * i], ctl->nsh[m_f0 + 2 * i + 1]);
+                ps[i] = f2_pack(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { mn_sh[i] = mn_sl[i] = 0.f; mn_sc[i] = ctl->sc[m_f0 + i]; }
+            auto fold_sums = [&]() {                     // float32 partial sums (<= 8 values each) -> float pairs
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float p0, p1;
+                    f2_unpack(ps[i], p0, p1);
+                    const float pv[2] = {p0, p1};
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float ts = pv[e], h0 = mn_sh[2 * i + e];
+                        const float tt = h0 + ts, bp = tt - h0;
+                        mn_sl[2 * i + e] += (h0 - (tt - bp)) + (ts - bp);
+                        mn_sh[2 * i + e] = tt;
+                    }
+                    ps[i] = f2_pack(0.f, 0.f);
+                }
+            };
+            for (int t = 0; t < conv_tiles; ++t) {
+                long long q0 = dbg_on ? clock64() : 0;
+                mbar_wait(&ctl->raw_full[stage], phase);
+                long long q1 = dbg_on ? clock64() : 0;
+                mbar_wait(&ctl->empty[ostage], ophase ^ 1);          // the UMMAs that read this ring tile are done
+                long long q2 = dbg_on ? clock64() : 0;
+                const int valid = ctl->valid_rows[stage];
+                const uint32_t rawst = raw_s + (uint32_t)stage * raw_stage_bytes;
+                const uint32_t st = op_s + (uint32_t)ostage * (UM_KT * 128) + dst0;
+                const bool count = t < my_tiles;                     // the extra tile belongs to the next group's sums
+                float4 va[2], vb[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    va[u] = lds_v4f(rawst + src_a + (uint32_t)u * (16 * 128));
+                    vb[u] = lds_v4f(rawst + src_b + (uint32_t)u * (16 * 128));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const bool live = row_lo + 16 * u < valid;        // rows behind the sequence: zeros
+                    uint64_t as2[4];
+                    as2[0] = f2_fma(f2_pack(va[u].x, va[u].y), sc2[0], nsh2[0]);
+                    as2[1] = f2_fma(f2_pack(va[u].z, va[u].w), sc2[1], nsh2[1]);
+                    as2[2] = f2_fma(f2_pack(vb[u].x, vb[u].y), sc2[2], nsh2[2]);
+                    as2[3] = f2_fma(f2_pack(vb[u].z, vb[u].w), sc2[3], nsh2[3]);
+                    uint32_t hw[4], lw[4], qw[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!live) as2[i] = f2_pack(0.f, 0.f);
+                        float a0, a1;
+                        f2_unpack(as2[i], a0, a1);
+                        hw[i] = pack_f16(a0, a1);
+                        float l0, l1;
+                        asm("{\n\t.reg .f16 lo, hi, m1;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+                            "fma.rn.f32.f16 %0, lo, m1, %3;\n\tfma.rn.f32.f16 %1, hi, m1, %4;\n\t}"
+                            : "=f"(l0), "=f"(l1) : "r"(hw[i]), "f"(a0), "f"(a1));
+                        lw[i] = pack_f16(l0, l1);
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(qw[i]) : "r"(hw[i]), "r"(0x38003800u));
+                        if (count) ps[i] = f2_add(ps[i], as2[i]);
+                    }
+                    {
+                        uint32_t m01, m23;
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(hw[0] & 0x7FFF7FFFu), "r"(hw[1] & 0x7FFF7FFFu));
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(m23) : "r"(hw[2] & 0x7FFF7FFFu), "r"(hw[3] & 0x7FFF7FFFu));
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(m01) : "r"(m01), "r"(m23));
+                        asm("max.u16x2 %0, %1, %2;" : "=r"(hmax) : "r"(hmax), "r"(m01));
+                    }
+                    const uint32_t d = st + (uint32_t)u * (16 * 128);
+                    sts_v4r(d, hw[0], hw[1], hw[2], hw[3]);
+                    sts_v4r(d + V3_WIN_BYTES, lw[0], lw[1], lw[2], lw[3]);
+                    sts_v4r(d + 2 * V3_WIN_BYTES, qw[0], qw[1], qw[2], qw[3]);
+                    if (ostage == 0) {                               // ring tile 0 again behind tile 3
+                        sts_v4r(d + V3_MIRROR, hw[0], hw[1], hw[2], hw[3]);
+                        sts_v4r(d + V3_MIRROR + V3_WIN_BYTES, lw[0], lw[1], lw[2], lw[3]);
+                        sts_v4r(d + V3_MIRROR + 2 * V3_WIN_BYTES, qw[0], qw[1], qw[2], qw[3]);
+                    }
+                }
+                if ((t & 3) == 3) fold_sums();
+                long long q3 = dbg_on ? clock64() : 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
+                if (tid == V2_CONV_TID0) {
+                    mbar_arrive_local(&ctl->raw_empty[stage]);
+                    if constexpr (CG == 2) mbar_arrive_cluster(&ctl->conv[ostage], 0);
+                    else mbar_arrive_local(&ctl->conv[ostage]);
+                }
+                if (dbg_on) { long long q4 = clock64(); d_raw += q1 - q0; d_empty += q2 - q1; d_comp += q3 - q2; d_sync += q4 - q3; }
+                if (++stage == n_raw) { stage = 0; phase ^= 1; }
+                if (++ostage == S) { ostage = 0; ophase ^= 1; }
+            }
+            fold_sums();
+        } else
         for (int t = 0; t < my_tiles; ++t) {
             long long q0 = dbg_on ? clock64() : 0;
             mbar_wait(&ctl->raw_full[stage], phase);
@@ -665,7 +864,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         // column sums: the 4 threads (one per K chunk) that share a feature combine through shared
         // memory in a fixed order (the raw ring is idle: every TMA load has landed and been
         // converted); the doubles appear only here, after this CTA's last tile
-        {
+        if (mn) {
+            // 16 threads (swp, rp) share a feature: fixed order through shared memory
+            double *s_sum = reinterpret_cast<double *>(raw_ring);        // [16][UM_F]
+            const int contrib = m_swp + 2 * m_rp;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                s_sum[contrib * UM_F + m_f0 + i] = ((double)mn_sh[i] + (double)mn_sl[i]) / (double)mn_sc[i];
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * V2_CONV_WARPS) : "memory");
+            const int f = tid - V2_CONV_TID0;
+            if (f < UM_F) {
+                double tot = 0.0;
+                for (int c = 0; c < 16; ++c) tot += s_sum[c * UM_F + f];
+                P.sums[(size_t)group * UM_D + UM_F * cta_rank + f] = tot;
+            }
+        } else {
             double *s_sum = reinterpret_cast<double *>(raw_ring);        // [4][UM_F]
 #pragma unroll
             for (int k = 0; k < U; ++k)
@@ -831,7 +1044,7 @@ tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restr
                              int n_groups, const double *__restrict__ E, const double *__restrict__ es,
                              const float *__restrict__ shift, const float *__restrict__ scale,
                              const int *__restrict__ rescued, double n_pairs_total, double n_obs,
-                             double n_seq, int Dr, double *__restrict__ acc)
+                             double n_seq, int Dr, int all_rows, double *__restrict__ acc)
 {
     constexpr int D = UM_D;
     constexpr int RW = 128 * CG;
@@ -851,7 +1064,7 @@ tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restr
     double c00 = (at(1, i, j) + at(1, j, i)) * inv;        // C_00 = G + G^T
     const size_t pidx = (size_t)i * D + j;
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-    double esi[2] = {0.0, 0.0}, esj[3] = {0.0, 0.0, 0.0};
+    double esi[3] = {0.0, 0.0, 0.0}, esj[3] = {0.0, 0.0, 0.0};
     for (int c = 0; c < UM_EDGE_SLOTS; ++c) {
         const double *Ec = E + (size_t)c * 4 * DD;
         const double *ec = es + (size_t)c * 3 * D;
@@ -861,6 +1074,7 @@ tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restr
         e3 += Ec[3 * DD + pidx];
         esi[0] += ec[i];
         esi[1] += ec[D + i];
+        esi[2] += ec[2 * D + i];
         esj[0] += ec[j];
         esj[1] += ec[D + j];
         esj[2] += ec[2 * D + j];
@@ -871,18 +1085,34 @@ tica_umma_v2_finalize_kernel(const double *__restrict__ R, const double *__restr
         sum_j += sums[(size_t)p * D + j];
     }
     ctau += e0;
-    c00 += e1;
-    const double ctt = c00 - e2 + e3;
+    double ctt, S0i, S0j, Sti, Stj, tail_j;
+    if (all_rows) {
+        // MN-major mode: G and the column sums run over EVERY row of a sequence; the tail rows (E[3],
+        // es[2]) leave C_00 / S_0, the head rows (E[2], es[2] - es[1]) leave C_tautau / S_tau
+        ctt = c00 - e2;
+        c00 -= e3;
+        S0i = sum_i - esi[2];
+        S0j = sum_j - esj[2];
+        Sti = sum_i - (esi[2] - esi[1]);
+        Stj = sum_j - (esj[2] - esj[1]);
+        tail_j = esj[2];
+    } else {
+        c00 += e1;
+        ctt = c00 - e2 + e3;
+        S0i = sum_i + esi[0];
+        S0j = sum_j + esj[0];
+        Sti = sum_i + esi[1];
+        Stj = sum_j + esj[1];
+        tail_j = esj[2];
+    }
     const double si = (double)shift[i], sj = (double)shift[j];
-    const double S0i = sum_i + esi[0], S0j = sum_j + esj[0];
-    const double Sti = sum_i + esi[1], Stj = sum_j + esj[1];
     const double Np = n_pairs_total;
     acc[idx] += ctau + S0i * sj + si * Stj + Np * si * sj;
     acc[RR + idx] += c00 + S0i * sj + si * S0j + Np * si * sj;
     acc[2 * RR + idx] += ctt + Sti * sj + si * Stj + Np * si * sj;
     if (i == 0) {
         const double S0 = S0j, St = Stj;
-        const double Sall = S0 + esj[2];
+        const double Sall = S0 + tail_j;
         acc[3 * RR + j] += S0 + Np * sj;
         acc[3 * RR + Dr + j] += St + Np * sj;
         acc[3 * RR + 2 * Dr + j] += Sall + n_obs * sj;

@@ -27,7 +27,10 @@ def _round_to_bits(a, bits=11):
     return ((u + add) & mask).view(F32)
 
 
-def device_algebra(seqs, lag, split=True):
+def device_algebra(seqs, lag, split=True, all_rows=False):
+    """all_rows: the MN-major mode of tica_umma_v2.cuh -- G = sum over EVERY row of h (h/2)^T + h l^T (C_00 = G + G^T)
+    and the column sums over every row; the finalize kernel takes the tail rows out of C_00 / S_0 and the head
+    rows out of C_tautau / S_tau."""
     D = seqs[0].shape[1]
     usable = [np.ascontiguousarray(s, dtype=F32) for s in seqs if len(s) > lag]
     allrows = np.concatenate(usable)                                             # tica_shift_kernel: 1024 rows
@@ -50,12 +53,16 @@ def device_algebra(seqs, lag, split=True):
             h = h.astype(np.float16).astype(np.float64)
             A, B = (h[:n - lag], l[:n - lag]), (h[lag:], l[lag:])
             Ctau += A[0].T @ B[0] + A[0].T @ B[1] + A[1].T @ B[0]
-            C00 += A[0].T @ A[0] + A[0].T @ A[1] + A[1].T @ A[0]
+            if all_rows:
+                G = h.T @ (h / 2) + h.T @ l
+                C00 += G + G.T
+            else:
+                C00 += A[0].T @ A[0] + A[0].T @ A[1] + A[1].T @ A[0]
         else:
             ad = a.astype(np.float64)
             Ctau += ad[:n - lag].T @ ad[lag:]
-            C00 += ad[:n - lag].T @ ad[:n - lag]
-        S0 += a[:n - lag].astype(np.float64).sum(0)                              # column sums, scaled units
+            C00 += ad.T @ ad if all_rows else ad[:n - lag].T @ ad[:n - lag]
+        S0 += (a if all_rows else a[:n - lag]).astype(np.float64).sum(0)         # column sums, scaled units
         xd = xp.astype(np.float64)                                               # edge kernel: float64, unscaled
         E2 += xd[:lag].T @ xd[:lag]
         E3 += xd[n - lag:].T @ xd[n - lag:]
@@ -67,8 +74,14 @@ def device_algebra(seqs, lag, split=True):
     Ctau *= np.outer(inv, inv)
     C00 *= np.outer(inv, inv)
     S0 = S0 * inv
-    Ctt = C00 - E2 + E3
-    St = S0 - head + tail
+    if all_rows:
+        Ctt = C00 - E2
+        C00 = C00 - E3
+        St = S0 - head
+        S0 = S0 - tail
+    else:
+        Ctt = C00 - E2 + E3
+        St = S0 - head + tail
     sh = shift.astype(np.float64)
     Np = float(n_pairs)
     raw_tau = Ctau + np.outer(S0, sh) + np.outer(sh, St) + Np * np.outer(sh, sh)
@@ -80,7 +93,8 @@ def device_algebra(seqs, lag, split=True):
 
 @pytest.mark.parametrize("lag", [1, 7, 10])
 @pytest.mark.parametrize("split", [False, True])
-def test_device_algebra_reproduces_the_reference_moments(lag, split):
+@pytest.mark.parametrize("all_rows", [False, True])
+def test_device_algebra_reproduces_the_reference_moments(lag, split, all_rows):
     lens = [1500, 700, 64, lag + 1, lag, 3, 900]                 # the last three: barely usable / skipped
     seqs = [s[:n] for s, n in zip(ar1_numpy(len(lens), 1500, 32, seed=5), lens)]
     rs = np.random.RandomState(1)
@@ -88,7 +102,7 @@ def test_device_algebra_reproduces_the_reference_moments(lag, split):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         ref = TicaOracle(n_components=3, lag_time=lag).fit(seqs).packed_moments()
-    got = device_algebra(seqs, lag, split=split)
+    got = device_algebra(seqs, lag, split=split, all_rows=all_rows)
     D = 32
     assert got[-2] == ref[-2] and got[-1] == ref[-1]             # n_observations_, n_sequences_
     sd = np.sqrt(np.abs(np.diag(ref[D * D:2 * D * D].reshape(D, D))))
