@@ -334,6 +334,13 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()             # before the warm-up: nvidia-smi takes a while to produce samples
+    # like timeit: no cyclic garbage collection inside the timed region (a generation-2 sweep of this
+    # process -- torch, sklearn and 500 tensor views per step -- takes 50-100 ms; single tICA phases of
+    # 80-118 ms showed up between steps of 30 ms, profiles/r2w_bench_gc_outliers.json).  Collected
+    # BEFORE the warm-up so that the GPU does not sit idle between the warm-up and the timed steps.
+    import gc
+    gc.collect()
+    gc.disable()
     for _ in range(args.warmup):
         step(False)
     barrier()
@@ -343,12 +350,6 @@ def run_ours(args):
     profiling = os.environ.get("MSMB_PROFILE") == "1"     # ncu --profile-from-start off
     if profiling:
         torch.cuda.profiler.start()
-    # like timeit: no cyclic garbage collection inside the timed region (a generation-2 sweep of this
-    # process -- torch, sklearn and 500 tensor views per step -- takes 50-100 ms and showed up as single
-    # tICA phases of 80-118 ms between steps of 30 ms, profiles/r2w_bench_gc_outliers.json)
-    import gc
-    gc.collect()
-    gc.disable()
     sampler.mark_begin()
     t_start.record()
     state["time_passes"] = True          # CUDA events around every fused K2 launch (look-ahead path)
@@ -543,7 +544,7 @@ def run_ours(args):
     issued = {"auto": 2.5, "umma_3xf16": 2.5, "umma_6xbf16": 6, "umma_3xbf16": 3, "umma_3xtf32": 3,
               "umma_tf32": 1}.get(args.engine, 1)
     tica_ach = flops_tica / tica_s / 1e12
-    roof_k2 = {"kernel": "kcenters_multi_pass_kernel" if pass_ms else "kcenters_pass_fast_kernel",
+    roof_k2 = {"kernel": "kcenters_first_pass_kernel + kcenters_fused_pass_kernel" if pass_ms else "kcenters_pass_fast_kernel",
                "bound": "hbm", "achieved": hbm_ach,
                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                "traffic": None, "peak_source": peaks["source"],
@@ -558,10 +559,11 @@ def run_ours(args):
                "algorithmic_flops_per_launch": flops_tica, "ms_per_launch": tica_s * 1e3,
                "issued_mma_products": issued, "issued_frac": issued * tica_ach / tf32_peak,
                "note": "a kind::f16 UMMA M256 x N256 x K16 from shared-memory operands takes 167.6 cycles on "
-                       "this part, not the 128 of the nominal rate (profiles/r2e_probe5_mma_shapes.log): "
-                       "issued_frac tops out at ~0.76 of a peak derived from the nominal rate; the kernel "
-                       "itself is bound by shared-memory bandwidth (operand reads of the UMMAs + conversion "
-                       "traffic, DESIGN.md section 4)",
+                       "this part, not the 128 of the nominal rate (profiles/r2d_probe5_mma_shapes.log): "
+                       "issued_frac tops out at ~0.76 of a peak derived from the nominal rate.  With the MN-major "
+                       "rolling-window operands (one conversion per frame) the kernel runs within ~10 % of ten such "
+                       "UMMAs per 32-frame tile: tensor-pipe bound (DESIGN.md section 4); ms_per_launch is the whole "
+                       "tICA phase (K1 + edge / reduce / finalize kernels + host enqueue)",
                "share_of_step": tica_s / (ms_per_step / 1e3)}
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/ncu_traffic.json),
     # only when this run has the captured shape; otherwise null
@@ -570,7 +572,7 @@ def run_ours(args):
             tr = json.load(fh)
         if tr["frames_per_gpu"] == n_total // ws and tr["features"] == D:
             if pass_ms and not args.no_lookahead:
-                per = [tr["kcenters_multi_pass_kernel"]["first" if c == 1 and i == 0 else "fused"]
+                per = [tr["kcenters_lookahead_passes"]["first" if c == 1 and i == 0 else "fused"]
                        for i, c in enumerate(pass_centres[-n_passes:])]
                 roof_k2["traffic"] = float(np.mean(per))
             elif args.no_lookahead:

@@ -1249,7 +1249,10 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     const int v2_cg = D <= UM_F ? 1 : 2;
     // MN-major rolling-window operands (tica_umma_v2.cuh, "MN-major mode"): every CTA has its four feature
     // blocks and the lag fits the mirror tile
-    const bool v3 = v2 && (D == UM_D || D == UM_F) && lag <= UM_KT && env_int("MSMB200_UMMA_MN", 0) != 0;
+    // (MSMB200_UMMA_MN=0 keeps the K-major mode; MSMB200_UMMA_MN_STAGES = ring tiles, 4 or 5)
+    const bool v3 = v2 && (D == UM_D || D == UM_F) && lag <= UM_KT && env_int("MSMB200_UMMA_MN", 1) != 0;
+    int v3_stages = env_int("MSMB200_UMMA_MN_STAGES", 5);
+    v3_stages = v3_stages < 4 ? 4 : (v3_stages > 5 ? 5 : v3_stages);
     const size_t n_items = v2 ? tica_simt_items(seq_ptrs, seq_rows, n_seq_in, lag, nullptr, nullptr, nullptr) : 0;
     const size_t o_items = off; off = align_up(off + tica_simt_item_bytes() * n_items, 128);
     int dev = 0;
@@ -1457,7 +1460,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     V.D = D;
     V.box_blocks = box_blocks;
     V.dbg_mode = P.dbg_mode;
-    V.mn = v3 ? 1 : 0;
+    V.mn = v3 ? v3_stages : 0;
     V.lag = lag;
     V.shift = d_shift;
     V.scale = d_scale;

@@ -39,11 +39,11 @@
 // (features contiguous, one frame = one 128-byte row of 64 features, SWIZZLE_128B, LBO = distance of the
 // next 64 features, SBO = 8 rows), and the swizzle is a function of the absolute shared-memory address,
 // so a descriptor may start at ANY row: the lagged operand is the same converted buffer, `lag` rows on.
-// Per CTA three windows H (h), L (l), Q (h / 2) of [2 blocks of 64 features][4 ring tiles + 1 mirror tile
-// of 32 rows][128 B] (120 KB, inside the operand ring of the K-major mode); a frame is loaded once and
+// Per CTA three windows H (h), L (l), Q (h / 2) of [2 blocks of 64 features][S ring tiles + 1 mirror tile
+// of 32 rows][128 B] (S = 5: 144 KB, inside the operand ring of the K-major mode); a frame is loaded once and
 // converted once: two 16-byte loads of the raw row, three 16-byte stores.  Tile t's UMMAs read rows
 // [32 t, 32 t + 32 + lag): they wait for ring tiles t and t + 1, a group converts one tile more than it
-// multiplies, ring tile 0 is mirrored behind tile 3.  Tiles cover ALL rows of a sequence plus `lag` rows
+// multiplies, ring tile 0 is mirrored behind the last one.  Tiles cover ALL rows of a sequence plus `lag` rows
 // of zeros (TMA fills them), so G sums x x^T over every row and the finalize kernel takes the tail rows
 // out of C_00 and the head rows out of C_tautau (the float64 edge terms it already has).
 #pragma once
@@ -56,6 +56,7 @@ constexpr int V2_STAGE_BYTES = V2_NTILES * V2_TILE; // 40 KB
 constexpr int V2_RAW_STAGES = 2;                    // raw ring depth with full 4-block boxes (64 KB in all)
 constexpr int V2_RAW_MAX = 8;                       // ... 4 / 8 stages when a box only brings 2 / 1 feature blocks
 constexpr int V2_OP_STAGES = 4;
+constexpr int V2_MAX_STAGES = 6;                    // barrier slots (the MN-major mode runs 4 or 5 ring tiles)
 constexpr int V2_CONV_WARPS = 8;
 constexpr int V2_DRAIN_WARPS = 8;
 constexpr int V2_UNITS_PER_WARP = 4;                // 8 * 4 feature blocks = 32 units per tile at most
@@ -82,7 +83,7 @@ struct V2Params {
     int D;                        // real feature count (32k)
     int box_blocks;               // 32-feature blocks one TMA box brings (4; D / 32 for the single-CTA kernel)
     int dbg_mode;                 // 1: converters skip their work, 2: no drain (timing experiments)
-    int mn;                       // 1: MN-major rolling-window operands (see "MN-major mode" below)
+    int mn;                       // 0, or the number of ring tiles (4 / 5) of the MN-major rolling-window mode
     int lag;                      // (MN-major mode) rows between the two operands
     const float *shift;           // [UM_D]
     const float *scale;           // [UM_D]
@@ -96,8 +97,8 @@ struct V2Params {
 struct V2Smem {
     uint64_t raw_full[V2_RAW_MAX];
     uint64_t raw_empty[V2_RAW_MAX];
-    uint64_t conv[V2_OP_STAGES];       // leader's copy is used; CG arrivals
-    uint64_t empty[V2_OP_STAGES];      // local; one commit arrival
+    uint64_t conv[V2_MAX_STAGES];      // leader's copy is used; CG arrivals
+    uint64_t empty[V2_MAX_STAGES];     // local; one commit arrival
     uint64_t acc_full[V2_REGIONS];     // local; one commit arrival
     uint64_t acc_empty[V2_REGIONS];    // leader's copy is used; 8 * CG arrivals
     uint32_t tmem_base;
@@ -251,12 +252,12 @@ __device__ __forceinline__ void sts_v4r(uint32_t addr, uint32_t a, uint32_t b, u
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// MN-major windows: rows of 128 bytes (64 features), 4 ring tiles + the mirror of tile 0
-constexpr int V3_WIN_ROWS = 32 * V2_OP_STAGES + 32;               // 160
-constexpr int V3_BLOCK_BYTES = V3_WIN_ROWS * 128;                 // 20480: LBO (next 64 features)
-constexpr int V3_WIN_BYTES = 2 * V3_BLOCK_BYTES;                  // 40960: H, L, Q follow each other
-constexpr int V3_MIRROR = 32 * V2_OP_STAGES * 128;                // 16384: ring tile 0 again, behind tile 3
-static_assert(3 * V3_WIN_BYTES <= V2_OP_STAGES * V2_STAGE_BYTES, "the windows live in the operand ring");
+// MN-major windows: rows of 128 bytes (64 features); S ring tiles of 32 rows + the mirror of tile 0 behind them.
+// S = 4 or 5 (5 fits the operand ring of the K-major mode: 3 windows x 2 blocks x 192 rows x 128 B = 144 KB)
+__host__ __device__ constexpr int v3_block_bytes(int S) { return (32 * S + 32) * 128; }   // LBO: next 64 features
+__host__ __device__ constexpr int v3_win_bytes(int S) { return 2 * v3_block_bytes(S); }   // H, L, Q follow each other
+__host__ __device__ constexpr int v3_mirror(int S) { return 32 * S * 128; }               // ring tile 0 again
+static_assert(3 * v3_win_bytes(5) <= V2_OP_STAGES * V2_STAGE_BYTES, "the windows live in the operand ring");
 
 template <int IMM>
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
 {
     constexpr int RW = 128 * CG;                     // columns reserved per region (N <= RW)
     constexpr int TMEM_COLS = V2_REGIONS * RW;       // 512 (CG = 2) or 256 (CG = 1)
-    constexpr int S = V2_OP_STAGES;
+    const int S = P.mn ? P.mn : V2_OP_STAGES;        // operand stages / ring tiles
     constexpr int CW = RW / 2;                       // columns of a region one drain warp owns
     constexpr int NG = CW / 16;                      // its 16-column fold groups
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *raw_ring = ring;                                        // [2][A raw | B raw]
     unsigned char *op_ring = ring + V2_RAW_STAGES * UM_RAW_BYTES;          // [4][a|al|ah|b|bl]
-    V2Smem *ctl = reinterpret_cast<V2Smem *>(op_ring + S * V2_STAGE_BYTES);
+    V2Smem *ctl = reinterpret_cast<V2Smem *>(op_ring + V2_OP_STAGES * V2_STAGE_BYTES);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             mbar_init(&ctl->raw_full[s], 1);
             mbar_init(&ctl->raw_empty[s], 1);
         }
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < V2_MAX_STAGES; ++s) {
             mbar_init(&ctl->conv[s], CG);
             mbar_init(&ctl->empty[s], 1);
         }
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         // NaN pattern and trip the range check through its accumulators)
         uint4 *p = reinterpret_cast<uint4 *>(op_ring);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < S * V2_STAGE_BYTES / 16; i += V2_THREADS) p[i] = z;
+        for (int i = tid; i < V2_OP_STAGES * V2_STAGE_BYTES / 16; i += V2_THREADS) p[i] = z;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 0) {
@@ -441,11 +442,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             };
             // MN-major mode: window `win` (0 H, 1 L, 2 Q), row `row` of the ring: SWIZZLE_128B (layout type 2 in
             // bits 61-63), LBO = next 64 features, SBO = 8 rows; any row may start a descriptor
-            auto desc_mn = [](uint32_t ring, int win, int row) -> uint64_t {
-                const uint32_t a = ring + (uint32_t)win * V3_WIN_BYTES + (uint32_t)row * 128;
+            const uint32_t mn_win = (uint32_t)v3_win_bytes(S), mn_lbo = (uint32_t)(v3_block_bytes(S) >> 4) << 16;
+            auto desc_mn = [&](uint32_t ring, int win, int row) -> uint64_t {
+                const uint32_t a = ring + (uint32_t)win * mn_win + (uint32_t)row * 128;
                 uint64_t d;
                 asm("mov.b64 %0, {%1, %2};" : "=l"(d)
-                    : "r"(((a >> 4) & 0x3FFFu) | ((uint32_t)(V3_BLOCK_BYTES >> 4) << 16)),
+                    : "r"(((a >> 4) & 0x3FFFu) | mn_lbo),
                       "r"((uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29))));
                 return d;
             };
@@ -632,7 +634,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const uint32_t swz = (uint32_t)(row_lo & 7);           // (row_lo + 16) & 7 is the same
             const uint32_t src_a = (uint32_t)((2 * m_fbh + m_fbl) * (UM_KT * 128) + row_lo * 128) + (((2u * m_cq) ^ swz) << 4);
             const uint32_t src_b = (uint32_t)((2 * m_fbh + m_fbl) * (UM_KT * 128) + row_lo * 128) + (((2u * m_cq + 1u) ^ swz) << 4);
-            const uint32_t dst0 = (uint32_t)(m_fbh * V3_BLOCK_BYTES + row_lo * 128) + ((((uint32_t)(4 * m_fbl + m_cq)) ^ swz) << 4);
+            const uint32_t win_bytes = (uint32_t)v3_win_bytes(S), mirror = (uint32_t)v3_mirror(S);
+            const uint32_t dst0 = (uint32_t)(m_fbh * v3_block_bytes(S) + row_lo * 128) + ((((uint32_t)(4 * m_fbl + m_cq)) ^ swz) << 4);
             uint64_t sc2[4], nsh2[4], ps[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -706,12 +709,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                     }
                     const uint32_t d = st + (uint32_t)u * (16 * 128);
                     sts_v4r(d, hw[0], hw[1], hw[2], hw[3]);
-                    sts_v4r(d + V3_WIN_BYTES, lw[0], lw[1], lw[2], lw[3]);
-                    sts_v4r(d + 2 * V3_WIN_BYTES, qw[0], qw[1], qw[2], qw[3]);
-                    if (ostage == 0) {                               // ring tile 0 again behind tile 3
-                        sts_v4r(d + V3_MIRROR, hw[0], hw[1], hw[2], hw[3]);
-                        sts_v4r(d + V3_MIRROR + V3_WIN_BYTES, lw[0], lw[1], lw[2], lw[3]);
-                        sts_v4r(d + V3_MIRROR + 2 * V3_WIN_BYTES, qw[0], qw[1], qw[2], qw[3]);
+                    sts_v4r(d + win_bytes, lw[0], lw[1], lw[2], lw[3]);
+                    sts_v4r(d + 2 * win_bytes, qw[0], qw[1], qw[2], qw[3]);
+                    if (ostage == 0) {                               // ring tile 0 again behind the last tile
+                        sts_v4r(d + mirror, hw[0], hw[1], hw[2], hw[3]);
+                        sts_v4r(d + mirror + win_bytes, lw[0], lw[1], lw[2], lw[3]);
+                        sts_v4r(d + mirror + 2 * win_bytes, qw[0], qw[1], qw[2], qw[3]);
                     }
                 }
                 if ((t & 3) == 3) fold_sums();

@@ -1,4 +1,6 @@
-"""One assign_nearest call at BASELINE.json config 3 (10M x 16, k = 500) for ncu / timing."""
+"""One assign_nearest call at BASELINE.json config 3 (10M x 16, k = 500) for ncu / timing.
+
+    python tools/profile_assign.py [n d k]      e.g. 10000000 128 2000 (the streamed-centres kernel)"""
 import os
 import sys
 
@@ -7,7 +9,7 @@ sys.path.insert(0, ROOT)
 import torch
 from msmbuilder_b200 import _kernels as K
 
-n, D, k = 10_000_000, 16, 500
+n, D, k = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (10_000_000, 16, 500)
 g = torch.Generator(device="cuda")
 g.manual_seed(3)
 X = torch.randn((n, D), generator=g, device="cuda") * torch.linspace(3, 0.3, D, device="cuda")
@@ -18,4 +20,4 @@ for _ in range(3):
     labels, _, inertia = K.assign_nearest(X, C, "euclidean")
     e1.record()
     e1.synchronize()
-    print("assign 10M x 16 -> k=500: %.3f ms" % e0.elapsed_time(e1), flush=True)
+    print("assign %d x %d -> k=%d: %.3f ms" % (n, D, k, e0.elapsed_time(e1)), flush=True)
