@@ -494,6 +494,85 @@ assign_refine_kernel(const float *__restrict__ X, int d, long long ld, const flo
     }
 }
 
+// The same re-scan for many centres (k >= 64): one WARP per listed frame.  A float32 scan first (lane =
+// centre, no reductions: 8 instead of 40 warp instructions per (frame, centre)), its values kept in
+// shared memory; only the centres within the float32 error bound of the smallest value are then
+// recomputed in float64 -- by the same group_distance call as above, in ascending centre order with
+// strict '<' -- so the label is the one assign_refine_kernel finds.  With k = 2000 centres and ~1 % of
+// ambiguous frames the full float64 re-scan took 8.4 of the 26 ms of assign_nearest
+// (profiles/r2f_launches_assign_stream.csv).
+__global__ void __launch_bounds__(kThreads)
+assign_refine_wide_kernel(const float *__restrict__ X, int d, long long ld, const float *__restrict__ Y,
+                          int k, const long long *__restrict__ rows, const int *__restrict__ amb_list,
+                          const int *__restrict__ amb_count, int *__restrict__ labels, int G, int sq,
+                          float rel_margin)
+{
+    extern __shared__ float s_ref[];                    // per warp: x[d] | s[k]
+    const int n_amb = *amb_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    float *sx = s_ref + (size_t)warp * (d + k);
+    float *sv = sx + d;
+    const int lig = lane & (G - 1);
+    // 16-byte loads when every centre row and every warp's staging row is 16-byte aligned
+    const bool vec4 = (d & 3) == 0 && (k & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15u) == 0;
+    for (long long a = (long long)blockIdx.x * warps_per_block + warp; a < n_amb;
+         a += (long long)gridDim.x * warps_per_block) {
+        const long long i = amb_list[a];
+        const long long r = rows ? rows[i] : i;
+        const float *u = X + r * ld;
+        __syncwarp();
+        for (int e = lane; e < d; e += 32) sx[e] = u[e];
+        __syncwarp();
+        // float32 scan: lane takes centres lane, lane + 32, ...
+        float m = INFINITY;
+        bool odd = false;                               // a NaN somewhere: leave the frame to the full scan
+        for (int j = lane; j < k; j += 32) {
+            const float *c = Y + (long long)j * d;
+            float acc = 0.f;
+            if (vec4) {
+                const float4 *c4 = reinterpret_cast<const float4 *>(c);
+                const float4 *x4 = reinterpret_cast<const float4 *>(sx);
+                for (int e = 0; e < (d >> 2); ++e) {
+                    const float4 cv = __ldg(c4 + e), xv = x4[e];
+                    float t = xv.x - cv.x; acc = fmaf(t, t, acc);
+                    t = xv.y - cv.y; acc = fmaf(t, t, acc);
+                    t = xv.z - cv.z; acc = fmaf(t, t, acc);
+                    t = xv.w - cv.w; acc = fmaf(t, t, acc);
+                }
+            } else {
+                for (int e = 0; e < d; ++e) {
+                    const float t = sx[e] - __ldg(c + e);
+                    acc = fmaf(t, t, acc);
+                }
+            }
+            sv[j] = acc;
+            if (acc != acc) odd = true;
+            m = fminf(m, acc);
+        }
+        for (int off = 16; off > 0; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        odd = __any_sync(0xffffffffu, odd) || !(m < INFINITY);
+        __syncwarp();
+        const float thr = fmaxf(m * (1.f + rel_margin), 1e-30f);
+        double bestd = 1.7976931348623157e308;
+        int arg = 0;
+        for (int j0 = 0; j0 < k; j0 += 32) {
+            const int j = j0 + lane;
+            const bool cand = j < k && (odd || sv[j] <= thr);
+            unsigned mask = __ballot_sync(0xffffffffu, cand);
+            while (mask) {
+                const int jj = j0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double dv = sq
+                    ? group_distance<MSMB200_SQEUCLIDEAN, float, false, false>(u, Y + (long long)jj * d, d, lig, G)
+                    : group_distance<MSMB200_EUCLIDEAN, float, false, false>(u, Y + (long long)jj * d, d, lig, G);
+                if (dv < bestd) { bestd = dv; arg = jj; }
+            }
+        }
+        if (lane == 0) labels[i] = arg;
+    }
+}
+
 // exact float64 distance of every frame to its assigned centre (+ block partial sums)
 __global__ void __launch_bounds__(kThreads)
 assign_mindist_kernel(const float *__restrict__ X, long long n_out, int d, long long ld,
@@ -802,9 +881,21 @@ extern "C" int msmb200_assign_nearest(const void *X, int64_t n, int d, int64_t l
             MSMB_LAUNCH_CHECK();
         }
         const int G = lanes_per_row(d, 1, false);
-        assign_refine_kernel<<<sm_count() * 4, kThreads, 0, st>>>(
-            (const float *)X, d, ld, (const float *)Y, k, (const long long *)rows, amb_list,
-            amb_count, labels, G, sq);
+        const size_t wide_smem = sizeof(float) * (size_t)(d + k) * (kThreads / 32);
+        if (k >= 64 && wide_smem <= 200 * 1024 && !getenv("MSMB200_ASSIGN_REFINE_FULL")) {
+            // float32 pre-scan, float64 only for the centres within its error bound (relative margin of the
+            // squared distance: twice the 4 (d + 4) 2^-24 of the SIMT filter, both values carry the error)
+            if (wide_smem > 48 * 1024)
+                MSMB_CUDA(cudaFuncSetAttribute(assign_refine_wide_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
+            assign_refine_wide_kernel<<<sm_count() * 2, kThreads, wide_smem, st>>>(
+                (const float *)X, d, ld, (const float *)Y, k, (const long long *)rows, amb_list,
+                amb_count, labels, G, sq, 4.0f * margin);
+        } else {
+            assign_refine_kernel<<<sm_count() * 4, kThreads, 0, st>>>(
+                (const float *)X, d, ld, (const float *)Y, k, (const long long *)rows, amb_list,
+                amb_count, labels, G, sq);
+        }
         MSMB_LAUNCH_CHECK();
         if (min_dist || inertia) {
             const int grid = grid_for(n_out, G);

@@ -1484,10 +1484,12 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MSMB_CUDA(cudaFuncSetAttribute(tica_umma_kernel<UM_KIND_F16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_v2_kernel<1>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
-        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_v2_kernel<2>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
+#define MSMB_V2_ATTR(CGV, MNV)                                                                      \
+        MSMB_CUDA(cudaFuncSetAttribute(tica_umma_v2_kernel<CGV, MNV>,                               \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2))
+        MSMB_V2_ATTR(1, 0); MSMB_V2_ATTR(2, 0); MSMB_V2_ATTR(1, 4); MSMB_V2_ATTR(2, 4);
+        MSMB_V2_ATTR(1, 5); MSMB_V2_ATTR(2, 5);
+#undef MSMB_V2_ATTR
         g_attr_set[dev] = true;
     }
     if (tiles > 0) {
@@ -1505,8 +1507,15 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
                 attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
-                if (v2_cg == 2) MSMB_CUDA(cudaLaunchKernelEx(&cfg, tica_umma_v2_kernel<2>, V));
-                else MSMB_CUDA(cudaLaunchKernelEx(&cfg, tica_umma_v2_kernel<1>, V));
+#define MSMB_V2_LAUNCH(MNV)                                                                         \
+                do {                                                                                \
+                    if (v2_cg == 2) MSMB_CUDA(cudaLaunchKernelEx(&cfg, tica_umma_v2_kernel<2, MNV>, V)); \
+                    else MSMB_CUDA(cudaLaunchKernelEx(&cfg, tica_umma_v2_kernel<1, MNV>, V));       \
+                } while (0)
+                if (V.mn == 5) MSMB_V2_LAUNCH(5);
+                else if (V.mn == 4) MSMB_V2_LAUNCH(4);
+                else MSMB_V2_LAUNCH(0);
+#undef MSMB_V2_LAUNCH
             } else {
                 tica_umma_kernel<UM_KIND_F16><<<2 * n_pairs, UM_THREADS, smem, st>>>(P);
             }

@@ -275,12 +275,16 @@ __device__ __forceinline__ uint64_t h2_to_f2(uint32_t h)
 }
 
 // ---------------------------------------------------------------------------------------
-template <int CG>
+// MN: 0 = K-major operand ring (4 stages), 4 / 5 = MN-major rolling window with that many ring tiles.
+// (A template parameter: with the stage count a run-time value the issuer of the narrow kernel -- which is
+// issue bound -- lost 35 %: config 2 went from 1.90 to 2.56 ms, profiles/r2f_bench_1gpu_runtime_stages.json.)
+template <int CG, int MN>
 __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Params P)
 {
     constexpr int RW = 128 * CG;                     // columns reserved per region (N <= RW)
     constexpr int TMEM_COLS = V2_REGIONS * RW;       // 512 (CG = 2) or 256 (CG = 1)
-    const int S = P.mn ? P.mn : V2_OP_STAGES;        // operand stages / ring tiles
+    constexpr bool mn = MN != 0;
+    constexpr int S = mn ? MN : V2_OP_STAGES;        // operand stages / ring tiles
     constexpr int CW = RW / 2;                       // columns of a region one drain warp owns
     constexpr int NG = CW / 16;                      // its 16-column fold groups
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -309,7 +313,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
     // raw ring: a stage holds the two boxes of a tile (unlagged, lagged), box_blocks * 4 KB each; the
     // ring always spans 64 KB, so narrow inputs get a deeper ring (the TMA latency showed as 240 cycles
     // of wait per tile at D = 64 with two stages)
-    const bool mn = P.mn != 0;
     const uint32_t raw_op_bytes = (uint32_t)P.box_blocks * (UM_KT * 128);
     const uint32_t raw_stage_bytes = mn ? raw_op_bytes : 2 * raw_op_bytes;      // MN-major: one box per tile
     // MN-major: one ring tile more is converted than multiplied (tile t's lagged rows reach into t + 1)
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 mbar_wait_idle<false>(&ctl->raw_empty[stage], phase ^ 1);   // hint only: the TMA issue is latency critical
                 ctl->valid_rows[stage] = valid;
                 unsigned char *st = raw_ring + (size_t)stage * raw_stage_bytes;
-                if (mn) {
+                if constexpr (mn) {
                     mbar_expect_tx(&ctl->raw_full[stage], P.box_blocks * (UM_KT * 128));
                     tma_load_3d(st, &P.mapsA[s], &ctl->raw_full[stage], 0, row0, 4 * (int)cta_rank, policy);
                 } else {
@@ -492,7 +495,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                         // B = h / 2, B = l (both of the unlagged frames)
                         const int ring_row = (tt % S) * UM_KT;
                         auto opd = [&](int which, int ks) -> uint64_t {
-                            if (mn) {
+                            if constexpr (mn) {
                                 const int ra = ring_row + 16 * ks, rb = ra + lag;
                                 switch (which) {
                                 case 0: return desc_mn(ring_addr, 0, ra);
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         const int mct = tid - V2_CONV_TID0;
         const int m_cq = mct & 3, m_fbl = (mct >> 2) & 1, m_swp = (mct >> 3) & 1, m_fbh = (mct >> 4) & 1, m_rp = mct >> 5;
         const int m_f0 = 32 * (2 * m_fbh + m_fbl) + 8 * m_cq;     // first feature (inside the CTA)
-        if (mn) {
+        if constexpr (mn) {
             const int row_lo = 2 * m_rp + (m_fbl ^ m_swp);
             const uint32_t swz = (uint32_t)(row_lo & 7);           // (row_lo + 16) & 7 is the same
             const uint32_t src_a = (uint32_t)((2 * m_fbh + m_fbl) * (UM_KT * 128) + row_lo * 128) + (((2u * m_cq) ^ swz) << 4);
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         // column sums: the 4 threads (one per K chunk) that share a feature combine through shared
         // memory in a fixed order (the raw ring is idle: every TMA load has landed and been
         // converted); the doubles appear only here, after this CTA's last tile
-        if (mn) {
+        if constexpr (mn) {
             // 16 threads (swp, rp) share a feature: fixed order through shared memory
             double *s_sum = reinterpret_cast<double *>(raw_ring);        // [16][UM_F]
             const int contrib = m_swp + 2 * m_rp;
