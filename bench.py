@@ -63,8 +63,6 @@ def parse():
                     help="skip timing KCenters with one pass per centre beside the look-ahead value")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short measurements of BASELINE.json configs 2, 3 and 5 (single GPU only)")
-    ap.add_argument("--no-lead-in", action="store_true",
-                    help="do not enqueue the untimed lead-in step between the barrier and the start event")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="KCenters: one pass per centre (the reference's schedule) instead of look-ahead")
     return ap.parse_args()
@@ -275,10 +273,7 @@ def workload_config(args, ws):
             "frames": args.frames, "features": args.features, "lag_time": args.lag,
             "n_clusters": args.k, "seq_len": args.seq_len, "sharding": "frames/%d" % ws,
             "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2" % (
-                args.frames / ws * args.features * 4 / 1e9),
-            "lead_in": ("none" if getattr(args, "no_lead_in", False) else
-                        "one untimed step enqueued (not waited for) between the barrier and the start event: the "
-                        "timed steps start from the power-capped steady state, not from an idle, boosted GPU")}
+                args.frames / ws * args.features * 4 / 1e9)}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -343,9 +338,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()             # before the warm-up: nvidia-smi takes a while to produce samples
     # like timeit: no cyclic garbage collection inside the timed region (a generation-2 sweep of this
-    # process -- torch, sklearn and 500 tensor views per step -- takes 50-100 ms; single tICA phases of
-    # 80-118 ms showed up between steps of 30 ms, profiles/r2w_bench_gc_outliers.json).  Collected
+    # process -- torch, sklearn and 500 tensor views per step -- takes tens of milliseconds).  Collected
     # BEFORE the warm-up so that the GPU does not sit idle between the warm-up and the timed steps.
+    # (The tICA phases of 45-118 ms that showed up between steps of 27 ms were something else: one
+    # cudaMallocHost per staging slot during the first eight calls of a process, since replaced by one
+    # allocation per device -- profiles/r2w_bench_gc_outliers.json, r2h_bench_pinned_alloc_outliers.json.)
     import gc
     gc.collect()
     gc.disable()
@@ -358,15 +355,6 @@ def run_ours(args):
     profiling = os.environ.get("MSMB_PROFILE") == "1"     # ncu --profile-from-start off
     if profiling:
         torch.cuda.profiler.start()
-    # Lead-in: one more UNTIMED step is enqueued behind the barrier and NOT waited for, the start event goes
-    # into the stream right behind it.  Without it the first timed step starts from an idle GPU (the host
-    # needs ~2 ms to prepare the step's 500 sequences): the clocks boost to 1.97 GHz, the tensor-core kernel
-    # starts far above the board's power cap and the limiter answers with tens of milliseconds of deep
-    # throttling -- tICA phases of 47, 48 and 73 ms in front of four steps of 27 ms
-    # (profiles/r2g_bench_1gpu_first_step_outlier.json).  A stream of frames keeps the GPU in the capped
-    # steady state the other steps are measured in; the events still time exactly `steps` steps.
-    if not args.no_lead_in:
-        step(False)
     sampler.mark_begin()
     t_start.record()
     state["time_passes"] = True          # CUDA events around every fused K2 launch (look-ahead path)

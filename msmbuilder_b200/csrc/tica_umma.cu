@@ -1178,23 +1178,38 @@ static int g_pinned_next[UM_MAX_DEVICES] = {0};
 static bool g_pool_tuned[UM_MAX_DEVICES] = {false};              // one-time set-up, per device
 static bool g_attr_set[UM_MAX_DEVICES] = {false};
 
-// a pinned buffer of >= bytes whose previous copy (if any) has left the host; call with g_host_mu held
+static void *g_pinned_arena[UM_MAX_DEVICES] = {nullptr};         // ONE page-locked allocation per device, cut into slots
+
+// a pinned buffer of >= bytes whose previous copy (if any) has left the host; call with g_host_mu held.
+// All slots of a device are carved out of one allocation made by the first call (and remade only when a call
+// needs more than a slot holds): cudaMallocHost page-locks memory, and with one allocation per slot every
+// fourth of the first eight calls of a process paid 20-70 ms for it (the driver grows its pinned pool in
+// steps) -- inside the timed steps of the bench, profiles/r2h_bench_pinned_alloc_outliers.json.
 static int pinned_acquire(int dev, size_t bytes, PinnedSlot **out)
 {
     PinnedSlot &s = g_pinned[dev][g_pinned_next[dev]];
     g_pinned_next[dev] = (g_pinned_next[dev] + 1) % UM_PINNED_SLOTS;
+    if (s.bytes < bytes) {
+        for (int i = 0; i < UM_PINNED_SLOTS; ++i) {
+            PinnedSlot &o = g_pinned[dev][i];
+            if (o.in_flight) {
+                MSMB_CUDA(cudaEventSynchronize(o.done));
+                o.in_flight = false;
+            }
+        }
+        if (g_pinned_arena[dev]) MSMB_CUDA(cudaFreeHost(g_pinned_arena[dev]));
+        g_pinned_arena[dev] = nullptr;
+        size_t cap = 1 << 18;
+        while (cap < bytes) cap <<= 1;
+        MSMB_CUDA(cudaMallocHost(&g_pinned_arena[dev], cap * UM_PINNED_SLOTS));
+        for (int i = 0; i < UM_PINNED_SLOTS; ++i) {
+            g_pinned[dev][i].host = reinterpret_cast<unsigned char *>(g_pinned_arena[dev]) + cap * (size_t)i;
+            g_pinned[dev][i].bytes = cap;
+        }
+    }
     if (s.in_flight) {
         MSMB_CUDA(cudaEventSynchronize(s.done));
         s.in_flight = false;
-    }
-    if (s.bytes < bytes) {
-        if (s.host) MSMB_CUDA(cudaFreeHost(s.host));
-        s.host = nullptr;
-        s.bytes = 0;
-        size_t cap = 1 << 16;
-        while (cap < bytes) cap <<= 1;
-        MSMB_CUDA(cudaMallocHost(&s.host, cap));
-        s.bytes = cap;
     }
     if (!s.done) MSMB_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     *out = &s;
@@ -1250,7 +1265,8 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     // MN-major rolling-window operands (tica_umma_v2.cuh, "MN-major mode"): every CTA has its four feature
     // blocks and the lag fits the mirror tile
     // (MSMB200_UMMA_MN=0 keeps the K-major mode; MSMB200_UMMA_MN_STAGES = ring tiles, 4 or 5)
-    const bool v3 = v2 && (D == UM_D || D == UM_F) && lag <= UM_KT && env_int("MSMB200_UMMA_MN", 1) != 0;
+    const bool v3 = v2 && (D == UM_D || D == UM_F || (D == 64 && env_int("MSMB200_UMMA_MN64", 1) != 0)) &&
+                    lag <= UM_KT && env_int("MSMB200_UMMA_MN", 1) != 0;
     int v3_stages = env_int("MSMB200_UMMA_MN_STAGES", 5);
     v3_stages = v3_stages < 4 ? 4 : (v3_stages > 5 ? 5 : v3_stages);
     const size_t n_items = v2 ? tica_simt_items(seq_ptrs, seq_rows, n_seq_in, lag, nullptr, nullptr, nullptr) : 0;

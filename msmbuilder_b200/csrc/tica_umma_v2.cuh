@@ -32,7 +32,7 @@
 //    independent CTAs): narrow inputs no longer pay 256-wide tiles (config 2, 10M x 64).
 //  * Bit-reproducible like v1: every address has one writer, all sums are taken in a fixed order.
 //
-// MN-major mode (P.mn, all four feature blocks per CTA, lag <= 32; profiles/r2z_probe7_mn_major_sw128.log).
+// MN-major mode (P.mn; D = 256, 128 or 64, lag <= 32; profiles/r2z_probe7_mn_major_sw128.log).
 // The K-major chunks above (8 frames of one feature per 16 bytes) cannot serve both operands: the lagged
 // operand's chunks start `lag` frames later, so every frame is TMA-loaded and converted twice and the
 // gather that builds a chunk costs eight 4-byte shared loads.  tcgen05 also takes MN-major fp16 operands
@@ -629,8 +629,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         // swizzled raw rows and the 16-byte stores into the swizzled windows are both bank-conflict free.
         float mn_sh[8], mn_sl[8];                        // column sums of this thread's 8 features (float pairs)
         float mn_sc[8];
+        // (64 features per CTA -- D = 64, two feature blocks: no fbh, rp = 0..15 covers the 32 rows, ONE row per thread)
         const int mct = tid - V2_CONV_TID0;
-        const int m_cq = mct & 3, m_fbl = (mct >> 2) & 1, m_swp = (mct >> 3) & 1, m_fbh = (mct >> 4) & 1, m_rp = mct >> 5;
+        const bool m_narrow = nfb == 2;
+        const int m_cq = mct & 3, m_fbl = (mct >> 2) & 1, m_swp = (mct >> 3) & 1;
+        const int m_fbh = m_narrow ? 0 : (mct >> 4) & 1, m_rp = m_narrow ? (mct >> 4) : (mct >> 5);
+        const int m_nu = m_narrow ? 1 : 2;                         // rows per thread and tile
         const int m_f0 = 32 * (2 * m_fbh + m_fbl) + 8 * m_cq;     // first feature (inside the CTA)
         if constexpr (mn) {
             const int row_lo = 2 * m_rp + (m_fbl ^ m_swp);
@@ -677,11 +681,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
                 float4 va[2], vb[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    va[u] = lds_v4f(rawst + src_a + (uint32_t)u * (16 * 128));
-                    vb[u] = lds_v4f(rawst + src_b + (uint32_t)u * (16 * 128));
+                    if (u < m_nu) {
+                        va[u] = lds_v4f(rawst + src_a + (uint32_t)u * (16 * 128));
+                        vb[u] = lds_v4f(rawst + src_b + (uint32_t)u * (16 * 128));
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
+                    if (u >= m_nu) break;                             // CTA uniform
                     const bool live = row_lo + 16 * u < valid;        // rows behind the sequence: zeros
                     uint64_t as2[4];
                     as2[0] = f2_fma(f2_pack(va[u].x, va[u].y), sc2[0], nsh2[0]);
@@ -871,8 +878,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
         // memory in a fixed order (the raw ring is idle: every TMA load has landed and been
         // converted); the doubles appear only here, after this CTA's last tile
         if constexpr (mn) {
-            // 16 threads (swp, rp) share a feature: fixed order through shared memory
-            double *s_sum = reinterpret_cast<double *>(raw_ring);        // [16][UM_F]
+            // 16 threads (swp, rp) share a feature (32 with 64 features per CTA): fixed order through shared memory
+            double *s_sum = reinterpret_cast<double *>(raw_ring);        // [16 or 32][UM_F]
             const int contrib = m_swp + 2 * m_rp;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -881,7 +888,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tica_umma_v2_kernel(const V2Par
             const int f = tid - V2_CONV_TID0;
             if (f < UM_F) {
                 double tot = 0.0;
-                for (int c = 0; c < 16; ++c) tot += s_sum[c * UM_F + f];
+                if (f < d_local)
+                    for (int c = 0; c < (m_narrow ? 32 : 16); ++c) tot += s_sum[c * UM_F + f];
                 P.sums[(size_t)group * UM_D + UM_F * cta_rank + f] = tot;
             }
         } else {
