@@ -1265,7 +1265,7 @@ int tica_umma_accumulate(const void *const *seq_ptrs, const int64_t *seq_rows, i
     // MN-major rolling-window operands (tica_umma_v2.cuh, "MN-major mode"): every CTA has its four feature
     // blocks and the lag fits the mirror tile
     // (MSMB200_UMMA_MN=0 keeps the K-major mode; MSMB200_UMMA_MN_STAGES = ring tiles, 4 or 5)
-    const bool v3 = v2 && (D == UM_D || D == UM_F || (D == 64 && env_int("MSMB200_UMMA_MN64", 1) != 0)) &&
+    const bool v3 = v2 && (D == UM_D || D == UM_F || (D == 64 && env_int("MSMB200_UMMA_MN64", 0) != 0)) &&
                     lag <= UM_KT && env_int("MSMB200_UMMA_MN", 1) != 0;
     int v3_stages = env_int("MSMB200_UMMA_MN_STAGES", 5);
     v3_stages = v3_stages < 4 ? 4 : (v3_stages > 5 ? 5 : v3_stages);
