@@ -389,6 +389,11 @@ kcenters_fused_pass_kernel(const float *__restrict__ X, long long n, int d, long
             float s[V];
 #pragma unroll
             for (int jj = 0; jj < JB; ++jj) {
+                if (j0 + jj >= J) {                              // padding centre of the last chunk (warp uniform):
+#pragma unroll
+                    for (int f = 0; f < R; ++f) s[f * JB + jj] = 0.f;   // its slots are never looked at
+                    continue;
+                }
                 float4 c[ITERS];
 #pragma unroll
                 for (int i = 0; i < ITERS; ++i) c[i] = s_c[(j0 + jj) * d4 + lane_in_group + i * G];
