@@ -936,7 +936,9 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
                        double *__restrict__ es)
 {
     constexpr int D = UM_D;       // padded width of every scratch array; Dr <= D real features
-    __shared__ double sx[D], sy[D];
+    constexpr int RB = 4;         // rows staged per barrier pair (one row per pair made the kernel 0.7 ms of
+                                  // pure barrier latency at 500 sequences; the sums keep their row order)
+    __shared__ double sx[RB][D], sy[D];
     const int tid = threadIdx.x;
     const int i0 = blockIdx.y * 16;
     double acc[4][16];
@@ -955,37 +957,43 @@ tica_umma_edges_kernel(const EdgeSeq *__restrict__ seqs, int n_seq, long long ld
         const long long n = seqs[s].n;
         const long long Pn = n - lag;
         const long long R = Pn;       // every pair index goes through the tensor cores (TMA zero-fills the tail)
-        // row list: remainder pairs, head rows, tail rows
-        const int n_rem = (int)(Pn - R);
-        const long long total = n_rem + 2LL * lag;
-        for (long long e = 0; e < total; ++e) {
-            int kind;
-            long long t;
-            if (e < n_rem) { kind = 0; t = R + e; }
-            else if (e < n_rem + lag) { kind = 2; t = e - n_rem; }
-            else { kind = 3; t = n - lag + (e - n_rem - lag); }
+        // remainder pairs (none while R == Pn), one row at a time
+        for (long long t = R; t < Pn; ++t) {
             __syncthreads();
-            sx[tid] = tid < Dr ? (double)(X[t * ld + tid] - shift[tid]) : 0.0;
-            if (kind == 0) sy[tid] = tid < Dr ? (double)(X[(t + lag) * ld + tid] - shift[tid]) : 0.0;
+            sx[0][tid] = tid < Dr ? (double)(X[t * ld + tid] - shift[tid]) : 0.0;
+            sy[tid] = tid < Dr ? (double)(X[(t + lag) * ld + tid] - shift[tid]) : 0.0;
             __syncthreads();
-            const double xj = sx[tid];
-            if (kind == 0) {
-                const double yj = sy[tid];
+            const double xj = sx[0][tid], yj = sy[tid];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const double xi = sx[i0 + u];
-                    acc[0][u] = fma(xi, yj, acc[0][u]);
-                    acc[1][u] = fma(xi, xj, acc[1][u]);
+            for (int u = 0; u < 16; ++u) {
+                const double xi = sx[0][i0 + u];
+                acc[0][u] = fma(xi, yj, acc[0][u]);
+                acc[1][u] = fma(xi, xj, acc[1][u]);
+            }
+            s0 += xj;
+        }
+        // head rows (t < lag), then tail rows (t >= n - lag): RB rows per barrier pair, folded in row order
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const long long t0 = part ? n - lag : 0;
+            for (int r0 = 0; r0 < lag; r0 += RB) {
+                const int nb = lag - r0 < RB ? lag - r0 : RB;
+                __syncthreads();
+                for (int b = 0; b < nb; ++b)
+                    sx[b][tid] = tid < Dr ? (double)(X[(t0 + r0 + b) * ld + tid] - shift[tid]) : 0.0;
+                __syncthreads();
+                for (int b = 0; b < nb; ++b) {
+                    const double xj = sx[b][tid];
+                    if (part == 0) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) acc[2][u] = fma(sx[b][i0 + u], xj, acc[2][u]);
+                        shead += xj;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) acc[3][u] = fma(sx[b][i0 + u], xj, acc[3][u]);
+                        stail += xj;
+                    }
                 }
-                s0 += xj;
-            } else if (kind == 2) {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) acc[2][u] = fma(sx[i0 + u], xj, acc[2][u]);
-                shead += xj;
-            } else {
-#pragma unroll
-                for (int u = 0; u < 16; ++u) acc[3][u] = fma(sx[i0 + u], xj, acc[3][u]);
-                stail += xj;
             }
         }
     }
