@@ -584,6 +584,11 @@ def run_ours(args):
                 roof_k2["traffic"] = tr.get("kcenters_pass_fast_kernel")
             if args.engine in ("auto", "umma_3xf16"):
                 roof_k1["traffic"] = tr.get("tica_umma_v2_kernel", tr.get("tica_umma_kernel_f16"))
+                # what the committed ncu capture of the same launch says (not measured in this run)
+                if "tica_umma_v2_kernel_ncu" in tr:
+                    roof_k1["ncu_capture"] = tr["tica_umma_v2_kernel_ncu"]
+            if pass_ms and not args.no_lookahead and "kcenters_lookahead_passes_ncu" in tr:
+                roof_k2["ncu_capture"] = tr["kcenters_lookahead_passes_ncu"]
             roof_k1["traffic_source"] = roof_k2["traffic_source"] = tr["source"]
     except (OSError, KeyError, ValueError):
         pass
