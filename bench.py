@@ -46,6 +46,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "assign"],
+                    help="pipeline: tICA.fit + KCenters.fit on 50M x 256 (the headline metric); assign: one "
+                         "libdistance.assign_nearest pass, BASELINE.json config 3 (10M x 16 projections -> k = 500)")
+    ap.add_argument("--assign-frames", type=int, default=10_000_000)
+    ap.add_argument("--assign-features", type=int, default=16)
+    ap.add_argument("--assign-k", type=int, default=500)
     ap.add_argument("--frames", type=int, default=50_000_000)
     ap.add_argument("--features", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=100_000)
@@ -811,13 +817,182 @@ def emit(line):
         sys.stdout.flush()
 
 
+# ----------------------------------------------------------------------------- second workload: assign_nearest
+def assign_config(args, ws):
+    return {"workload": "libdistance.assign_nearest(X, centres, 'euclidean') on %d x %d float32 projections, k = %d "
+                        "(BASELINE.json config 3: the MiniBatchKMeans / KCenters.predict label pass)"
+                        % (args.assign_frames, args.assign_features, args.assign_k),
+            "frames": args.assign_frames, "features": args.assign_features, "k": args.assign_k,
+            "sharding": "frames/%d, centres replicated, no collective" % ws,
+            "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2" % (
+                args.assign_frames / ws * args.assign_features * 4 / 1e9)}
+
+
+def assign_data_numpy(n, d, k, seed=3):
+    rs = np.random.RandomState(seed)
+    X = (rs.standard_normal((n, d)) * np.linspace(3, 0.3, d)).astype(np.float32)
+    C = X[rs.randint(0, n, k)].copy()
+    return X, C
+
+
+def run_assign_reference(args):
+    """--impl reference --workload assign: the reference's own assign.hpp (oracle/_ref) on a bounded sample."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import libdistance_oracle as lo
+    n = min(args.assign_frames, 400_000)
+    X, C = assign_data_numpy(n, args.assign_features, args.assign_k)
+    for _ in range(max(0, min(args.warmup, 1))):
+        lo.assign_nearest(X[:20_000], C, "euclidean")
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        lo.assign_nearest(X, C, "euclidean")
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    value = n / (ms / 1e3)
+    kind = "reference" if lo.have_reference() else "port"
+    emit({"impl": "reference", "metric": "frames/sec assign_nearest", "value": value, "unit": "frames/s",
+          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": dict(assign_config(args, 1), frames_timed_per_step=n),
+          "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": kind,
+                           "sample": "%d of the frames, the reference's single-threaded libdistance C++" % n},
+          "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
+
+
+def run_assign(args):
+    import torch
+    import torch.distributed as dist
+    from msmbuilder_b200 import _lib, _kernels as K, libdistance as ld
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.require_gpu()
+    lib = _lib.load()
+    n_total, d, k = args.assign_frames, args.assign_features, args.assign_k
+    n = n_total // ws                                      # this rank's frames (the tail of an uneven split is dropped)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    Xall = torch.randn((n_total, d), generator=g, device="cuda") * torch.linspace(3, 0.3, d, device="cuda")
+    C = Xall[torch.randint(0, n_total, (k,), generator=g, device="cuda")].contiguous()
+    X = Xall[rank * n:(rank + 1) * n].clone()
+    del Xall
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    import gc
+    gc.collect()
+    gc.disable()
+    out = None
+    for _ in range(args.warmup):
+        out = K.assign_nearest(X, C, "euclidean")
+    barrier()
+    launches0 = lib.msmb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.mark_begin()
+    e0.record()
+    for _ in range(args.steps):
+        out = K.assign_nearest(X, C, "euclidean")
+    e1.record()
+    barrier()
+    gc.enable()
+    sampler.mark_end()
+    launches = int(lib.msmb200_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if ws > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms = float(total_ms.item()) / args.steps
+    value = n * ws / (ms / 1e3)
+    labels = out[0]
+
+    # parity on the timed frames: the float64 scan of a prefix
+    m = min(n, 2_000_000)
+    os.environ["MSMB200_ASSIGN_EXACT"] = "1"
+    try:
+        exact, _, _ = K.assign_nearest(X[:m], C, "euclidean")
+    finally:
+        os.environ.pop("MSMB200_ASSIGN_EXACT", None)
+    labels_ok = bool((labels[:m] == exact).all())
+
+    # e2e: the public libdistance call on pageable NumPy arrays (H2D of the frames, D2H of the labels)
+    e2e = None
+    if not args.no_e2e:
+        Xh, Ch = X.cpu().numpy(), C.cpu().numpy()
+        ld.assign_nearest(Xh, Ch, "euclidean")
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ld.assign_nearest(Xh, Ch, "euclidean")
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+        if ws > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * ws / float(dt.item()), "unit": "frames/s", "frames": n * ws,
+               "h2d_bytes_per_step": (n * d * 4 + k * d * 4) * ws, "d2h_bytes_per_step": (n * 8 + 8) * ws,
+               "host_memory": "pageable NumPy arrays", "api": "msmbuilder_b200.libdistance.assign_nearest(X, Y, 'euclidean')"}
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    tf = 2.0 * n * k * d / (ms / 1e3) / 1e12
+    hbm = n * d * 4 / (ms / 1e3) / 1e9
+    engine = {0: "tcgen05 filter, centres resident in shared memory", 1: "tcgen05 filter, streamed centre chunks",
+              2: "SIMT float32 filter"}[int(lib.msmb200_assign_engine(n, k, d))]
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import libdistance_oracle as lo
+        ns = min(n, 400_000)
+        Xs, Cs = X[:ns].cpu().numpy(), C.cpu().numpy()
+        t0 = time.perf_counter()
+        ref_labels, _ = lo.assign_nearest(Xs, Cs, "euclidean")
+        sec = time.perf_counter() - t0
+        cpu = {"value": ns / sec, "unit": "frames/s", "cores": 1,
+               "kind": "reference" if lo.have_reference() else "port",
+               "sample": "%d of the same frames through the reference's single-threaded libdistance C++ (%.2f s)" % (ns, sec),
+               "labels_equal_gpu": bool((labels[:ns].cpu().numpy() == ref_labels).all())}
+    emit({"metric": "frames/sec assign_nearest", "value": value, "unit": "frames/s", "n_gpus": ws,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+          "scaling": "strong", "vs_baseline": None,
+          "dtype": "f32 in; fp16 h+l split tensor-core inner products (filter), f64 re-scan of the ambiguous frames and f64 winning distance",
+          "data": "synthetic", "config": assign_config(args, ws), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+          "roofline": {"kernel": "assign_umma_kernel + assign_refine / assign_mindist", "bound": "hbm",
+                       "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
+                       "traffic": None, "algorithmic_bytes_per_launch": float(n * d * 4),
+                       "algorithmic_tflops": tf, "engine": engine,
+                       "note": "4 d bytes per frame; at k = 500, d = 16 the pass is bound by the epilogue's k compares "
+                               "per frame (tensor pipe ~10 % active, profiles/r2o_ncu_assign_umma_config3.txt), not by HBM"},
+          "check": {"labels_equal_float64_scan": labels_ok, "frames_checked": m},
+          "cpu_baseline": cpu})
+
+
 def main():
     global _REAL_STDOUT
     args = parse()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)                      # stray prints -> stderr
-    if args.impl == "reference":
+    if args.workload == "assign":
+        if args.impl == "reference":
+            run_assign_reference(args)
+        else:
+            run_assign(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
