@@ -70,3 +70,19 @@ while True:
     out = s.stop()
     assert out["samples"] >= 1 and out["window"].startswith("warm-up")
     assert bench.ClockSampler(0).stop()["samples"] == 0      # never started: empty, no exception
+
+
+def test_reference_arm_of_the_assign_workload_runs_on_cpu():
+    # bench.py --impl reference --workload assign: the reference's assign.hpp (oracle/_ref, or the port) on a
+    # bounded sample; one JSON line with the keys the driver reads
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "assign", "--steps", "1", "--warmup", "0", "--assign-frames", "20000"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "frames/sec assign_nearest"
+    assert line["value"] > 0 and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
