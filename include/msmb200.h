@@ -157,10 +157,12 @@ int msmb200_candidate_from_row(const void *X, int64_t row, int d, int64_t ld,
  *    multi_pass  applies the J pending centres (labels label0 .. label0+J-1) in
  *                ONE streaming read -- float32 filter, reference arithmetic for
  *                every (frame, centre) pair that could lower the frame's minimum
- *                -- and records each lane's largest / second largest minimum;
+ *                -- and records each lane's three largest minima (the two
+ *                largest with their rows);
  *    select      turns those into this shard's candidate set: up to t_cap
- *                frames (value, global row, the row itself) and the bound tau on
- *                every frame that is NOT a candidate;
+ *                frames (value, global row, the row itself; a lane contributes
+ *                its two largest) and the bound tau on every frame that is NOT
+ *                a candidate (largest third-best of a lane, or the cut);
  *    chain       replays the reference's arg-max / update loop on the candidate
  *                sets of all shards (all-gathered by the caller) and emits the
  *                centres it can certify (value > tau; the first pick is the true
